@@ -1,0 +1,213 @@
+// extern "C" surface of lib3dahv_b200 (see include/ahv_b200.h for the contract
+// and the reference interface each entry replaces).
+#include "ahv_common.cuh"
+
+using namespace ahv;
+
+namespace {
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// The library contains sm_100a code only; refuse anything else loudly.
+int check_device() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return AHV_ECUDA;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return AHV_ECUDA;
+  return major == 10 ? AHV_OK : AHV_ENOTSUP;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+AHV_API int ahv_version(void) { return AHV_VERSION; }
+
+AHV_API const char* ahv_status_string(int status) {
+  switch (status) {
+    case AHV_OK: return "ok";
+    case AHV_EINVAL: return "invalid argument (shape, null or misaligned pointer, enum)";
+    case AHV_ENOTSUP: return "unsupported device: lib3dahv_b200 holds sm_100a code only, no fallback";
+    case AHV_ECUDA: return "CUDA runtime error (see cudaGetLastError)";
+    case AHV_EWORKSPACE: return "workspace too small (see ahv_workspace_bytes)";
+    default: return "unknown status";
+  }
+}
+
+AHV_API int ahv_so3_from_normals(const float* normals, float* R, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!normals || !R)) || !aligned16(normals)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_so3_from_normals(normals, R, n, (cudaStream_t)stream);
+}
+
+AHV_API int ahv_so3_sample(uint64_t seed, int64_t first_index, float* R, int64_t n, void* stream) {
+  if (n < 0 || first_index < 0 || (n > 0 && !R)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_so3_sample(seed, first_index, R, n, (cudaStream_t)stream);
+}
+
+AHV_API int ahv_rotate_volume(const float* vol, int vol_per_rotation, const float* R, const float* base,
+                      float* out, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!vol || !R || !base || !out))) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_rotate_volume(vol, vol_per_rotation != 0, R, base, out, n, (cudaStream_t)stream);
+}
+
+AHV_API int ahv_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
+                     float* feat, int64_t m, void* stream) {
+  if (m < 0 || (m > 0 && (!vol || !W1 || !W2 || !b2 || !feat))) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_forward_3d2d(vol, W1, W2, b2, feat, m, (cudaStream_t)stream);
+}
+
+// workspace = [scores B*N fp32 | top-k partial keys | tensor-core path scratch]
+AHV_API size_t ahv_workspace_bytes(int B, int64_t N, int k) {
+  if (B < 0 || N < 0) return 0;
+  return align_up((size_t)B * (size_t)N * sizeof(float), 256) +
+         align_up(topk_workspace_bytes(B, N, k), 256) + align_up(score_tc_workspace_bytes(B, N), 256);
+}
+
+AHV_API int ahv_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* topk_val,
+             int64_t* topk_idx, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || N < 0 || N > 0x7fffffffLL || k < 1 || k > kMaxK) return AHV_EINVAL;
+  if (B > 0 && (!scores || !topk_val || !topk_idx || !workspace)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_topk(scores, B, N, k, idx_offset, topk_val, topk_idx, workspace, workspace_bytes,
+                     (cudaStream_t)stream);
+}
+
+AHV_API int ahv_topk_merge(const float* vals, const int64_t* idx, int parts, int B, int k, float* out_val,
+                   int64_t* out_idx, void* stream) {
+  if (parts < 1 || B < 0 || k < 1 || k > kMaxK) return AHV_EINVAL;
+  if (B > 0 && (!vals || !idx || !out_val || !out_idx)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_topk_merge(vals, idx, parts, B, k, out_val, out_idx, (cudaStream_t)stream);
+}
+
+AHV_API int ahv_gather_rotations(const float* R, int r_per_pair, const int64_t* idx, int64_t idx_offset,
+                         int B, int64_t N, int k, float* R_out, void* stream) {
+  if (B < 0 || N < 0 || k < 1) return AHV_EINVAL;
+  if (B > 0 && (!R || !idx || !R_out)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_gather_rotations(R, r_per_pair != 0, idx, idx_offset, B, N, k, R_out,
+                                 (cudaStream_t)stream);
+}
+
+AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
+              int r_per_pair, const float* W1, const float* W2, const float* b2, const float* base,
+              float* scores, float* topk_val, int64_t* topk_idx, int k, int64_t idx_offset, int B,
+              int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || N < 0 || N > 0x7fffffffLL) return AHV_EINVAL;
+  if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
+  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32) return AHV_EINVAL;
+  if (k < 0 || k > kMaxK) return AHV_EINVAL;
+  if (k > 0 && (!topk_val || !topk_idx)) return AHV_EINVAL;
+  if ((int64_t)B * N > 0 && (!vol_src || !tgt_feat || !R || !W1 || !W2 || !b2 || !base))
+    return AHV_EINVAL;
+  if (!aligned16(vol_src) || !aligned16(tgt_feat) || !aligned16(R) || !aligned16(W1) ||
+      !aligned16(W2) || !aligned16(workspace))
+    return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  if ((int64_t)B * N == 0) return AHV_OK;
+
+  const size_t need_scores = scores ? 0 : align_up((size_t)B * (size_t)N * sizeof(float), 256);
+  const size_t need_topk = k > 0 ? align_up(topk_workspace_bytes(B, N, k), 256) : 0;
+  const size_t need_tc = math_mode == AHV_MATH_TC ? align_up(score_tc_workspace_bytes(B, N), 256) : 0;
+  if (need_scores + need_topk + need_tc > 0 && !workspace) return AHV_EWORKSPACE;
+  if (workspace_bytes < need_scores + need_topk + need_tc) return AHV_EWORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  float* sc = scores ? scores : reinterpret_cast<float*>(ws);
+  void* ws_topk = ws + need_scores;
+  void* ws_tc = ws + need_scores + need_topk;
+
+  cudaStream_t s = (cudaStream_t)stream;
+  if (math_mode == AHV_MATH_FP32)
+    st = launch_score_fp32(vol_src, vol_dtype, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, sc, B,
+                           N, s);
+  else
+    st = launch_score_tc(vol_src, vol_dtype, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, sc, B, N,
+                         ws_tc, need_tc, s);
+  if (st != AHV_OK) return st;
+  if (k > 0) st = launch_topk(sc, B, N, k, idx_offset, topk_val, topk_idx, ws_topk, need_topk, s);
+  return st;
+}
+
+AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_host, const float* R_host,
+                     int r_per_pair, const float* W1_host, const float* W2_host,
+                     const float* b2_host, const float* base_host, float* scores_host,
+                     float* topk_val_host, int64_t* topk_idx_host, float* R_best_host, int k, int B,
+                     int64_t N, int math_mode, void* stream) {
+  if (B < 1 || N < 1 || k < 1 || k > kMaxK) return AHV_EINVAL;
+  if (!vol_src_host || !vol_tgt_host || !R_host || !W1_host || !W2_host || !b2_host || !base_host)
+    return AHV_EINVAL;
+  if (!topk_val_host || !topk_idx_host) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t vol_b = (size_t)B * kC * kVox * sizeof(float);
+  const size_t r_b = (size_t)(r_per_pair ? B : 1) * N * 9 * sizeof(float);
+  const size_t feat_b = (size_t)B * kO * kP * sizeof(float);
+  const size_t w_b = (size_t)(kO * kK + kO * kO + kO + 8) * sizeof(float);
+  const size_t out_b = (size_t)B * k * (sizeof(float) + sizeof(int64_t) + 9 * sizeof(float));
+  const size_t ws_b = ahv_workspace_bytes(B, N, k);
+  const size_t total = align_up(vol_b, 256) * 2 + align_up(r_b, 256) + align_up(feat_b, 256) +
+                       align_up(w_b, 256) + align_up(out_b, 256) + ws_b;
+  unsigned char* d = nullptr;
+  AHV_CUDA_OK(cudaMallocAsync((void**)&d, total, s));
+  unsigned char* p = d;
+  auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 256); return r; };
+  float* d_src = (float*)take(vol_b);
+  float* d_tgt = (float*)take(vol_b);
+  float* d_R = (float*)take(r_b);
+  float* d_feat = (float*)take(feat_b);
+  float* d_w = (float*)take(w_b);
+  unsigned char* d_out = take(out_b);
+  void* d_ws = p;
+  float* d_W1 = d_w; float* d_W2 = d_W1 + kO * kK; float* d_b2 = d_W2 + kO * kO; float* d_base = d_b2 + kO;
+  // d_out: [idx int64 B*k | val fp32 B*k | R_best fp32 B*k*9]
+  int64_t* d_idx = (int64_t*)d_out;
+  float* d_val = (float*)(d_out + (size_t)B * k * sizeof(int64_t));
+  float* d_Rb = d_val + (size_t)B * k;
+  st = AHV_ECUDA;
+  do {
+    if (cudaMemcpyAsync(d_src, vol_src_host, vol_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_tgt, vol_tgt_host, vol_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_R, R_host, r_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_W1, W1_host, kO * kK * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_W2, W2_host, kO * kO * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_b2, b2_host, kO * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_base, base_host, 8 * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    st = launch_forward_3d2d(d_tgt, d_W1, d_W2, d_b2, d_feat, B, s);
+    if (st != AHV_OK) break;
+    st = ahv_score(d_src, AHV_VOL_F32, d_feat, d_R, r_per_pair, d_W1, d_W2, d_b2, d_base, nullptr,
+                   d_val, d_idx, k, 0, B, N, math_mode, d_ws, ws_b, stream);
+    if (st != AHV_OK) break;
+    st = launch_gather_rotations(d_R, r_per_pair != 0, d_idx, 0, B, N, k, d_Rb, s);
+    if (st != AHV_OK) break;
+    st = AHV_ECUDA;
+    if (scores_host &&
+        cudaMemcpyAsync(scores_host, d_ws, (size_t)B * N * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      break;
+    if (cudaMemcpyAsync(topk_idx_host, d_idx, (size_t)B * k * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(topk_val_host, d_val, (size_t)B * k * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) break;
+    if (R_best_host &&
+        cudaMemcpyAsync(R_best_host, d_Rb, (size_t)B * k * 36, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      break;
+    st = AHV_OK;
+  } while (0);
+  cudaFreeAsync(d, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess && st == AHV_OK) st = AHV_ECUDA;
+  return st;
+}
+
+}  // extern "C"

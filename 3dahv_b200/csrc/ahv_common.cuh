@@ -1,0 +1,92 @@
+// Shared constants and small device helpers for lib3dahv_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ahv_b200.h"
+
+namespace ahv {
+
+constexpr int kC = 16;      // volume channels            modules/modules.py:64
+constexpr int kS = 8;       // D = H = W                  modules/modules.py:97-100
+constexpr int kVox = 512;   // voxel samples per hypothesis
+constexpr int kK = 384;     // tri-plane channels          modules/modules.py:67
+constexpr int kO = 32;      // head output channels        modules/model.py:34
+constexpr int kP = 64;      // positions of the folded 8x8 plane
+constexpr int kMaxK = 32;   // largest supported top-k
+
+// Source volume staged in shared memory with a one-voxel zero halo, channel
+// innermost: line L = ((z+1)*10 + (y+1))*10 + (x+1), 16 fp32 (64 B) per line.
+// Out-of-range taps of padding_mode='zeros' (utils.py:129) then read zeros and
+// need no per-tap bounds test.
+constexpr int kHalo = 10;
+constexpr int kLines = kHalo * kHalo * kHalo;  // 1000
+constexpr int kVolSmemBytes = kLines * kC * 4; // 64000
+
+#define AHV_CUDA_OK(expr)                          \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return AHV_ECUDA;       \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sample position of output voxel (x,y,z base coordinates) under rotation R
+// (F.affine_grid, utils.py:126), un-normalised as grid_sample does with
+// align_corners=False: i = ((g+1)*8-1)/2.  ((g+1)*8 is exact, so one FFMA
+// (g+1)*4-0.5 reproduces ATen's two-step rounding bit for bit.)
+struct Tap {
+  int line;          // halo line index of the (x0,y0,z0) corner
+  float fx, fy, fz;  // fractional parts
+};
+
+__device__ __forceinline__ float unnorm(float g) { return fmaf(__fadd_rn(g, 1.0f), 4.0f, -0.5f); }
+
+__device__ __forceinline__ Tap make_tap(const float* R, float x, float y, float z) {
+  // grid = R @ (x, y, z); x -> W, y -> H, z -> D
+  float gx = fmaf(R[2], z, fmaf(R[1], y, R[0] * x));
+  float gy = fmaf(R[5], z, fmaf(R[4], y, R[3] * x));
+  float gz = fmaf(R[8], z, fmaf(R[7], y, R[6] * x));
+  // clamp to [-1, 8]: anything outside only ever touches the zero halo
+  float ix = fminf(fmaxf(unnorm(gx), -1.0f), 8.0f);
+  float iy = fminf(fmaxf(unnorm(gy), -1.0f), 8.0f);
+  float iz = fminf(fmaxf(unnorm(gz), -1.0f), 8.0f);
+  float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
+  Tap t;
+  t.fx = ix - x0;
+  t.fy = iy - y0;
+  t.fz = iz - z0;
+  t.line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
+  return t;
+}
+
+// Launch-side helpers implemented in the .cu files --------------------------
+int launch_so3_from_normals(const float* normals, float* R, int64_t n, cudaStream_t s);
+int launch_so3_sample(uint64_t seed, int64_t first, float* R, int64_t n, cudaStream_t s);
+int launch_rotate_volume(const float* vol, int per_rot, const float* R, const float* base,
+                         float* out, int64_t n, cudaStream_t s);
+int launch_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
+                        float* feat, int64_t m, cudaStream_t s);
+int launch_score_fp32(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
+                      int r_per_pair, const float* W1, const float* W2, const float* b2,
+                      const float* base, float* scores, int B, int64_t N, cudaStream_t s);
+int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
+                    int r_per_pair, const float* W1, const float* W2, const float* b2,
+                    const float* base, float* scores, int B, int64_t N, void* ws, size_t ws_bytes,
+                    cudaStream_t s);
+size_t score_tc_workspace_bytes(int B, int64_t N);
+int launch_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* val,
+                int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t topk_workspace_bytes(int B, int64_t N, int k);
+int launch_topk_merge(const float* vals, const int64_t* idx, int parts, int B, int k, float* out_val,
+                      int64_t* out_idx, cudaStream_t s);
+int launch_gather_rotations(const float* R, int r_per_pair, const int64_t* idx, int64_t idx_offset,
+                            int B, int64_t N, int k, float* R_out, cudaStream_t s);
+
+}  // namespace ahv

@@ -1,0 +1,204 @@
+"""Tensor-level wrappers over the C ABI: device pointers, current stream, checks.
+
+PyTorch is used only for device memory and streams; all arithmetic of the hot
+path happens inside lib3dahv_b200.so.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import MATH_FP32, MATH_TC, VOL_BF16, VOL_F32
+
+_BASE_CPU = None
+
+
+def base_coords(device=None) -> torch.Tensor:
+    """The 8 base coordinates F.affine_grid(align_corners=False) uses for size 8
+    (ATen: linspace(-1,1,8)*7/8 — not exactly (2i+1)/8-1), taken from ATen itself
+    so the kernel sees the reference's values (utils.py:126)."""
+    global _BASE_CPU
+    if _BASE_CPU is None:
+        g = F.affine_grid(torch.eye(3, 4)[None], (1, 1, 8, 8, 8), align_corners=False)
+        _BASE_CPU = g[0, 0, 0, :, 0].contiguous().clone()
+    return _BASE_CPU if device is None else _BASE_CPU.to(device)
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the 3DAHV hot path has no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def rotations_from_normals(normals: torch.Tensor) -> torch.Tensor:
+    """[n,4] normals (GPU) -> [n,3,3]; pytorch3d random_rotations arithmetic."""
+    o = _dev(normals, "normals")
+    n = o.shape[0]
+    R = torch.empty(n, 3, 3, device=o.device, dtype=torch.float32)
+    with torch.cuda.device(o.device):
+        _lib.check(_lib.lib().ahv_so3_from_normals(o.data_ptr(), R.data_ptr(), n, _stream(o)), "ahv_so3_from_normals")
+    return R
+
+
+def sample_rotations(n: int, seed: int, first_index: int = 0, device="cuda") -> torch.Tensor:
+    """Native Philox sampler: hypothesis i depends only on (seed, first_index+i)."""
+    device = torch.device(device)
+    R = torch.empty(n, 3, 3, device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().ahv_so3_sample(seed & (2**64 - 1), first_index, R.data_ptr(), n, _stream(R)), "ahv_so3_sample")
+    return R
+
+
+def rotate_volume(volume: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
+    """utils.rotate_volume (utils.py:113-131) on the GPU.  `volume` is
+    [16,8,8,8] (one volume under n rotations) or [n,16,8,8,8] (one per rotation)."""
+    R = _dev(R, "R")
+    n = R.shape[0]
+    per_rot = volume.dim() == 5
+    if per_rot and volume.shape[0] != n:
+        raise ValueError("volume batch must match the number of rotations")
+    if tuple(volume.shape[-4:]) != (16, 8, 8, 8):
+        raise ValueError("volume must be [...,16,8,8,8]")
+    v = _dev(volume, "volume")
+    out = torch.empty(n, 16, 8, 8, 8, device=v.device, dtype=torch.float32)
+    base = base_coords(v.device)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().ahv_rotate_volume(v.data_ptr(), int(per_rot), R.data_ptr(), base.data_ptr(), out.data_ptr(), n, _stream(v)), "ahv_rotate_volume")
+    return out
+
+
+def forward_3d2d(vol: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """Feature_Aligner.forward_3d2d (modules/modules.py:112-124): [m,16,8,8,8] -> [m,32,64]."""
+    v = _dev(vol, "vol")
+    if tuple(v.shape[1:]) != (16, 8, 8, 8):
+        raise ValueError("vol must be [m,16,8,8,8]")
+    W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
+    m = v.shape[0]
+    feat = torch.empty(m, 32, 64, device=v.device, dtype=torch.float32)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().ahv_forward_3d2d(v.data_ptr(), W1.data_ptr(), W2.data_ptr(), b2.data_ptr(), feat.data_ptr(), m, _stream(v)), "ahv_forward_3d2d")
+    return feat
+
+
+def workspace_bytes(B: int, N: int, k: int) -> int:
+    return int(_lib.lib().ahv_workspace_bytes(B, N, k))
+
+
+def score(vol_src, tgt_feat, R, W1, W2, b2, k: int = 1, idx_offset: int = 0, math: int = MATH_TC,
+          return_scores: bool = True, workspace: torch.Tensor | None = None):
+    """The fused hot path (modules/model.py:186-196).
+
+    vol_src [B,16,8,8,8] fp32|bf16, tgt_feat [B,32,64], R [N,3,3] or [B,N,3,3].
+    Returns (scores [B,N] or None, topk_val [B,k], topk_idx [B,k] int64)."""
+    if vol_src.dtype == torch.bfloat16:
+        vs, vdt = _dev(vol_src, "vol_src", torch.bfloat16), VOL_BF16
+    else:
+        vs, vdt = _dev(vol_src, "vol_src"), VOL_F32
+    B = vs.shape[0]
+    if tuple(vs.shape[1:]) != (16, 8, 8, 8):
+        raise ValueError("vol_src must be [B,16,8,8,8]")
+    tf = _dev(tgt_feat, "tgt_feat")
+    if tuple(tf.shape) != (B, 32, 64):
+        raise ValueError("tgt_feat must be [B,32,64]")
+    R = _dev(R, "R")
+    per_pair = R.dim() == 4
+    if per_pair and R.shape[0] != B:
+        raise ValueError("per-pair R must be [B,N,3,3]")
+    if tuple(R.shape[-2:]) != (3, 3):
+        raise ValueError("R must be [...,3,3]")
+    N = R.shape[1] if per_pair else R.shape[0]
+    if k < 0 or k > 32:
+        raise ValueError("k must be in [0,32]")
+    W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
+    dev = vs.device
+    scores = torch.empty(B, N, device=dev, dtype=torch.float32) if return_scores else None
+    kk = max(k, 1)
+    val = torch.empty(B, kk, device=dev, dtype=torch.float32)
+    idx = torch.empty(B, kk, device=dev, dtype=torch.int64)
+    need = workspace_bytes(B, N, kk)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    base = base_coords(dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().ahv_score(
+            vs.data_ptr(), vdt, tf.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(), W2.data_ptr(),
+            b2.data_ptr(), base.data_ptr(), scores.data_ptr() if scores is not None else None,
+            val.data_ptr() if k > 0 else None, idx.data_ptr() if k > 0 else None, k, idx_offset, B, N,
+            math, workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream(vs))
+    _lib.check(st, "ahv_score")
+    if k == 0:
+        return scores, None, None
+    return scores, val, idx
+
+
+def topk(scores: torch.Tensor, k: int, idx_offset: int = 0):
+    """torch.max / top-k with the reference's tie rule (lowest index wins)."""
+    s = _dev(scores, "scores")
+    B, N = s.shape
+    val = torch.empty(B, k, device=s.device, dtype=torch.float32)
+    idx = torch.empty(B, k, device=s.device, dtype=torch.int64)
+    need = workspace_bytes(B, N, k)
+    ws = torch.empty(max(need, 16), device=s.device, dtype=torch.uint8)
+    with torch.cuda.device(s.device):
+        st = _lib.lib().ahv_topk(s.data_ptr(), B, N, k, idx_offset, val.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(), _stream(s))
+    _lib.check(st, "ahv_topk")
+    return val, idx
+
+
+def topk_merge(vals: torch.Tensor, idx: torch.Tensor):
+    """Merge [parts,B,k] shard lists into [B,k] (same ordering rule)."""
+    v, i = _dev(vals, "vals"), _dev(idx, "idx", torch.int64)
+    parts, B, k = v.shape
+    out_v = torch.empty(B, k, device=v.device, dtype=torch.float32)
+    out_i = torch.empty(B, k, device=v.device, dtype=torch.int64)
+    with torch.cuda.device(v.device):
+        st = _lib.lib().ahv_topk_merge(v.data_ptr(), i.data_ptr(), parts, B, k, out_v.data_ptr(), out_i.data_ptr(), _stream(v))
+    _lib.check(st, "ahv_topk_merge")
+    return out_v, out_i
+
+
+def gather_rotations(R: torch.Tensor, idx: torch.Tensor, idx_offset: int = 0) -> torch.Tensor:
+    """sampled_R[pred_index] (modules/model.py:196): [B,k,3,3]."""
+    R, idx = _dev(R, "R"), _dev(idx, "idx", torch.int64)
+    per_pair = R.dim() == 4
+    B, k = idx.shape
+    N = R.shape[1] if per_pair else R.shape[0]
+    out = torch.empty(B, k, 3, 3, device=R.device, dtype=torch.float32)
+    with torch.cuda.device(R.device):
+        st = _lib.lib().ahv_gather_rotations(R.data_ptr(), int(per_pair), idx.data_ptr(), idx_offset, B, N, k, out.data_ptr(), _stream(R))
+    _lib.check(st, "ahv_gather_rotations")
+    return out
+
+
+def predict_host(vol_src, vol_tgt, R, W1, W2, b2, k: int = 1, math: int = MATH_TC, return_scores: bool = False,
+                 device="cuda"):
+    """ahv_predict_host: HOST tensors in, HOST results out (copies inside)."""
+    f = torch.float32
+    vs, vt = vol_src.to(f).contiguous(), vol_tgt.to(f).contiguous()
+    Rc = R.to(f).contiguous()
+    if vs.is_cuda or vt.is_cuda or Rc.is_cuda:
+        raise RuntimeError("predict_host takes host tensors")
+    W1c, W2c, b2c = W1.reshape(32, 384).to(f).contiguous().cpu(), W2.reshape(32, 32).to(f).contiguous().cpu(), b2.to(f).contiguous().cpu()
+    per_pair = Rc.dim() == 4
+    B = vs.shape[0]
+    N = Rc.shape[1] if per_pair else Rc.shape[0]
+    scores = torch.empty(B, N, dtype=f) if return_scores else None
+    val = torch.empty(B, k, dtype=f)
+    idx = torch.empty(B, k, dtype=torch.int64)
+    Rb = torch.empty(B, k, 3, 3, dtype=f)
+    base = base_coords()
+    device = torch.device(device)
+    with torch.cuda.device(device):
+        st = _lib.lib().ahv_predict_host(
+            vs.data_ptr(), vt.data_ptr(), Rc.data_ptr(), int(per_pair), W1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(),
+            base.data_ptr(), scores.data_ptr() if scores is not None else None, val.data_ptr(), idx.data_ptr(),
+            Rb.data_ptr(), k, B, N, math, torch.cuda.current_stream(device).cuda_stream)
+    _lib.check(st, "ahv_predict_host")
+    return scores, val, idx, Rb

@@ -1,0 +1,106 @@
+"""HypothesisVerifier — the fused hypothesis-and-verification step.
+
+Replaces the idiom the reference pastes at modules/model.py:131-146, :184-196,
+test_co3d.py:137-146 and test_linemod.py:43-63:
+
+    rotate_volume(vol.expand(N), R) -> forward_3d2d -> (a*b[:,None]).sum(2).mean(-1)
+    -> torch.max(dim=1) -> R[idx]
+
+with one call into lib3dahv_b200 (no rotated volume, grid or feature tensor is
+ever materialised).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from ._lib import MATH_FP32, MATH_TC
+
+DEFAULT_MATH = MATH_TC
+
+
+@dataclass
+class VerifyResult:
+    scores: torch.Tensor | None    # [B,N] pred_sim (modules/model.py:193)
+    topk_val: torch.Tensor         # [B,k]
+    topk_idx: torch.Tensor         # [B,k] int64, global hypothesis index
+    R_best: torch.Tensor           # [B,k,3,3] sampled_R[pred_index] (:196)
+
+
+class HypothesisVerifier:
+    """Holds the verification-head weights (state-dict names
+    `feature_aligner.feature_embedding_2d.{0.weight,2.weight,2.bias}`)."""
+
+    def __init__(self, W1: torch.Tensor, W2: torch.Tensor, b2: torch.Tensor, math: int | None = None):
+        self.W1 = W1.detach().reshape(32, 384).float().contiguous()
+        self.W2 = W2.detach().reshape(32, 32).float().contiguous()
+        self.b2 = b2.detach().float().contiguous()
+        self.math = DEFAULT_MATH if math is None else math
+        self._ws = None
+
+    @classmethod
+    def from_feature_aligner(cls, feature_aligner, math: int | None = None) -> "HypothesisVerifier":
+        head = feature_aligner.feature_embedding_2d
+        return cls(head[0].weight, head[2].weight, head[2].bias, math)
+
+    def to(self, device) -> "HypothesisVerifier":
+        self.W1, self.W2, self.b2 = self.W1.to(device), self.W2.to(device), self.b2.to(device)
+        return self
+
+    def _weights_on(self, device):
+        if self.W1.device != device:
+            self.to(device)
+        return self.W1, self.W2, self.b2
+
+    def target_features(self, vol_tgt: torch.Tensor) -> torch.Tensor:
+        """feature_aligner.forward_3d2d(img_feat_tgt) (modules/model.py:191)."""
+        W1, W2, b2 = self._weights_on(vol_tgt.device)
+        return ops.forward_3d2d(vol_tgt.float(), W1, W2, b2)
+
+    def _workspace(self, B, N, k, device):
+        need = ops.workspace_bytes(B, N, max(k, 1))
+        if self._ws is None or self._ws.device != device or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 16), device=device, dtype=torch.uint8)
+        return self._ws
+
+    @torch.no_grad()
+    def score(self, vol_src, vol_tgt, R, k: int = 1, return_scores: bool = True, tgt_feat=None,
+              idx_offset: int = 0, gather: bool = True) -> VerifyResult:
+        """vol_src/vol_tgt [B,16,8,8,8]; R [N,3,3] shared or [B,N,3,3] per pair."""
+        dev = vol_src.device
+        W1, W2, b2 = self._weights_on(dev)
+        if tgt_feat is None:
+            tgt_feat = self.target_features(vol_tgt)
+        per_pair = R.dim() == 4
+        N = R.shape[1] if per_pair else R.shape[0]
+        B = vol_src.shape[0]
+        if N == 0:
+            raise ValueError("empty hypothesis set")
+        k = min(k, N)
+        vs = vol_src if vol_src.dtype == torch.bfloat16 else vol_src.float()
+        scores, val, idx = ops.score(vs, tgt_feat, R, W1, W2, b2, k=k, idx_offset=idx_offset, math=self.math,
+                                     return_scores=return_scores, workspace=self._workspace(B, N, k, dev))
+        R_best = ops.gather_rotations(R, idx, idx_offset) if gather else None
+        return VerifyResult(scores, val, idx, R_best)
+
+    @torch.no_grad()
+    def predict(self, vol_src, vol_tgt, R):
+        """argmax hypothesis per pair: (R_best [B,3,3], score [B], index [B])."""
+        r = self.score(vol_src, vol_tgt, R, k=1, return_scores=False)
+        return r.R_best[:, 0], r.topk_val[:, 0], r.topk_idx[:, 0]
+
+    @torch.no_grad()
+    def refine(self, vol_src, vol_tgt, R, k: int = 32, m: int = 64, max_angle_deg: float = 5.0, seed: int = 0):
+        """Two-pass selection (BASELINE config 4; extension): score the set, keep
+        the top-k, score m local perturbations of each, return the best."""
+        from . import so3
+
+        tgt = self.target_features(vol_tgt)
+        first = self.score(vol_src, vol_tgt, R, k=k, return_scores=False, tgt_feat=tgt)
+        cand = so3.perturb_rotations(first.R_best, m, max_angle_deg, seed)      # [B,k,m,3,3]
+        B = vol_src.shape[0]
+        cand = cand.reshape(B, -1, 3, 3).contiguous()
+        second = self.score(vol_src, vol_tgt, cand, k=1, return_scores=False, tgt_feat=tgt)
+        return second.R_best[:, 0], second.topk_val[:, 0], first, cand

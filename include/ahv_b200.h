@@ -1,0 +1,141 @@
+/* lib3dahv_b200 — C ABI of the B200-native 3DAHV hypothesis-and-verification path.
+ *
+ * The reference (sailor-z/3DAHV) is pure Python/PyTorch and has no FFI of its
+ * own; the hot path is an idiom pasted at modules/model.py:131-146, :184-196,
+ * test_co3d.py:106,137-146 and test_linemod.py:43-63.  Every entry point below
+ * cites the reference code it replaces.  All pointers are DEVICE pointers to
+ * contiguous, 16-byte-aligned buffers owned by the caller unless the name ends
+ * in `_host`.  `stream` is a `cudaStream_t` passed as `void*`.  Calls are
+ * asynchronous and stream-ordered, allocate nothing, keep no global state, and
+ * are CUDA-graph capturable.  Return value: 0 on success, negative `AHV_E*`.
+ * There is NO CPU fallback: on a device that is not sm_100 the compute entry
+ * points return AHV_ENOTSUP.
+ *
+ * Fixed sizes of the path (modules/modules.py:64,97-100): volume C=16, D=H=W=8;
+ * tri-plane K=384; verification head 384->32->32; 64 positions.
+ */
+#ifndef AHV_B200_H_
+#define AHV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AHV_API __attribute__((visibility("default")))
+#else
+#define AHV_API
+#endif
+
+#define AHV_VERSION 100 /* 0.1.0 */
+
+enum {
+  AHV_OK = 0,
+  AHV_EINVAL = -1,  /* bad shape / null pointer / misaligned pointer / bad enum */
+  AHV_ENOTSUP = -2, /* device is not sm_100 (no fallback path exists) */
+  AHV_ECUDA = -3,   /* a CUDA runtime call or kernel launch failed */
+  AHV_EWORKSPACE = -4 /* workspace too small: see ahv_workspace_bytes */
+};
+
+/* volume element type of `vol_src` */
+enum { AHV_VOL_F32 = 0, AHV_VOL_BF16 = 1 };
+
+/* arithmetic of the two 1x1 convolutions inside ahv_score:
+ *   AHV_MATH_TC   fp16 operands (10-bit mantissa, TF32-equivalent) on tcgen05
+ *                 tensor cores with fp32 accumulation in TMEM — the fast path;
+ *   AHV_MATH_FP32 plain fp32 FFMA on CUDA cores — the bit-tight verification
+ *                 mode (about 1e-6 relative to the reference).
+ * Trilinear resampling, normalisation, correlation and selection are fp32 in
+ * both modes. */
+enum { AHV_MATH_TC = 0, AHV_MATH_FP32 = 1 };
+
+AHV_API int ahv_version(void);
+AHV_API const char* ahv_status_string(int status);
+
+/* pytorch3d.transforms.random_rotations arithmetic (call sites
+ * modules/model.py:102,131,184; model_co3d.py:86; test_co3d.py:106):
+ * normals [n,4] (drawn by the caller, e.g. torch's CPU generator as the
+ * reference does) -> unit quaternion with real part >= 0 -> R [n,3,3] row-major.
+ * Individually rounded IEEE fp32 ops, bit-exact with oracle/ahv_oracle.c. */
+AHV_API int ahv_so3_from_normals(const float* normals, float* R, int64_t n, void* stream);
+
+/* Native sampler (extension; the reference only has CPU i.i.d. sampling):
+ * Philox-4x32-10 counter RNG + Box-Muller normals + the same quaternion map.
+ * Hypothesis i depends only on (seed, first_index + i), so any shard of the set
+ * can be generated independently on any GPU. */
+AHV_API int ahv_so3_sample(uint64_t seed, int64_t first_index, float* R, int64_t n, void* stream);
+
+/* utils.rotate_volume (utils.py:113-131): F.affine_grid + F.grid_sample
+ * (trilinear, zeros padding, align_corners=False), materialised.
+ * vol: [16,8,8,8] when vol_per_rotation==0 (the stride-0 `expand` of
+ * modules/model.py:186) or [n,16,8,8,8] when 1 (:137).  out: [n,16,8,8,8].
+ * base: the 8 base coordinates of affine_grid for size 8. */
+AHV_API int ahv_rotate_volume(const float* vol, int vol_per_rotation, const float* R, const float* base,
+                      float* out, int64_t n, void* stream);
+
+/* Feature_Aligner.forward_3d2d (modules/modules.py:112-124): tri-plane fold,
+ * conv1x1 384->32, ReLU, conv1x1 32->32 + bias, L2 normalise over channels.
+ * vol [m,16,8,8,8] -> feat [m,32,64].  W1 [32,384], W2 [32,32], b2 [32]
+ * (state-dict feature_embedding_2d.{0.weight,2.weight,2.bias}). fp32 FFMA. */
+AHV_API int ahv_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
+                     float* feat, int64_t m, void* stream);
+
+/* Bytes of scratch ahv_score / ahv_topk need for (B pairs, N hypotheses, k). */
+AHV_API size_t ahv_workspace_bytes(int B, int64_t N, int k);
+
+/* The fused hot path, modules/model.py:186-196 (shared rotation set) and
+ * :53-56 / :137-143 (per-pair rotations):
+ *   for every pair b and hypothesis n:
+ *     scores[b,n] = mean_p < normalize(head(rotate(vol_src[b], R[n]))) , tgt_feat[b] >
+ *   then per pair the k best (score desc, ties -> lowest index).
+ * vol_src  [B,16,8,8,8] fp32 or bf16 (vol_dtype)
+ * tgt_feat [B,32,64] fp32 = ahv_forward_3d2d(vol_tgt)
+ * R        [N,3,3] (r_per_pair==0) or [B,N,3,3] (r_per_pair==1)
+ * scores   [B,N] or NULL (then they live only in the workspace)
+ * topk_val [B,k], topk_idx [B,k] int64 (global index = local + idx_offset) or
+ *          both NULL with k==0 to skip selection.
+ * 1 <= k <= 32. */
+AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
+              int r_per_pair, const float* W1, const float* W2, const float* b2, const float* base,
+              float* scores, float* topk_val, int64_t* topk_idx, int k, int64_t idx_offset, int B,
+              int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.max / top-k over an existing score matrix (modules/model.py:195). */
+AHV_API int ahv_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* topk_val,
+             int64_t* topk_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge `parts` per-shard top-k lists (layout [parts,B,k], e.g. the result of
+ * an NCCL all-gather over hypothesis shards) into one [B,k] list with the same
+ * ordering rule, so every rank obtains bit-identical results. */
+AHV_API int ahv_topk_merge(const float* vals, const int64_t* idx, int parts, int B, int k, float* out_val,
+                   int64_t* out_idx, void* stream);
+
+/* sampled_R[pred_index] (modules/model.py:196): R_out[b,j] = R[idx[b,j]-idx_offset]. */
+AHV_API int ahv_gather_rotations(const float* R, int r_per_pair, const int64_t* idx, int64_t idx_offset,
+                         int B, int64_t N, int k, float* R_out, void* stream);
+
+/* Convenience entry taking HOST buffers (pageable or pinned): copies the
+ * inputs to the device, computes the target features, runs ahv_score and
+ * copies the selection back; synchronises `stream` before returning.  This is
+ * the call a non-PyTorch host (ctypes / cgo / JNI) would bind. vol_src_host and
+ * vol_tgt_host [B,16,8,8,8] fp32; R_host as R above; outputs as above (scores
+ * may be NULL).  Allocates and frees its own device scratch. */
+AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_host, const float* R_host,
+                     int r_per_pair, const float* W1_host, const float* W2_host,
+                     const float* b2_host, const float* base_host, float* scores_host,
+                     float* topk_val_host, int64_t* topk_idx_host, float* R_best_host, int k, int B,
+                     int64_t N, int math_mode, void* stream);
+
+/* Diagnostic: conflict-free LDS.128 streaming read on `ctas` CTAs of 1024
+ * threads (2 per SM); `*bytes` receives the shared-memory bytes read.  bench.py
+ * times it to obtain the measured shared-memory peak the gather roofline uses. */
+AHV_API int ahv_diag_smem_read(float* out, int ctas, int iters, unsigned long long* bytes,
+                               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AHV_B200_H_ */

@@ -1,0 +1,37 @@
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    out = {}
+    for name in ("weights", "shared_n3000_b3", "primitives", "per_pair"):
+        out[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    return out
+
+
+@pytest.fixture(scope="session")
+def ahv():
+    """The product package (loads lib3dahv_b200.so lazily)."""
+    return importlib.import_module("3dahv_b200")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import ahv_oracle
+
+    return ahv_oracle

@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library loads and exports exactly what include/ahv_b200.h declares."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ahv_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"AHV_API\s+[\w\s\*]+?\b(ahv_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for s in ("ahv_score", "ahv_topk", "ahv_topk_merge", "ahv_so3_from_normals", "ahv_rotate_volume",
+              "ahv_forward_3d2d", "ahv_workspace_bytes", "ahv_predict_host", "ahv_version", "ahv_status_string"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(ahv):
+    lib = ahv._lib.lib()
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+    assert set(ahv._lib.SIGNATURES) == set(declared_symbols())
+    assert lib.ahv_version() == 100
+
+
+def test_status_strings(ahv):
+    lib = ahv._lib.lib()
+    assert lib.ahv_status_string(0) == b"ok"
+    assert b"no fallback" in lib.ahv_status_string(ahv._lib.AHV_ENOTSUP)
+    with pytest.raises(RuntimeError):
+        ahv._lib.check(ahv._lib.AHV_EINVAL, "x")
+
+
+def test_argument_validation_without_gpu(ahv):
+    lib = ahv._lib.lib()
+    # invalid arguments are rejected before any device work
+    assert lib.ahv_topk(None, 1, 10, 0, 0, None, None, None, 0, None) == ahv._lib.AHV_EINVAL
+    assert lib.ahv_topk(None, 1, 10, 33, 0, None, None, None, 0, None) == ahv._lib.AHV_EINVAL
+    assert lib.ahv_score(None, 7, None, None, 0, None, None, None, None, None, None, None, 1, 0, 1, 1, 0, None, 0, None) == ahv._lib.AHV_EINVAL
+    assert lib.ahv_workspace_bytes(32, 50000, 1) >= 32 * 50000 * 4
+
+
+def test_library_has_sm100a_code_only():
+    so = os.path.join(ROOT, "3dahv_b200", "lib3dahv_b200.so")
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_ops_refuse_cpu_tensors(ahv):
+    import torch
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ahv.ops.forward_3d2d(torch.zeros(1, 16, 8, 8, 8), torch.zeros(32, 384), torch.zeros(32, 32), torch.zeros(32))
+    with pytest.raises(RuntimeError):
+        ahv.so3.random_rotations(4, device="cpu")
