@@ -1,9 +1,534 @@
-// tcgen05 tensor-core scoring path (placeholder until the kernel lands).
+// Fused hypothesis-and-verification kernel on tcgen05 tensor cores (AHV_MATH_TC).
+//
+// Replaces modules/model.py:186-193 (rotate_volume -> forward_3d2d -> correlate
+// -> mean) for every (pair, hypothesis) without materialising anything in HBM:
+// algorithmic HBM traffic is 36 B of rotation in and 4 B of score out.
+//
+// One persistent CTA per SM, 13 warps, warp-specialised:
+//   warps 0-7   GATHER   trilinear resampling (utils.py:113-131) of the source
+//                        volume held in shared memory (fp32, zero halo, channel
+//                        innermost).  4 lanes per output voxel x float4 channels,
+//                        x-taps issued in bank-parity order => conflict-free
+//                        LDS.128.  Results are rounded to fp16 and written as the
+//                        tri-plane A operand of conv1 in UMMA K-major layout:
+//                        copy YZ  [chalf][d][h][w][c8]  serves views y and z,
+//                        copy X   [chalf][d][w][h][c8]  serves view x.
+//   warp  12    MMA      one elected thread issues tcgen05.mma (kind::f16, fp32
+//                        accumulate in TMEM): conv1 = 24 x (M=64,N=32,K=16) per
+//                        hypothesis, two hypotheses interleaved in the two
+//                        16-lane halves of each TMEM sub-partition; conv2 =
+//                        2 x (M=128,N=32,K=16) per hypothesis pair.
+//   warps 8-11  EPILOGUE tcgen05.ld D1 -> ReLU -> fp16 -> smem A2 (conv2 operand);
+//                        tcgen05.ld D2 -> +bias -> L2 norm -> dot with the target
+//                        features (registers) -> mean over 64 positions -> score.
+// Pipelines (mbarrier): A-operand stages full/empty (3 hypotheses deep), TMEM
+// D1 full/empty, A2 full, D2 full (double-buffered per hypothesis pair).
+//
+// Precision: gather, normalisation and correlation are fp32; the two 1x1 convs
+// use fp16 operands (10-bit mantissa = TF32-equivalent) with fp32 accumulation.
+// The source volume is pre-scaled per pair by a power of two (exact) so fp16
+// can neither overflow nor go subnormal; the scale is undone after conv2
+// (ReLU and the bias-free conv1 are positively homogeneous).
 #include "ahv_common.cuh"
+
 namespace ahv {
-size_t score_tc_workspace_bytes(int, int64_t) { return 0; }
-int launch_score_tc(const void*, int, const float*, const float*, int, const float*, const float*,
-                    const float*, const float*, float*, int, int64_t, void*, size_t, cudaStream_t) {
-  return AHV_ENOTSUP;
+
+namespace tc {
+
+constexpr int kGatherWarps = 8;
+constexpr int kEpiWarp0 = 8;
+constexpr int kMmaWarp = 12;
+constexpr int kThreadsTC = 13 * 32;
+constexpr int kStages = 3;
+
+// ---- shared memory map (bytes) ----
+constexpr int kW1Bytes = 24 * 1024;  // 24 MMA slices x [2 chalf][4 ngroup][8][8] fp16
+constexpr int kW2Bytes = 2 * 1024;
+// A operand, copy YZ: core matrix CM(d,h,chalf) = [w][c8] (128 B)
+constexpr int kYZ_h = 128, kYZ_d = 1024, kYZ_ch = 8192 + 64;  // chalf block shifted by 64 B: STS.64 conflict-free
+constexpr int kYZBytes = kYZ_ch + 8192;                       // 16448
+// copy X: core matrix CM(d,w,chalf) = [h][c8]
+constexpr int kX_w = 144, kX_d = 8 * kX_w, kX_ch = 8 * kX_d + 64;  // 144: quads land 16 B apart mod 128
+constexpr int kXBytes = kX_ch + 8 * kX_d;                          // 18496
+constexpr int kStageBytes = ((kYZBytes + kXBytes + 127) / 128) * 128;  // 35072
+constexpr int kA2Bytes = 8192;  // [4 kc][16 rowgroup][8][8] fp16
+
+constexpr int kOffVol = 0;
+constexpr int kOffW1 = kOffVol + kVolSmemBytes;       // 64000
+constexpr int kOffW2 = kOffW1 + kW1Bytes;             // 88576
+constexpr int kOffA = kOffW2 + kW2Bytes;              // 90624
+constexpr int kOffA2 = kOffA + kStages * kStageBytes; // 195840
+constexpr int kOffBar = kOffA2 + 2 * kA2Bytes;        // 212224
+constexpr int kNumBars = 3 + 3 + 2 + 2 + 2 + 2;
+constexpr int kOffMisc = kOffBar + kNumBars * 8;      // tmem ptr, partial sums, base table
+constexpr int kSmemBytes = kOffMisc + 256;
+static_assert(kOffW1 % 128 == 0 && kOffA % 128 == 0 && kOffA2 % 128 == 0 && kOffBar % 8 == 0, "align");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+enum Bar { kFull = 0, kEmpty = 3, kD1Full = 6, kD1Empty = 8, kA2Full = 10, kD2Full = 12 };
+
+// ---- PTX wrappers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: 8-row x 16-byte core
+// matrices; LBO = byte distance between the two K chunks of one MMA, SBO = byte
+// distance between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: D=f32, A=B=f16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Work {  // contiguous range of (pair, hypothesis) items of this CTA
+  int64_t lo, hi, N;
+};
+
+// tile = two consecutive hypotheses of one pair; returns false when exhausted
+struct TileIter {
+  int64_t next, hi, N;
+  int b;
+  int64_t n0;  // first hypothesis of the tile
+  int cnt;     // 1 or 2 valid hypotheses
+  __device__ __forceinline__ TileIter(const Work& w) : next(w.lo), hi(w.hi), N(w.N), b(0), n0(0), cnt(0) {}
+  __device__ __forceinline__ bool advance() {
+    if (next >= hi) return false;
+    b = (int)(next / N);
+    n0 = next - (int64_t)b * N;
+    const int64_t seg_end = min(hi, (int64_t)(b + 1) * N);
+    cnt = (seg_end - next >= 2) ? 2 : 1;
+    next += cnt;
+    return true;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ float ld_vol(const T* p);
+template <>
+__device__ __forceinline__ float ld_vol<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_vol<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// ------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_feat,
+                const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
+                const float* __restrict__ base, const uint4* __restrict__ w_packed,
+                const float2* __restrict__ pair_scale, float* __restrict__ scores, int B, int64_t N) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Work work;
+  {
+    const int64_t total = (int64_t)B * N;
+    work.lo = total * blockIdx.x / gridDim.x;
+    work.hi = total * (blockIdx.x + 1) / gridDim.x;
+    work.N = N;
+  }
+  if (work.lo >= work.hi) return;
+
+  float* vol = reinterpret_cast<float*>(smem + kOffVol);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar0 = s_base + kOffBar;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc);
+  float* partial = reinterpret_cast<float*>(smem + kOffMisc + 16);  // [2 tilebuf][2 slot][4 warps]
+  float* sbase = reinterpret_cast<float*>(smem + kOffMisc + 96);    // 8 base coordinates
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i < kVolSmemBytes / 16; i += kThreadsTC)
+    reinterpret_cast<uint4*>(vol)[i] = make_uint4(0, 0, 0, 0);  // halo stays zero for the whole kernel
+  for (int i = threadIdx.x; i < (kW1Bytes + kW2Bytes) / 16; i += kThreadsTC)
+    reinterpret_cast<uint4*>(smem + kOffW1)[i] = w_packed[i];
+  if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar0 + (kD1Full + i) * 8, 1);
+        mbar_init(bar0 + (kD1Empty + i) * 8, 4);
+        mbar_init(bar0 + (kA2Full + i) * 8, 4);
+        mbar_init(bar0 + (kD2Full + i) * 8, 1);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 128);
+  }
+  fence_proxy_async();  // weights were written through the generic proxy, UMMA reads through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < kGatherWarps) {
+    // =========================== GATHER ===========================
+    const int j = lane & 3, q = lane >> 2, gw = warp;
+    const float bx = sbase[q], by = sbase[gw];
+    const uint32_t yz_lane = (j >> 1) * kYZ_ch + gw * kYZ_h + q * 16 + (j & 1) * 8;
+    const uint32_t x_lane = kYZBytes + (j >> 1) * kX_ch + q * kX_w + gw * 16 + (j & 1) * 8;
+    const int gtid = threadIdx.x;  // 0..255
+    TileIter it(work);
+    int cur_b = -1;
+    uint32_t h = 0;  // hypothesis counter of this CTA (stage = h % 3)
+    while (it.advance()) {
+      if (it.b != cur_b) {
+        named_bar_sync(1, kGatherWarps * 32);  // everyone is done reading the previous volume
+        const T* vg = vol_src + (size_t)it.b * kC * kVox;
+        const float sc = pair_scale[it.b].x;
+        for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
+          const int v = task & 511, jj = task >> 9;
+          const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
+          const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
+          float4 o;
+          o.x = ld_vol<T>(vg + (jj * 4 + 0) * kVox + v) * sc;
+          o.y = ld_vol<T>(vg + (jj * 4 + 1) * kVox + v) * sc;
+          o.z = ld_vol<T>(vg + (jj * 4 + 2) * kVox + v) * sc;
+          o.w = ld_vol<T>(vg + (jj * 4 + 3) * kVox + v) * sc;
+          *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
+        }
+        named_bar_sync(1, kGatherWarps * 32);
+        cur_b = it.b;
+      }
+      for (int sl = 0; sl < 2; ++sl, ++h) {
+        const int64_t n = it.n0 + (sl < it.cnt ? sl : 0);  // odd tail: recompute the valid hypothesis
+        const float* Rg = R + (r_per_pair ? ((size_t)it.b * N + n) : (size_t)n) * 9;
+        float Rr[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Rr[e] = __ldg(Rg + e);
+        const uint32_t stage = h % kStages, use = h / kStages;
+        if (use > 0) mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1);
+        unsigned char* st = smem + kOffA + stage * kStageBytes;
+        // grid = R @ (x, y, z): x and y are fixed per lane, z walks with d
+        const float pgx = fmaf(Rr[1], by, Rr[0] * bx), pgy = fmaf(Rr[4], by, Rr[3] * bx), pgz = fmaf(Rr[7], by, Rr[6] * bx);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          const float bz = sbase[d];
+          float ix = unnorm(fmaf(Rr[2], bz, pgx)), iy = unnorm(fmaf(Rr[5], bz, pgy)), iz = unnorm(fmaf(Rr[8], bz, pgz));
+          ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
+          const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
+          const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
+          const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
+          const int swap = (line ^ q) & 1;  // bank-parity order of the two x taps (see ahv_score_fp32.cu)
+          const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
+          const float* p0 = vol + (line + swap) * kC + j * 4;
+          const float* p1 = vol + (line + 1 - swap) * kC + j * 4;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+              const float wyz = (dy ? fy : 1.0f - fy) * (dz ? fz : 1.0f - fz);
+              const int off = (dz * kHalo * kHalo + dy * kHalo) * kC;
+              const float4 a = *reinterpret_cast<const float4*>(p0 + off);
+              const float4 c = *reinterpret_cast<const float4*>(p1 + off);
+              const float wa = wyz * wxa, wb = wyz * wxb;
+              acc.x = fmaf(wa, a.x, acc.x); acc.y = fmaf(wa, a.y, acc.y);
+              acc.z = fmaf(wa, a.z, acc.z); acc.w = fmaf(wa, a.w, acc.w);
+              acc.x = fmaf(wb, c.x, acc.x); acc.y = fmaf(wb, c.y, acc.y);
+              acc.z = fmaf(wb, c.z, acc.z); acc.w = fmaf(wb, c.w, acc.w);
+            }
+          const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(st + yz_lane + d * kYZ_d) = pk;
+          *reinterpret_cast<uint2*>(st + x_lane + d * kX_d) = pk;
+        }
+        fence_proxy_async();  // make this thread's A-operand stores visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + (kFull + stage) * 8);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA ISSUER ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = instr_desc(64, 32), idesc2 = instr_desc(128, 32);
+      const uint32_t w1s = s_base + kOffW1, w2s = s_base + kOffW2;
+      TileIter it(work);
+      uint32_t h = 0, g = 0;
+      auto conv2 = [&](uint32_t gg) {
+        const uint32_t gb = gg & 1, u = gg >> 1;
+        mbar_wait(bar0 + (kA2Full + gb) * 8, u & 1);
+        tc_fence_after();
+        const uint32_t a2 = s_base + kOffA2 + gb * kA2Bytes;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          umma_f16(tmem + 64 + gb * 32, smem_desc(a2 + i * 4096, 2048, 128), smem_desc(w2s + i * 1024, 512, 128), idesc2, i);
+        umma_commit(bar0 + (kD2Full + gb) * 8);
+      };
+      while (it.advance()) {
+        const uint32_t gb = g & 1, u = g >> 1;
+        if (u > 0) mbar_wait(bar0 + (kD1Empty + gb) * 8, (u - 1) & 1);
+        for (int sl = 0; sl < 2; ++sl, ++h) {
+          const uint32_t stage = h % kStages, use = h / kStages;
+          mbar_wait(bar0 + (kFull + stage) * 8, use & 1);
+          tc_fence_after();
+          const uint32_t a = s_base + kOffA + stage * kStageBytes;
+          const uint32_t d1 = tmem + ((uint32_t)(16 * sl) << 16) + gb * 32;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // view x: rows (d,h), K slice = (w=kk, c)
+            umma_f16(d1, smem_desc(a + kYZBytes + kk * kX_w, kX_ch, kX_d), smem_desc(w1s + kk * 1024, 512, 128), idesc1, kk);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // view y: rows (d,w), K slice = (h=kk, c)
+            umma_f16(d1, smem_desc(a + kk * kYZ_h, kYZ_ch, kYZ_d), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // view z: rows (h,w), K slice = (d=kk, c)
+            umma_f16(d1, smem_desc(a + kk * kYZ_d, kYZ_ch, kYZ_h), smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
+          umma_commit(bar0 + (kEmpty + stage) * 8);  // A stage may be overwritten once these MMAs retire
+        }
+        umma_commit(bar0 + (kD1Full + gb) * 8);
+        if (g > 0) conv2(g - 1);
+        ++g;
+      }
+      conv2(g - 1);
+    }
+    __syncwarp();
+  } else {
+    // =========================== EPILOGUE ===========================
+    const int s = warp - kEpiWarp0;       // TMEM sub-partition = warp % 4
+    const int slot = lane >> 4;           // which hypothesis of the tile
+    const int pos = 16 * s + (lane & 15); // position p*8+q of the folded plane
+    const uint32_t row = 32 * s + lane;   // TMEM lane == row of the conv2 A operand
+    float b2r[kO], tg[kO];
+#pragma unroll
+    for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
+    TileIter it(work);
+    int cur_b = -1;
+    float inv_s = 1.0f;
+    uint32_t g = 0;
+    int prev_b = 0, prev_cnt = 0;
+    int64_t prev_n0 = 0;
+    float prev_inv = 1.0f;
+    auto phase_b = [&](uint32_t gg, int pb, int64_t pn0, int pcnt, float pinv) {
+      const uint32_t gb = gg & 1, u = gg >> 1;
+      mbar_wait(bar0 + (kD2Full + gb) * 8, u & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + 64 + gb * 32, r);
+      tmem_ld_wait();
+      float ss = 0.0f, dt = 0.0f;
+#pragma unroll
+      for (int o = 0; o < kO; ++o) {
+        const float v = fmaf(__uint_as_float(r[o]), pinv, b2r[o]);  // undo the pair scale, add bias
+        ss = fmaf(v, v, ss);
+        dt = fmaf(v, tg[o], dt);
+      }
+      float cosv = dt / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (modules/modules.py:122)
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) cosv += __shfl_xor_sync(0xffffffffu, cosv, o);  // 16 positions of this slot
+      if ((lane & 15) == 0) partial[(gb * 2 + slot) * 4 + s] = cosv;
+      tc_fence_before();
+      named_bar_sync(2, 128);
+      if (s == 0 && lane < pcnt) {
+        const float* pp = partial + (gb * 2 + lane) * 4;
+        const float tot = ((pp[0] + pp[1]) + pp[2]) + pp[3];
+        scores[(size_t)pb * N + pn0 + lane] = tot * (1.0f / 64.0f);  // .mean(dim=-1)
+      }
+    };
+    while (it.advance()) {
+      const uint32_t gb = g & 1, u = g >> 1;
+      // ---- phase A: D1 -> ReLU -> fp16 -> A2 ----
+      mbar_wait(bar0 + (kD1Full + gb) * 8, u & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + gb * 32, r);
+      tmem_ld_wait();
+      unsigned char* a2 = smem + kOffA2 + gb * kA2Bytes + row * 16;
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[kc * 8 + 2 * e]), 0.0f),
+                                               fmaxf(__uint_as_float(r[kc * 8 + 2 * e + 1]), 0.0f));
+          w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(a2 + kc * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar0 + (kA2Full + gb) * 8);
+        mbar_arrive(bar0 + (kD1Empty + gb) * 8);
+      }
+      // ---- phase B of the previous tile ----
+      if (g > 0) phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+      if (it.b != cur_b) {  // target features / scale of the tile just handed to conv2
+        cur_b = it.b;
+        inv_s = pair_scale[cur_b].y;
+#pragma unroll
+        for (int o = 0; o < kO; ++o) tg[o] = __ldg(tgt_feat + ((size_t)cur_b * kO + o) * kP + pos);
+      }
+      prev_b = it.b; prev_n0 = it.n0; prev_cnt = it.cnt; prev_inv = inv_s;
+      ++g;
+    }
+    phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// ---- weight packing + per-pair scale (one small launch before the main kernel) ----
+// w_packed: conv1 B operand, 24 slices j=(view,kk): [chalf][ngroup][n%8][c%8] fp16, then conv2 B operand.
+template <typename T>
+__global__ void __launch_bounds__(256)
+tc_prep_kernel(const T* __restrict__ vol_src, const float* __restrict__ W1, const float* __restrict__ W2,
+               __half* __restrict__ w_packed, float2* __restrict__ pair_scale) {
+  __shared__ float red[8];
+  __shared__ float l1max_s;
+  const int t = threadIdx.x;
+  if (blockIdx.x == 0) {
+    for (int i = t; i < kO * kK; i += 256) {
+      const int n = i / kK, k = i % kK;
+      const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7;
+      const int j = view * 8 + kk;
+      w_packed[j * 512 + (c >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (c & 7)] = __float2half_rn(W1[i]);
+    }
+    for (int i = t; i < kO * kO; i += 256) {
+      const int n = i / kO, k = i % kO;
+      w_packed[kW1Bytes / 2 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2half_rn(W2[i]);
+    }
+    return;
+  }
+  const int b = blockIdx.x - 1;
+  // largest L1 norm of a W1 row bounds |conv1 output| / max|V|
+  float l1 = 0.0f;
+  {
+    const int o = t >> 3, part = t & 7;  // 8 threads per output row
+    for (int k = part; k < kK; k += 8) l1 += fabsf(W1[o * kK + k]);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 4);
+#pragma unroll
+    for (int o2 = 8; o2 < 32; o2 <<= 1) l1 = fmaxf(l1, __shfl_xor_sync(0xffffffffu, l1, o2));
+    if ((t & 31) == 0) red[t >> 5] = l1;
+    __syncthreads();
+    if (t == 0) {
+      float m = red[0];
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+      l1max_s = m;
+    }
+    __syncthreads();
+  }
+  float mx = 0.0f;
+  const T* v = vol_src + (size_t)b * kC * kVox;
+  for (int i = t; i < kC * kVox; i += 256) mx = fmaxf(mx, fabsf(ld_vol<T>(v + i)));
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+  __syncthreads();
+  if ((t & 31) == 0) red[t >> 5] = mx;
+  __syncthreads();
+  if (t == 0) {
+    float m = red[0];
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    // power-of-two scale: max|V|*s <= 2^12 and max|V|*s*L1max <= 2^14 (fp16 max 65504)
+    float s = 1.0f;
+    if (m > 0.0f && isfinite(m)) {
+      const float bound = fminf(4096.0f, 16384.0f / fmaxf(l1max_s, 1e-20f));
+      int e = ilogbf(bound / m);  // floor(log2)
+      e = max(-100, min(100, e));
+      s = scalbnf(1.0f, e);
+    }
+    pair_scale[b] = make_float2(s, 1.0f / s);
+  }
+}
+
+}  // namespace tc
+
+size_t score_tc_workspace_bytes(int B, int64_t N) {
+  (void)N;
+  return (size_t)(tc::kW1Bytes + tc::kW2Bytes) + (size_t)B * sizeof(float2) + 256;
+}
+
+int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
+                    int r_per_pair, const float* W1, const float* W2, const float* b2,
+                    const float* base, float* scores, int B, int64_t N, void* ws, size_t ws_bytes,
+                    cudaStream_t s) {
+  const int64_t total = (int64_t)B * N;
+  if (total == 0) return AHV_OK;
+  if (ws_bytes < score_tc_workspace_bytes(B, N)) return AHV_EWORKSPACE;
+  int dev = 0, sms = 0;
+  AHV_CUDA_OK(cudaGetDevice(&dev));
+  AHV_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  __half* w_packed = reinterpret_cast<__half*>(ws);
+  float2* pair_scale = reinterpret_cast<float2*>(static_cast<unsigned char*>(ws) + tc::kW1Bytes + tc::kW2Bytes);
+  // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
+  const int64_t tiles = (total + 1) / 2;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  if (vol_dtype == AHV_VOL_F32) {
+    tc::tc_prep_kernel<float><<<B + 1, 256, 0, s>>>((const float*)vol_src, W1, W2, w_packed, pair_scale);
+    AHV_CUDA_OK(cudaGetLastError());
+    AHV_CUDA_OK(cudaFuncSetAttribute(tc::score_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    tc::score_tc_kernel<float><<<grid, tc::kThreadsTC, tc::kSmemBytes, s>>>(
+        (const float*)vol_src, tgt_feat, R, r_per_pair, b2, base, (const uint4*)w_packed, pair_scale, scores, B, N);
+  } else {
+    tc::tc_prep_kernel<__nv_bfloat16><<<B + 1, 256, 0, s>>>((const __nv_bfloat16*)vol_src, W1, W2, w_packed, pair_scale);
+    AHV_CUDA_OK(cudaGetLastError());
+    AHV_CUDA_OK(cudaFuncSetAttribute(tc::score_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    tc::score_tc_kernel<__nv_bfloat16><<<grid, tc::kThreadsTC, tc::kSmemBytes, s>>>(
+        (const __nv_bfloat16*)vol_src, tgt_feat, R, r_per_pair, b2, base, (const uint4*)w_packed, pair_scale, scores, B, N);
+  }
+  AHV_CUDA_OK(cudaGetLastError());
+  return AHV_OK;
+}
+
 }  // namespace ahv
