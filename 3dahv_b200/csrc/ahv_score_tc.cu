@@ -7,10 +7,14 @@
 // One persistent CTA per SM, 13 warps, warp-specialised:
 //   warps 0-7   GATHER   trilinear resampling (utils.py:113-131) of the source
 //                        volume held in shared memory (fp32, zero halo, channel
-//                        innermost).  4 lanes per output voxel x float4 channels,
-//                        x-taps issued in bank-parity order => conflict-free
-//                        LDS.128.  Results are rounded to fp16 and written as the
-//                        tri-plane A operand of conv1 in UMMA K-major layout:
+//                        innermost, 64 B per voxel line).  One lane per output
+//                        voxel, all 16 channels; warp w owns the slab d = w.  The
+//                        four 16-byte channel chunks of a line are visited in a
+//                        per-lane rotated order and the two x taps in bank-parity
+//                        order, which makes every LDS.128 phase conflict-free by
+//                        construction.  Results are rounded to fp16 and written
+//                        as the tri-plane A operand of conv1 in UMMA K-major
+//                        core-matrix layout:
 //                        copy YZ  [chalf][d][h][w][c8]  serves views y and z,
 //                        copy X   [chalf][d][w][h][c8]  serves view x.
 //   warp  12    MMA      one elected thread issues tcgen05.mma (kind::f16, fp32
@@ -44,13 +48,13 @@ constexpr int kStages = 3;
 // ---- shared memory map (bytes) ----
 constexpr int kW1Bytes = 24 * 1024;  // 24 MMA slices x [2 chalf][4 ngroup][8][8] fp16
 constexpr int kW2Bytes = 2 * 1024;
-// A operand, copy YZ: core matrix CM(d,h,chalf) = [w][c8] (128 B)
-constexpr int kYZ_h = 128, kYZ_d = 1024, kYZ_ch = 8192 + 64;  // chalf block shifted by 64 B: STS.64 conflict-free
-constexpr int kYZBytes = kYZ_ch + 8192;                       // 16448
-// copy X: core matrix CM(d,w,chalf) = [h][c8]
-constexpr int kX_w = 144, kX_d = 8 * kX_w, kX_ch = 8 * kX_d + 64;  // 144: quads land 16 B apart mod 128
-constexpr int kXBytes = kX_ch + 8 * kX_d;                          // 18496
-constexpr int kStageBytes = ((kYZBytes + kXBytes + 127) / 128) * 128;  // 35072
+// A operand of conv1, two dense copies of the rotated volume in fp16 (8-row x 16-byte core matrices):
+//   copy YZ: CM(d,h,chalf) = [w][c8] at chalf*kCh + d*1024 + h*128   (views y and z)
+//   copy X : CM(d,w,chalf) = [h][c8] at chalf*kCh + d*1024 + w*128   (view x)
+// the second channel-half block is shifted by 64 B so the gather's STS.64 are conflict-free
+constexpr int kCh = 8192 + 64;
+constexpr int kCopyBytes = kCh + 8192;       // 16448
+constexpr int kStageBytes = 2 * kCopyBytes;  // 32896
 constexpr int kA2Bytes = 8192;  // [4 kc][16 rowgroup][8][8] fp16
 
 constexpr int kOffVol = 0;
@@ -77,11 +81,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
-  do {
+  do {  // try_wait suspends the warp (no issue slots burnt) until the phase flips or the hint expires
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
   } while (!done);
 }
@@ -138,19 +142,28 @@ struct Work {  // contiguous range of (pair, hypothesis) items of this CTA
 
 // tile = two consecutive hypotheses of one pair; returns false when exhausted
 struct TileIter {
-  int64_t next, hi, N;
+  int64_t next, hi, N, seg_end;
   int b;
   int64_t n0;  // first hypothesis of the tile
   int cnt;     // 1 or 2 valid hypotheses
-  __device__ __forceinline__ TileIter(const Work& w) : next(w.lo), hi(w.hi), N(w.N), b(0), n0(0), cnt(0) {}
+  __device__ __forceinline__ TileIter(const Work& w) : next(w.lo), hi(w.hi), N(w.N), n0(0), cnt(0) {
+    b = (int)(w.lo / w.N);
+    seg_end = (int64_t)(b + 1) * w.N;
+  }
   __device__ __forceinline__ bool advance() {
     if (next >= hi) return false;
-    b = (int)(next / N);
-    n0 = next - (int64_t)b * N;
-    const int64_t seg_end = min(hi, (int64_t)(b + 1) * N);
-    cnt = (seg_end - next >= 2) ? 2 : 1;
+    if (next >= seg_end) { ++b; seg_end += N; }
+    n0 = next - (seg_end - N);
+    const int64_t end = seg_end < hi ? seg_end : hi;
+    cnt = (end - next >= 2) ? 2 : 1;
     next += cnt;
     return true;
+  }
+  // (pair, hypothesis) of the item following this tile, or the tile's own first item at the very end
+  __device__ __forceinline__ void peek(int& pb, int64_t& pn) const {
+    if (next >= hi) { pb = b; pn = n0; }
+    else if (next >= seg_end) { pb = b + 1; pn = 0; }
+    else { pb = b; pn = next - (seg_end - N); }
   }
 };
 
@@ -214,14 +227,33 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
 
   if (warp < kGatherWarps) {
     // =========================== GATHER ===========================
-    const int j = lane & 3, q = lane >> 2, gw = warp;
-    const float bx = sbase[q], by = sbase[gw];
-    const uint32_t yz_lane = (j >> 1) * kYZ_ch + gw * kYZ_h + q * 16 + (j & 1) * 8;
-    const uint32_t x_lane = kYZBytes + (j >> 1) * kX_ch + q * kX_w + gw * 16 + (j & 1) * 8;
+    // lane -> voxel (d = warp, h = 4e + hh, w): w = lane>>2, hh = lane&3
+    const int w = lane >> 2, hh = lane & 3, d = warp;
+    const int pf = w & 1;                 // bank parity this lane reads first
+    const int rot = ((w & 3) + hh) & 3;   // chunk rotation: lanes of one LDS phase hit 8 distinct bank groups
+    const float bx = sbase[w], bz = sbase[d];
+    const float by0 = sbase[hh], by1 = sbase[4 + hh];
+    uint32_t koff[4], syz[4], sx[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ck = (rot + t) & 3;       // logical channel chunk (channels 4ck..4ck+3) held in acc[t]
+      koff[t] = ck * 16;
+      syz[t] = (ck >> 1) * kCh + (ck & 1) * 8 + d * 1024 + hh * 128 + w * 16;
+      sx[t] = kCopyBytes + (ck >> 1) * kCh + (ck & 1) * 8 + d * 1024 + w * 128 + hh * 16;
+    }
+    const unsigned char* volb = smem + kOffVol;
     const int gtid = threadIdx.x;  // 0..255
     TileIter it(work);
     int cur_b = -1;
     uint32_t h = 0;  // hypothesis counter of this CTA (stage = h % 3)
+    float Rn[9];
+    {
+      const int b0 = (int)(work.lo / N);
+      const int64_t n0 = work.lo - (int64_t)b0 * N;
+      const float* Rg = R + (r_per_pair ? ((size_t)b0 * N + n0) : (size_t)n0) * 9;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
+    }
     while (it.advance()) {
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);  // everyone is done reading the previous volume
@@ -242,49 +274,77 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
         cur_b = it.b;
       }
       for (int sl = 0; sl < 2; ++sl, ++h) {
-        const int64_t n = it.n0 + (sl < it.cnt ? sl : 0);  // odd tail: recompute the valid hypothesis
-        const float* Rg = R + (r_per_pair ? ((size_t)it.b * N + n) : (size_t)n) * 9;
         float Rr[9];
 #pragma unroll
-        for (int e = 0; e < 9; ++e) Rr[e] = __ldg(Rg + e);
+        for (int e = 0; e < 9; ++e) Rr[e] = Rn[e];
+        {  // prefetch the next hypothesis' rotation (hides the L2 round trip behind this gather)
+          int nb; int64_t nn;
+          if (sl == 0) { nb = it.b; nn = it.n0 + (it.cnt > 1 ? 1 : 0); }
+          else it.peek(nb, nn);
+          const float* Rg = R + (r_per_pair ? ((size_t)nb * N + nn) : (size_t)nn) * 9;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
+        }
         const uint32_t stage = h % kStages, use = h / kStages;
         if (use > 0) mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1);
         unsigned char* st = smem + kOffA + stage * kStageBytes;
-        // grid = R @ (x, y, z): x and y are fixed per lane, z walks with d
-        const float pgx = fmaf(Rr[1], by, Rr[0] * bx), pgy = fmaf(Rr[4], by, Rr[3] * bx), pgz = fmaf(Rr[7], by, Rr[6] * bx);
-#pragma unroll
-        for (int d = 0; d < 8; ++d) {
-          const float bz = sbase[d];
-          float ix = unnorm(fmaf(Rr[2], bz, pgx)), iy = unnorm(fmaf(Rr[5], bz, pgy)), iz = unnorm(fmaf(Rr[8], bz, pgz));
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+          const float by = e ? by1 : by0;
+          // grid = R @ (x, y, z)  (F.affine_grid, utils.py:126), then grid_sample's un-normalisation
+          float ix = unnorm(fmaf(Rr[2], bz, fmaf(Rr[1], by, Rr[0] * bx)));
+          float iy = unnorm(fmaf(Rr[5], bz, fmaf(Rr[4], by, Rr[3] * bx)));
+          float iz = unnorm(fmaf(Rr[8], bz, fmaf(Rr[7], by, Rr[6] * bx)));
           ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
           const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
           const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
           const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
-          const int swap = (line ^ q) & 1;  // bank-parity order of the two x taps (see ahv_score_fp32.cu)
+          const int swap = (line ^ pf) & 1;  // first x tap = the one whose 64 B line has bank parity pf
           const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
-          const float* p0 = vol + (line + swap) * kC + j * 4;
-          const float* p1 = vol + (line + 1 - swap) * kC + j * 4;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const unsigned char* pa = volb + (line + swap) * 64;
+          const unsigned char* pb = volb + (line + 1 - swap) * 64;
+          float wa[4], wb[4];
 #pragma unroll
-          for (int dz = 0; dz < 2; ++dz)
+          for (int c = 0; c < 4; ++c) {
+            const float wyz = ((c & 1) ? fy : 1.0f - fy) * ((c >> 1) ? fz : 1.0f - fz);
+            wa[c] = wyz * wxa;
+            wb[c] = wyz * wxb;
+          }
+          // 4 chunk batches of 8 LDS.128 each, software-pipelined: batch t+1 is in flight
+          // while batch t is consumed (two register buffers)
+          float4 buf[2][8];
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy) {
-              const float wyz = (dy ? fy : 1.0f - fy) * (dz ? fz : 1.0f - fz);
-              const int off = (dz * kHalo * kHalo + dy * kHalo) * kC;
-              const float4 a = *reinterpret_cast<const float4*>(p0 + off);
-              const float4 c = *reinterpret_cast<const float4*>(p1 + off);
-              const float wa = wyz * wxa, wb = wyz * wxb;
-              acc.x = fmaf(wa, a.x, acc.x); acc.y = fmaf(wa, a.y, acc.y);
-              acc.z = fmaf(wa, a.z, acc.z); acc.w = fmaf(wa, a.w, acc.w);
-              acc.x = fmaf(wb, c.x, acc.x); acc.y = fmaf(wb, c.y, acc.y);
-              acc.z = fmaf(wb, c.z, acc.z); acc.w = fmaf(wb, c.w, acc.w);
+          for (int c = 0; c < 4; ++c) {  // c = dz*2 + dy
+            const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+            buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
+            buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t < 3) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+                buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
+                buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+              }
             }
-          const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(st + yz_lane + d * kYZ_d) = pk;
-          *reinterpret_cast<uint2*>(st + x_lane + d * kX_d) = pk;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 a = buf[t & 1][2 * c], g = buf[t & 1][2 * c + 1];
+              acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
+              acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
+              acc.x = fmaf(wb[c], g.x, acc.x); acc.y = fmaf(wb[c], g.y, acc.y);
+              acc.z = fmaf(wb[c], g.z, acc.z); acc.w = fmaf(wb[c], g.w, acc.w);
+            }
+            const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi2 = __floats2half2_rn(acc.z, acc.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
+            *reinterpret_cast<uint2*>(st + syz[t] + e * 512) = pk;  // h += 4
+            *reinterpret_cast<uint2*>(st + sx[t] + e * 64) = pk;
+          }
         }
         fence_proxy_async();  // make this thread's A-operand stores visible to the tensor core
         __syncwarp();
@@ -319,13 +379,13 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
           const uint32_t d1 = tmem + ((uint32_t)(16 * sl) << 16) + gb * 32;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view x: rows (d,h), K slice = (w=kk, c)
-            umma_f16(d1, smem_desc(a + kYZBytes + kk * kX_w, kX_ch, kX_d), smem_desc(w1s + kk * 1024, 512, 128), idesc1, kk);
+            umma_f16(d1, smem_desc(a + kCopyBytes + kk * 128, kCh, 1024), smem_desc(w1s + kk * 1024, 512, 128), idesc1, kk);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view y: rows (d,w), K slice = (h=kk, c)
-            umma_f16(d1, smem_desc(a + kk * kYZ_h, kYZ_ch, kYZ_d), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
+            umma_f16(d1, smem_desc(a + kk * 128, kCh, 1024), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view z: rows (h,w), K slice = (d=kk, c)
-            umma_f16(d1, smem_desc(a + kk * kYZ_d, kYZ_ch, kYZ_h), smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
+            umma_f16(d1, smem_desc(a + kk * 1024, kCh, 128), smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
           umma_commit(bar0 + (kEmpty + stage) * 8);  // A stage may be overwritten once these MMAs retire
         }
         umma_commit(bar0 + (kD1Full + gb) * 8);
