@@ -38,6 +38,11 @@ def import_reference():
     sys.path.insert(0, "/root/reference")
     from utils import rotate_volume  # utils.py:113
     from modules.modules import Feature_Aligner  # modules/modules.py:49
+    import modules.modules as _ref_mod
+
+    # this repo also has modules/ and transformer/ (drop-in API): make sure the REFERENCE's were imported
+    assert _ref_mod.__file__.startswith("/root/reference/"), _ref_mod.__file__
+    assert sys.modules["transformer.attention"].__file__.startswith("/root/reference/")
 
     return rotate_volume, Feature_Aligner
 
