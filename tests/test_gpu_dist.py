@@ -1,0 +1,53 @@
+"""GPU, >=2 devices: hypothesis sharding over NCCL gives the single-GPU result on every rank."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, k, out_q):
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ahv = importlib.import_module("3dahv_b200")
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "shared_n3000_b3.npz")))
+    w = dict(np.load(os.path.join(ROOT, "tests", "golden", "weights.npz")))
+    T = lambda a: torch.from_numpy(a).to(dev)
+    v = ahv.HypothesisVerifier(T(w["W1"]), T(w["W2"]), T(w["b2"]))
+    sv = ahv.dist.ShardedVerifier(v)
+    val, idx, Rb = sv.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=k)
+    single = v.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=k, return_scores=False)
+    torch.cuda.synchronize()
+    out_q.put((rank, val.cpu().numpy(), idx.cpu().numpy(), Rb.cpu().numpy(), single.topk_val.cpu().numpy(),
+               single.topk_idx.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_equals_single_gpu_nccl(golden):
+    world, k = 2, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, 29611, k, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, val, idx, Rb, sval, sidx in res:
+        assert np.array_equal(idx, sidx) and np.array_equal(val, sval)
+        assert np.array_equal(Rb, golden["shared_n3000_b3"]["R"][idx])
+    assert np.array_equal(res[0][2], res[1][2])
