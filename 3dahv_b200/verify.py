@@ -104,3 +104,42 @@ class HypothesisVerifier:
         cand = cand.reshape(B, -1, 3, 3).contiguous()
         second = self.score(vol_src, vol_tgt, cand, k=1, return_scores=False, tgt_feat=tgt)
         return second.R_best[:, 0], second.topk_val[:, 0], first, cand
+
+
+class GraphedVerifier:
+    """CUDA-graph replay of one verification step for fixed (B, N, k): target
+    features + fused scoring + selection + winner gather are captured once and
+    replayed with a single launch, which is what bounds the B=1 latency
+    (the reference's per-pair loop is batch 1, test_co3d.py:133).  Inputs are
+    copied into static buffers; outputs are static tensors valid until the next
+    replay."""
+
+    def __init__(self, verifier: HypothesisVerifier, B: int, N: int, k: int = 1, per_pair_R: bool = False,
+                 device="cuda", vol_dtype=torch.float32):
+        self.v = verifier.to(torch.device(device))
+        dev = torch.device(device)
+        self.vol_src = torch.zeros(B, 16, 8, 8, 8, device=dev, dtype=vol_dtype)
+        self.vol_tgt = torch.zeros(B, 16, 8, 8, 8, device=dev)
+        self.R = torch.eye(3, device=dev).repeat(*((B, N) if per_pair_R else (N,)), 1, 1).contiguous()
+        self.k = min(k, N)
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            for _ in range(2):                      # warm-up outside capture (module load, attributes)
+                self.out = self.v.score(self.vol_src, self.vol_tgt, self.R, k=self.k, return_scores=False)
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self.v.score(self.vol_src, self.vol_tgt, self.R, k=self.k, return_scores=False)
+
+    @torch.no_grad()
+    def __call__(self, vol_src=None, vol_tgt=None, R=None) -> VerifyResult:
+        if vol_src is not None:
+            self.vol_src.copy_(vol_src, non_blocking=True)
+        if vol_tgt is not None:
+            self.vol_tgt.copy_(vol_tgt, non_blocking=True)
+        if R is not None:
+            self.R.copy_(R, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -245,6 +245,21 @@ def run_ours(args):
     smem_peak_gbs = nbytes.value / (a.elapsed_time(b_) * 1e-3) / 1e9
     clocks = sampler.stop() if rank == 0 else None
 
+    # p50 per-pair latency, B=1: CUDA-graph replay of the whole step, CUDA events
+    latency = {}
+    if rank == 0:
+        import statistics as _st
+        for n_lat in (3000, 50000):
+            gv = ahv.GraphedVerifier(verifier, 1, n_lat, k=1, device=dev)
+            gv(vs[:1], vt[:1], R[:n_lat])
+            for _ in range(10):
+                gv()
+            lev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+            for a, b_ in lev:
+                a.record(); gv(); b_.record()
+            torch.cuda.synchronize()
+            latency[f"N={n_lat}"] = {"p50_us": _st.median(a.elapsed_time(b_) for a, b_ in lev) * 1e3, "calls": 100}
+
     # e2e: host buffers through the C ABI (H2D + compute + D2H inside the timed region)
     vs_p, vt_p = vs_h.pin_memory(), vt_h.pin_memory()
     R_p = R.cpu().pin_memory()
@@ -280,6 +295,7 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB memset, untimed)"},
             "voxel_samples_per_s": value * 512,
             "clocks": clocks,
+            "latency_p50_per_pair": latency,
             "e2e": {"value": units_per_step * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "ahv_predict_host (C ABI, pinned host buffers)"},
             "gpu_launches": n_launch,
