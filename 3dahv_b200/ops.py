@@ -12,17 +12,26 @@ from . import _lib
 from ._lib import MATH_FP32, MATH_TC, VOL_BF16, VOL_F32
 
 _BASE_CPU = None
+_BASE_DEV = {}
 
 
 def base_coords(device=None) -> torch.Tensor:
     """The 8 base coordinates F.affine_grid(align_corners=False) uses for size 8
     (ATen: linspace(-1,1,8)*7/8 — not exactly (2i+1)/8-1), taken from ATen itself
-    so the kernel sees the reference's values (utils.py:126)."""
+    so the kernel sees the reference's values (utils.py:126).  Cached per device
+    (no host->device copy on the hot path, CUDA-graph safe)."""
     global _BASE_CPU
     if _BASE_CPU is None:
         g = F.affine_grid(torch.eye(3, 4)[None], (1, 1, 8, 8, 8), align_corners=False)
         _BASE_CPU = g[0, 0, 0, :, 0].contiguous().clone()
-    return _BASE_CPU if device is None else _BASE_CPU.to(device)
+    if device is None:
+        return _BASE_CPU
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    if device not in _BASE_DEV:
+        _BASE_DEV[device] = _BASE_CPU.to(device)
+    return _BASE_DEV[device]
 
 
 def _stream(t: torch.Tensor):
