@@ -50,6 +50,14 @@ AHV_API int ahv_so3_sample(uint64_t seed, int64_t first_index, float* R, int64_t
   return launch_so3_sample(seed, first_index, R, n, (cudaStream_t)stream);
 }
 
+AHV_API int ahv_so3_grid(int64_t n_total, int64_t first_index, float* R, int64_t count, void* stream) {
+  if (n_total < 1 || first_index < 0 || count < 0 || first_index + count > n_total || (count > 0 && !R))
+    return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_so3_grid(n_total, first_index, R, count, (cudaStream_t)stream);
+}
+
 AHV_API int ahv_rotate_volume(const float* vol, int vol_per_rotation, const float* R, const float* base,
                       float* out, int64_t n, void* stream) {
   if (n < 0 || (n > 0 && (!vol || !R || !base || !out))) return AHV_EINVAL;
@@ -163,6 +171,14 @@ AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_hos
   const size_t total = align_up(vol_b, 256) * 2 + align_up(r_b, 256) + align_up(feat_b, 256) +
                        align_up(w_b, 256) + align_up(out_b, 256) + ws_b;
   unsigned char* d = nullptr;
+  {  // keep the stream-ordered pool's memory across calls instead of returning it to the OS at every sync
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   AHV_CUDA_OK(cudaMallocAsync((void**)&d, total, s));
   unsigned char* p = d;
   auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 256); return r; };

@@ -69,6 +69,7 @@ __device__ __forceinline__ Tap make_tap(const float* R, float x, float y, float 
 // Launch-side helpers implemented in the .cu files --------------------------
 int launch_so3_from_normals(const float* normals, float* R, int64_t n, cudaStream_t s);
 int launch_so3_sample(uint64_t seed, int64_t first, float* R, int64_t n, cudaStream_t s);
+int launch_so3_grid(int64_t n_total, int64_t first, float* R, int64_t count, cudaStream_t s);
 int launch_rotate_volume(const float* vol, int per_rot, const float* R, const float* base,
                          float* out, int64_t n, cudaStream_t s);
 int launch_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,

@@ -81,6 +81,37 @@ __global__ void __launch_bounds__(256) so3_sample_kernel(uint64_t seed, int64_t 
   for (int e = 0; e < 9; ++e) R[t * 9 + e] = m[e];
 }
 
+// Deterministic near-uniform SO(3) grid: super-Fibonacci spiral (Alexa, CVPR 2022).  Point i of an
+// n-point set: s=i+1/2, t=s/n, r=sqrt(t), rr=sqrt(1-t), a=2*pi*s/sqrt(2), b=2*pi*s/psi, psi=1.5337511687...
+// q=(r sin a, r cos a, rr sin b, rr cos b) -> matrix by the same map as random_rotations.  Evaluated in fp64
+// and rounded once to fp32 so the CPU restatement (oracle/ahv_oracle.c) reproduces it bit for bit.
+__global__ void __launch_bounds__(256) so3_grid_kernel(int64_t n_total, int64_t first, float* __restrict__ R,
+                                                       int64_t count) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const double s = (double)(first + t) + 0.5;
+  const double u = s / (double)n_total;
+  const double r = sqrt(u), rr = sqrt(1.0 - u);
+  // reduce the angle to [0,1) turns before sinpi/cospi: exact in fp64 for these magnitudes
+  double ta = s * 0.70710678118654752440, tb = s * 0.65199624317913454;  // s/sqrt(2), s/psi
+  ta -= floor(ta);
+  tb -= floor(tb);
+  double sa, ca, sb, cb;
+  sincospi(2.0 * ta, &sa, &ca);
+  sincospi(2.0 * tb, &sb, &cb);
+  float m[9];
+  quat_to_matrix_exact((float)(r * sa), (float)(r * ca), (float)(rr * sb), (float)(rr * cb), m);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) R[t * 9 + e] = m[e];
+}
+
+int launch_so3_grid(int64_t n_total, int64_t first, float* R, int64_t count, cudaStream_t s) {
+  if (count == 0) return AHV_OK;
+  so3_grid_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(n_total, first, R, count);
+  AHV_CUDA_OK(cudaGetLastError());
+  return AHV_OK;
+}
+
 int launch_so3_from_normals(const float* normals, float* R, int64_t n, cudaStream_t s) {
   if (n == 0) return AHV_OK;
   int64_t blocks = (n + 255) / 256;

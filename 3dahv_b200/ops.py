@@ -65,6 +65,16 @@ def sample_rotations(n: int, seed: int, first_index: int = 0, device="cuda") -> 
     return R
 
 
+def grid_rotations(n_total: int, first_index: int = 0, count: int | None = None, device="cuda") -> torch.Tensor:
+    """Deterministic super-Fibonacci SO(3) grid, points [first, first+count) of n_total."""
+    device = torch.device(device)
+    count = n_total - first_index if count is None else count
+    R = torch.empty(count, 3, 3, device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().ahv_so3_grid(n_total, first_index, R.data_ptr(), count, _stream(R)), "ahv_so3_grid")
+    return R
+
+
 def rotate_volume(volume: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
     """utils.rotate_volume (utils.py:113-131) on the GPU.  `volume` is
     [16,8,8,8] (one volume under n rotations) or [n,16,8,8,8] (one per rotation)."""

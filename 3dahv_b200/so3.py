@@ -39,6 +39,12 @@ def sample_rotations(n: int, seed: int = 0, first_index: int = 0, device="cuda")
     return ops.sample_rotations(n, seed, first_index, device)
 
 
+def grid_rotations(n_total: int, first_index: int = 0, count: int | None = None, device="cuda") -> torch.Tensor:
+    """Deterministic, near-uniform SO(3) grid of any size (super-Fibonacci spiral): the
+    "dense SO(3) grid" of BASELINE config 4.  Shardable like the native sampler."""
+    return ops.grid_rotations(n_total, first_index, count, device)
+
+
 def perturb_rotations(R_center: torch.Tensor, m: int, max_angle_deg: float, seed: int = 0) -> torch.Tensor:
     """Local refinement set (BASELINE config 4; extension, the reference has no
     refinement): for each of the [...,3,3] centres, m rotations within

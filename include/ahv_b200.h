@@ -68,6 +68,11 @@ AHV_API int ahv_so3_from_normals(const float* normals, float* R, int64_t n, void
  * can be generated independently on any GPU. */
 AHV_API int ahv_so3_sample(uint64_t seed, int64_t first_index, float* R, int64_t n, void* stream);
 
+/* Deterministic SO(3) grid (extension, BASELINE config 4 "dense SO(3) grid"): points
+ * [first_index, first_index+count) of the n_total-point super-Fibonacci spiral, as rotation
+ * matrices.  Evaluated in fp64, rounded once: bit-identical to oracle/ahv_oracle.c. */
+AHV_API int ahv_so3_grid(int64_t n_total, int64_t first_index, float* R, int64_t count, void* stream);
+
 /* utils.rotate_volume (utils.py:113-131): F.affine_grid + F.grid_sample
  * (trilinear, zeros padding, align_corners=False), materialised.
  * vol: [16,8,8,8] when vol_per_rotation==0 (the stride-0 `expand` of

@@ -52,6 +52,24 @@ void ahv_oracle_so3_from_normals(const float *o, float *R, int64_t n) {
   }
 }
 
+/* Super-Fibonacci SO(3) grid (extension; Alexa 2022), fp64 then one rounding to fp32, then the
+ * same quaternion -> matrix map.  sin/cos of 2*pi*frac(x): glibc's fp64 sin/cos and CUDA's
+ * sincospi are both < 1 ulp in fp64, so the fp32 roundings agree. */
+void ahv_oracle_so3_grid(int64_t n_total, int64_t first, float *R, int64_t count) {
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int64_t t = 0; t < count; ++t) {
+    const double s = (double)(first + t) + 0.5;
+    const double u = s / (double)n_total;
+    const double r = sqrt(u), rr = sqrt(1.0 - u);
+    double ta = s * 0.70710678118654752440, tb = s * 0.65199624317913454;
+    ta -= floor(ta);
+    tb -= floor(tb);
+    float q[4] = {(float)(r * sin(two_pi * ta)), (float)(r * cos(two_pi * ta)),
+                  (float)(rr * sin(two_pi * tb)), (float)(rr * cos(two_pi * tb))};
+    ahv_oracle_so3_from_normals(q, R + 9 * t, 1);
+  }
+}
+
 /* utils.py:113-131: one hypothesis.  vol [16][512], out [16][512]. */
 void ahv_oracle_rotate_one(const float *vol, const float *R, const float *base, float *out) {
   for (int d = 0; d < AS; ++d)

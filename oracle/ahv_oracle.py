@@ -312,6 +312,8 @@ def c_lib(build: bool = True):
     lib = ctypes.CDLL(so)
     fp = ctypes.POINTER(ctypes.c_float)
     lib.ahv_oracle_so3_from_normals.argtypes = [fp, fp, ctypes.c_int64]
+    lib.ahv_oracle_so3_grid.argtypes = [ctypes.c_int64, ctypes.c_int64, fp, ctypes.c_int64]
+    lib.ahv_oracle_so3_grid.restype = None
     lib.ahv_oracle_score.argtypes = [fp, fp, fp, ctypes.c_int, fp, fp, fp, fp, ctypes.c_int, ctypes.c_int64, fp, ctypes.c_int]
     lib.ahv_oracle_argmax.argtypes = [fp, ctypes.c_int, ctypes.c_int64, fp, ctypes.POINTER(ctypes.c_int64)]
     for fn in (lib.ahv_oracle_so3_from_normals, lib.ahv_oracle_score, lib.ahv_oracle_argmax):
@@ -330,6 +332,14 @@ def rotations_from_normals_c(o: np.ndarray) -> np.ndarray:
     o = np.ascontiguousarray(o, dtype=np.float32)
     R = np.empty((o.shape[0], 9), dtype=np.float32)
     c_lib().ahv_oracle_so3_from_normals(_fp(o), _fp(R), o.shape[0])
+    return R.reshape(-1, 3, 3)
+
+
+def grid_rotations_c(n_total: int, first: int = 0, count: int | None = None) -> np.ndarray:
+    """Restatement of ahv_so3_grid (super-Fibonacci SO(3) grid; extension beyond the reference)."""
+    count = n_total - first if count is None else count
+    R = np.empty((count, 9), dtype=np.float32)
+    c_lib().ahv_oracle_so3_grid(n_total, first, _fp(R), count)
     return R.reshape(-1, 3, 3)
 
 

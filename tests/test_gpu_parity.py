@@ -76,6 +76,14 @@ def test_native_sampler_properties(ahv):
     assert abs(ang.mean().item() - 126.5) < 1.5
 
 
+def test_so3_grid_bit_exact_and_shardable(ahv, oracle):
+    dev = _dev()
+    R = ahv.so3.grid_rotations(50000, device=dev)
+    assert np.array_equal(R.cpu().numpy(), oracle.grid_rotations_c(50000))
+    part = ahv.so3.grid_rotations(50000, first_index=43750, count=6250, device=dev)   # rank 7 of 8
+    assert torch.equal(part, R[43750:])
+
+
 def test_rotate_volume_vs_reference(ahv, golden):
     dev = _dev()
     p, g = golden["primitives"], golden["shared_n3000_b3"]

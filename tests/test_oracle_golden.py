@@ -112,3 +112,23 @@ def test_select_np_ordering(oracle):
     s = np.array([[0.1, 0.5, 0.5, -0.0, 0.0, 0.3]], np.float32)
     val, idx = oracle.select_np(s, 4)
     assert idx.tolist() == [[1, 2, 5, 0]]
+
+
+def test_so3_grid_restatement_properties(oracle):
+    """Extension (BASELINE config 4): deterministic super-Fibonacci SO(3) grid."""
+    R = oracle.grid_rotations_c(20000)
+    det = np.linalg.det(R.astype(np.float64))
+    np.testing.assert_allclose(det, 1.0, atol=1e-5)
+    eye = np.einsum("nij,nkj->nik", R, R)
+    np.testing.assert_allclose(eye, np.broadcast_to(np.eye(3), eye.shape), atol=2e-6)
+    # shards of the set are slices of the whole (any rank can generate its own)
+    assert np.array_equal(oracle.grid_rotations_c(20000, 5000, 777), R[5000:5777])
+    # near-uniform: nearest-neighbour angles are concentrated (iid sampling would go below 1 degree)
+    q = R.reshape(-1, 9).astype(np.float64)
+    idx = np.arange(0, 20000, 100)
+    ang = np.degrees(np.arccos(np.clip((q[idx] @ q.T - 1) / 2, -1, 1)))
+    ang[np.arange(len(idx)), idx] = 1e9
+    nn = ang.min(1)
+    assert nn.min() > 4.0 and nn.max() < 10.0
+    mean_angle = np.degrees(np.arccos(np.clip((np.trace(R, axis1=1, axis2=2) - 1) / 2, -1, 1))).mean()
+    assert abs(mean_angle - 126.5) < 1.0          # Haar: pi/2 + 2/pi
