@@ -128,9 +128,10 @@ AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat,
   if (st != AHV_OK) return st;
   if ((int64_t)B * N == 0) return AHV_OK;
 
-  const size_t need_scores = scores ? 0 : align_up((size_t)B * (size_t)N * sizeof(float), 256);
-  const size_t need_topk = k > 0 ? align_up(topk_workspace_bytes(B, N, k), 256) : 0;
-  const size_t need_tc = math_mode == AHV_MATH_TC ? align_up(score_tc_workspace_bytes(B, N), 256) : 0;
+  // fixed layout [scores | top-k partials | tensor-core scratch], shared with ahv_verify
+  const size_t need_scores = align_up((size_t)B * (size_t)N * sizeof(float), 256);
+  const size_t need_topk = align_up(topk_workspace_bytes(B, N, k > 0 ? k : 1), 256);
+  const size_t need_tc = align_up(score_tc_workspace_bytes(B, N), 256);
   if (need_scores + need_topk + need_tc > 0 && !workspace) return AHV_EWORKSPACE;
   if (workspace_bytes < need_scores + need_topk + need_tc) return AHV_EWORKSPACE;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -147,6 +148,43 @@ AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat,
                          ws_tc, need_tc, s);
   if (st != AHV_OK) return st;
   if (k > 0) st = launch_topk(sc, B, N, k, idx_offset, topk_val, topk_idx, ws_topk, need_topk, s);
+  return st;
+}
+
+AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
+                       const float* W1, const float* W2, const float* b2, const float* base, float* scores,
+                       float* topk_val, int64_t* topk_idx, float* R_best, int k, int64_t idx_offset, int B,
+                       int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || N < 0 || N > 0x7fffffffLL || k < 1 || k > kMaxK) return AHV_EINVAL;
+  if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
+  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32) return AHV_EINVAL;
+  if ((int64_t)B * N > 0 && (!vol_src || !vol_tgt || !R || !W1 || !W2 || !b2 || !base || !topk_val || !topk_idx))
+    return AHV_EINVAL;
+  if (!aligned16(vol_src) || !aligned16(vol_tgt) || !aligned16(R) || !aligned16(W1) || !aligned16(W2) ||
+      !aligned16(workspace))
+    return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  if ((int64_t)B * N == 0) return AHV_OK;
+  if (!workspace || workspace_bytes < ahv_workspace_bytes(B, N, k)) return AHV_EWORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  // workspace = [scores | top-k partials | tensor-core scratch (packed weights, target features, scales, keys)]
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const size_t off_topk = align_up((size_t)B * (size_t)N * sizeof(float), 256);
+  const size_t off_tc = off_topk + align_up(topk_workspace_bytes(B, N, k), 256);
+  void* ws_tc = ws + off_tc;
+  if (math_mode == AHV_MATH_TC && k == 1)  // three launches, nothing but 40 B per hypothesis touches HBM
+    return launch_verify_tc_argmax(vol_src, vol_dtype, vol_tgt, R, r_per_pair != 0, W1, W2, b2, base, scores,
+                                   topk_val, topk_idx, R_best, idx_offset, B, N, ws_tc,
+                                   workspace_bytes - off_tc, s);
+  float* tgt = scratch_tgt_feat(ws_tc, B);
+  st = launch_forward_3d2d(vol_tgt, W1, W2, b2, tgt, B, s);
+  if (st != AHV_OK) return st;
+  st = ahv_score(vol_src, vol_dtype, tgt, R, r_per_pair, W1, W2, b2, base, scores, topk_val, topk_idx, k,
+                 idx_offset, B, N, math_mode, workspace, workspace_bytes, stream);
+  if (st != AHV_OK) return st;
+  if (R_best)
+    st = launch_gather_rotations(R, r_per_pair != 0, topk_idx, idx_offset, B, N, k, R_best, s);
   return st;
 }
 
@@ -203,12 +241,9 @@ AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_hos
     if (cudaMemcpyAsync(d_W2, W2_host, kO * kO * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (cudaMemcpyAsync(d_b2, b2_host, kO * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (cudaMemcpyAsync(d_base, base_host, 8 * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
-    st = launch_forward_3d2d(d_tgt, d_W1, d_W2, d_b2, d_feat, B, s);
-    if (st != AHV_OK) break;
-    st = ahv_score(d_src, AHV_VOL_F32, d_feat, d_R, r_per_pair, d_W1, d_W2, d_b2, d_base, nullptr,
-                   d_val, d_idx, k, 0, B, N, math_mode, d_ws, ws_b, stream);
-    if (st != AHV_OK) break;
-    st = launch_gather_rotations(d_R, r_per_pair != 0, d_idx, 0, B, N, k, d_Rb, s);
+    st = ahv_verify(d_src, AHV_VOL_F32, d_tgt, d_R, r_per_pair, d_W1, d_W2, d_b2, d_base,
+                    scores_host ? (float*)d_ws : nullptr, d_val, d_idx, d_Rb, k, 0, B, N, math_mode, d_ws, ws_b,
+                    stream);
     if (st != AHV_OK) break;
     st = AHV_ECUDA;
     if (scores_host &&

@@ -66,6 +66,22 @@ __device__ __forceinline__ Tap make_tap(const float* R, float x, float y, float 
   return t;
 }
 
+// (score, index) -> one ordered 64-bit key: larger key = higher score, ties -> lower index
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 make_key(float score, uint32_t idx) {
+  uint32_t u = __float_as_uint(score + 0.0f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((u64)u << 32) | (u64)(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float key_score(u64 key) {
+  uint32_t u = (uint32_t)(key >> 32);
+  u = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint32_t key_index(u64 key) { return 0xFFFFFFFFu - (uint32_t)key; }
+
+
 // Launch-side helpers implemented in the .cu files --------------------------
 int launch_so3_from_normals(const float* normals, float* R, int64_t n, cudaStream_t s);
 int launch_so3_sample(uint64_t seed, int64_t first, float* R, int64_t n, cudaStream_t s);
@@ -82,6 +98,12 @@ int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, c
                     const float* base, float* scores, int B, int64_t N, void* ws, size_t ws_bytes,
                     cudaStream_t s);
 size_t score_tc_workspace_bytes(int B, int64_t N);
+float* scratch_tgt_feat(void* ws, int B);  // [B,32,64] slot inside the tensor-core scratch
+int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R,
+                            int r_per_pair, const float* W1, const float* W2, const float* b2,
+                            const float* base, float* scores, float* best_val, int64_t* best_idx,
+                            float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
+                            cudaStream_t s);
 int launch_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* val,
                 int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t topk_workspace_bytes(int B, int64_t N, int k);

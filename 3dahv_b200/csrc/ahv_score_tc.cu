@@ -33,7 +33,7 @@
 // The source volume is pre-scaled per pair by a power of two (exact) so fp16
 // can neither overflow nor go subnormal; the scale is undone after conv2
 // (ReLU and the bias-free conv1 are positively homogeneous).
-#include "ahv_common.cuh"
+#include "ahv_head_fp32.cuh"
 
 namespace ahv {
 
@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_feat,
                 const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
                 const float* __restrict__ base, const uint4* __restrict__ w_packed,
-                const float2* __restrict__ pair_scale, float* __restrict__ scores, int B, int64_t N) {
+                const float2* __restrict__ pair_scale, float* __restrict__ scores,
+                u64* __restrict__ best_keys, int B, int64_t N) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Work work;
@@ -411,6 +412,11 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     int prev_b = 0, prev_cnt = 0;
     int64_t prev_n0 = 0;
     float prev_inv = 1.0f;
+    // arg-max fused into the epilogue (torch.max, modules/model.py:195): the two score-writing
+    // lanes keep a running best key for the pair they are in and publish it with one
+    // atomicMax per (CTA, pair) - keys order by score, ties by lowest index
+    int key_b = -1;
+    u64 key_best = 0;
     auto phase_b = [&](uint32_t gg, int pb, int64_t pn0, int pcnt, float pinv) {
       const uint32_t gb = gg & 1, u = gg >> 1;
       mbar_wait(bar0 + (kD2Full + gb) * 8, u & 1);
@@ -434,7 +440,18 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       if (s == 0 && lane < pcnt) {
         const float* pp = partial + (gb * 2 + lane) * 4;
         const float tot = ((pp[0] + pp[1]) + pp[2]) + pp[3];
-        scores[(size_t)pb * N + pn0 + lane] = tot * (1.0f / 64.0f);  // .mean(dim=-1)
+        const float sc = tot * (1.0f / 64.0f);  // .mean(dim=-1)
+        if (scores) scores[(size_t)pb * N + pn0 + lane] = sc;
+        if (best_keys) {
+          const u64 key = make_key(sc, (uint32_t)(pn0 + lane));
+          if (pb != key_b) {
+            if (key_b >= 0) atomicMax(best_keys + key_b, key_best);
+            key_b = pb;
+            key_best = key;
+          } else if (key > key_best) {
+            key_best = key;
+          }
+        }
       }
     };
     while (it.advance()) {
@@ -476,6 +493,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       ++g;
     }
     phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+    if (best_keys && key_b >= 0) atomicMax(best_keys + key_b, key_best);
   }
 
   // ---- teardown ----
@@ -487,26 +505,45 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   }
 }
 
-// ---- weight packing + per-pair scale (one small launch before the main kernel) ----
-// w_packed: conv1 B operand, 24 slices j=(view,kk): [chalf][ngroup][n%8][c%8] fp16, then conv2 B operand.
+// ---- prologue: one launch, three independent jobs running concurrently -------------------
+//   block 0        : pack W1/W2 to fp16 in the UMMA B-operand layouts; clear the arg-max keys
+//   blocks 1..B    : per-pair power-of-two scale
+//   blocks B+1..2B : target features forward_3d2d(vol_tgt[b]) (modules/model.py:191), fp32 FFMA
+// w_packed: conv1 B operand, 24 slices j=(view,kk): [chalf][ngroup][n%8][c%8] fp16, then conv2's.
 template <typename T>
-__global__ void __launch_bounds__(256)
-tc_prep_kernel(const T* __restrict__ vol_src, const float* __restrict__ W1, const float* __restrict__ W2,
-               __half* __restrict__ w_packed, float2* __restrict__ pair_scale) {
+__global__ void __launch_bounds__(kThreads, 1)
+tc_prologue_kernel(const T* __restrict__ vol_src, const float* __restrict__ vol_tgt,
+                   const float* __restrict__ W1, const float* __restrict__ W2,
+                   const float* __restrict__ b2, __half* __restrict__ w_packed,
+                   float2* __restrict__ pair_scale, u64* __restrict__ best_keys,
+                   float* __restrict__ tgt_feat, int B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[8];
   __shared__ float l1max_s;
   const int t = threadIdx.x;
   if (blockIdx.x == 0) {
-    for (int i = t; i < kO * kK; i += 256) {
+    for (int i = t; i < kO * kK; i += kThreads) {
       const int n = i / kK, k = i % kK;
       const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7;
       const int j = view * 8 + kk;
       w_packed[j * 512 + (c >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (c & 7)] = __float2half_rn(W1[i]);
     }
-    for (int i = t; i < kO * kO; i += 256) {
+    for (int i = t; i < kO * kO; i += kThreads) {
       const int n = i / kO, k = i % kO;
       w_packed[kW1Bytes / 2 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2half_rn(W2[i]);
     }
+    if (best_keys)
+      for (int i = t; i < B; i += kThreads) best_keys[i] = 0ull;
+    return;
+  }
+  if ((int)blockIdx.x > B) {  // target features
+    Fp32Smem& sm = *reinterpret_cast<Fp32Smem*>(smem_raw);
+    const int b = blockIdx.x - 1 - B;
+    stage_weights(sm, W1, W2, nullptr);
+    float b2r[8];
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo) b2r[oo] = b2[(t & 3) * 8 + oo];
+    forward_3d2d_block<float>(sm, vol_tgt + (size_t)b * kC * kVox, b2r, tgt_feat + (size_t)b * kO * kP);
     return;
   }
   const int b = blockIdx.x - 1;
@@ -531,7 +568,7 @@ tc_prep_kernel(const T* __restrict__ vol_src, const float* __restrict__ W1, cons
   }
   float mx = 0.0f;
   const T* v = vol_src + (size_t)b * kC * kVox;
-  for (int i = t; i < kC * kVox; i += 256) mx = fmaxf(mx, fabsf(ld_vol<T>(v + i)));
+  for (int i = t; i < kC * kVox; i += kThreads) mx = fmaxf(mx, fabsf(ld_vol<T>(v + i)));
 #pragma unroll
   for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
   __syncthreads();
@@ -552,41 +589,116 @@ tc_prep_kernel(const T* __restrict__ vol_src, const float* __restrict__ W1, cons
   }
 }
 
+// decode the arg-max keys: (score, global index, sampled_R[pred_index]) per pair (modules/model.py:195-196)
+__global__ void __launch_bounds__(128)
+tc_finalize_kernel(const u64* __restrict__ best_keys, const float* __restrict__ R, int r_per_pair,
+                   int64_t idx_offset, int B, int64_t N, float* __restrict__ val,
+                   int64_t* __restrict__ idx, float* __restrict__ R_best) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const u64 key = best_keys[b];
+  const uint32_t n = key_index(key);
+  val[b] = key_score(key);
+  idx[b] = (int64_t)n + idx_offset;
+  if (R_best) {
+    const float* src = R + ((r_per_pair ? (size_t)b * N : 0) + (size_t)n) * 9;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) R_best[b * 9 + e] = src[e];
+  }
+}
+
+struct Scratch {  // carve-up of the tensor-core path's workspace
+  __half* w_packed;
+  float2* pair_scale;
+  u64* best_keys;
+  float* tgt_feat;
+};
+__host__ inline size_t scratch_bytes(int B) {
+  return (size_t)(kW1Bytes + kW2Bytes) + (size_t)B * (sizeof(float2) + sizeof(u64)) + (size_t)B * kO * kP * 4 + 256;
+}
+__host__ inline Scratch carve(void* ws, int B) {
+  unsigned char* p = static_cast<unsigned char*>(ws);
+  Scratch sc;
+  sc.w_packed = reinterpret_cast<__half*>(p);
+  p += kW1Bytes + kW2Bytes;
+  sc.tgt_feat = reinterpret_cast<float*>(p);
+  p += (size_t)B * kO * kP * 4;
+  sc.pair_scale = reinterpret_cast<float2*>(p);
+  p += (size_t)B * sizeof(float2);
+  sc.best_keys = reinterpret_cast<u64*>(p);
+  return sc;
+}
+
+template <typename T>
+int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_in, const float* R,
+                 int r_per_pair, const float* W1, const float* W2, const float* b2, const float* base,
+                 float* scores, bool want_argmax, int B, int64_t N, const Scratch& sc, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  AHV_CUDA_OK(cudaGetDevice(&dev));
+  AHV_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int pro_blocks = 1 + B + (vol_tgt ? B : 0);
+  const size_t pro_smem = vol_tgt ? sizeof(Fp32Smem) : 0;
+  AHV_CUDA_OK(cudaFuncSetAttribute(tc_prologue_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(Fp32Smem)));
+  tc_prologue_kernel<T><<<pro_blocks, kThreads, pro_smem, s>>>(vol_src, vol_tgt, W1, W2, b2, sc.w_packed,
+                                                              sc.pair_scale, want_argmax ? sc.best_keys : nullptr,
+                                                              sc.tgt_feat, B);
+  AHV_CUDA_OK(cudaGetLastError());
+  // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
+  const int64_t tiles = ((int64_t)B * N + 1) / 2;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  score_tc_kernel<T><<<grid, kThreadsTC, kSmemBytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,
+                                                         b2, base, (const uint4*)sc.w_packed, sc.pair_scale, scores,
+                                                         want_argmax ? sc.best_keys : nullptr, B, N);
+  AHV_CUDA_OK(cudaGetLastError());
+  return AHV_OK;
+}
+
 }  // namespace tc
 
 size_t score_tc_workspace_bytes(int B, int64_t N) {
   (void)N;
-  return (size_t)(tc::kW1Bytes + tc::kW2Bytes) + (size_t)B * sizeof(float2) + 256;
+  return tc::scratch_bytes(B);
 }
 
+float* scratch_tgt_feat(void* ws, int B) { return tc::carve(ws, B).tgt_feat; }
+
+// scores only (target features supplied by the caller)
 int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
                     int r_per_pair, const float* W1, const float* W2, const float* b2,
                     const float* base, float* scores, int B, int64_t N, void* ws, size_t ws_bytes,
                     cudaStream_t s) {
-  const int64_t total = (int64_t)B * N;
-  if (total == 0) return AHV_OK;
-  if (ws_bytes < score_tc_workspace_bytes(B, N)) return AHV_EWORKSPACE;
-  int dev = 0, sms = 0;
-  AHV_CUDA_OK(cudaGetDevice(&dev));
-  AHV_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  __half* w_packed = reinterpret_cast<__half*>(ws);
-  float2* pair_scale = reinterpret_cast<float2*>(static_cast<unsigned char*>(ws) + tc::kW1Bytes + tc::kW2Bytes);
-  // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
-  const int64_t tiles = (total + 1) / 2;
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  if (vol_dtype == AHV_VOL_F32) {
-    tc::tc_prep_kernel<float><<<B + 1, 256, 0, s>>>((const float*)vol_src, W1, W2, w_packed, pair_scale);
-    AHV_CUDA_OK(cudaGetLastError());
-    AHV_CUDA_OK(cudaFuncSetAttribute(tc::score_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-    tc::score_tc_kernel<float><<<grid, tc::kThreadsTC, tc::kSmemBytes, s>>>(
-        (const float*)vol_src, tgt_feat, R, r_per_pair, b2, base, (const uint4*)w_packed, pair_scale, scores, B, N);
-  } else {
-    tc::tc_prep_kernel<__nv_bfloat16><<<B + 1, 256, 0, s>>>((const __nv_bfloat16*)vol_src, W1, W2, w_packed, pair_scale);
-    AHV_CUDA_OK(cudaGetLastError());
-    AHV_CUDA_OK(cudaFuncSetAttribute(tc::score_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-    tc::score_tc_kernel<__nv_bfloat16><<<grid, tc::kThreadsTC, tc::kSmemBytes, s>>>(
-        (const __nv_bfloat16*)vol_src, tgt_feat, R, r_per_pair, b2, base, (const uint4*)w_packed, pair_scale, scores, B, N);
-  }
+  if ((int64_t)B * N == 0) return AHV_OK;
+  if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
+  const tc::Scratch sc = tc::carve(ws, B);
+  if (vol_dtype == AHV_VOL_F32)
+    return tc::launch_typed<float>((const float*)vol_src, nullptr, tgt_feat, R, r_per_pair, W1, W2, b2, base,
+                                   scores, false, B, N, sc, s);
+  return tc::launch_typed<__nv_bfloat16>((const __nv_bfloat16*)vol_src, nullptr, tgt_feat, R, r_per_pair, W1, W2,
+                                         b2, base, scores, false, B, N, sc, s);
+}
+
+// the whole verification step with arg-max selection in three launches:
+// prologue (weights, scales, target features) -> fused scoring + arg-max -> finalize
+int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R,
+                            int r_per_pair, const float* W1, const float* W2, const float* b2,
+                            const float* base, float* scores, float* best_val, int64_t* best_idx,
+                            float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
+                            cudaStream_t s) {
+  if ((int64_t)B * N == 0) return AHV_OK;
+  if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
+  const tc::Scratch sc = tc::carve(ws, B);
+  int st;
+  if (vol_dtype == AHV_VOL_F32)
+    st = tc::launch_typed<float>((const float*)vol_src, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2, base, scores,
+                                 true, B, N, sc, s);
+  else
+    st = tc::launch_typed<__nv_bfloat16>((const __nv_bfloat16*)vol_src, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2,
+                                         base, scores, true, B, N, sc, s);
+  if (st != AHV_OK) return st;
+  tc::tc_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(sc.best_keys, R, r_per_pair, idx_offset, B, N, best_val,
+                                                         best_idx, R_best);
   AHV_CUDA_OK(cudaGetLastError());
   return AHV_OK;
 }

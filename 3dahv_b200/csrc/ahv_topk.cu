@@ -12,20 +12,6 @@
 
 namespace ahv {
 
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 make_key(float score, uint32_t idx) {
-  uint32_t u = __float_as_uint(score + 0.0f);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  return ((u64)u << 32) | (u64)(0xFFFFFFFFu - idx);
-}
-__device__ __forceinline__ float key_score(u64 key) {
-  uint32_t u = (uint32_t)(key >> 32);
-  u = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ uint32_t key_index(u64 key) { return 0xFFFFFFFFu - (uint32_t)key; }
-
 __device__ __forceinline__ u64 umax64(u64 a, u64 b) { return a > b ? a : b; }
 __device__ __forceinline__ u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
 

@@ -157,6 +157,47 @@ def score(vol_src, tgt_feat, R, W1, W2, b2, k: int = 1, idx_offset: int = 0, mat
     return scores, val, idx
 
 
+def verify(vol_src, vol_tgt, R, W1, W2, b2, k: int = 1, idx_offset: int = 0, math: int = MATH_TC,
+           return_scores: bool = False, gather: bool = True, workspace: torch.Tensor | None = None):
+    """ahv_verify: target features + fused scoring + selection + winner gather in one C call.
+    Returns (scores|None, topk_val [B,k], topk_idx [B,k], R_best [B,k,3,3]|None)."""
+    if vol_src.dtype == torch.bfloat16:
+        vs, vdt = _dev(vol_src, "vol_src", torch.bfloat16), VOL_BF16
+    else:
+        vs, vdt = _dev(vol_src, "vol_src"), VOL_F32
+    vt = _dev(vol_tgt, "vol_tgt")
+    B = vs.shape[0]
+    if tuple(vs.shape[1:]) != (16, 8, 8, 8) or tuple(vt.shape) != (B, 16, 8, 8, 8):
+        raise ValueError("vol_src / vol_tgt must be [B,16,8,8,8]")
+    R = _dev(R, "R")
+    per_pair = R.dim() == 4
+    if per_pair and R.shape[0] != B:
+        raise ValueError("per-pair R must be [B,N,3,3]")
+    if tuple(R.shape[-2:]) != (3, 3):
+        raise ValueError("R must be [...,3,3]")
+    N = R.shape[1] if per_pair else R.shape[0]
+    if k < 1 or k > 32:
+        raise ValueError("k must be in [1,32]")
+    W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
+    dev = vs.device
+    scores = torch.empty(B, N, device=dev, dtype=torch.float32) if return_scores else None
+    val = torch.empty(B, k, device=dev, dtype=torch.float32)
+    idx = torch.empty(B, k, device=dev, dtype=torch.int64)
+    Rb = torch.empty(B, k, 3, 3, device=dev, dtype=torch.float32) if gather else None
+    need = workspace_bytes(B, N, k)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    base = base_coords(dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().ahv_verify(
+            vs.data_ptr(), vdt, vt.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+            base.data_ptr(), scores.data_ptr() if scores is not None else None, val.data_ptr(), idx.data_ptr(),
+            Rb.data_ptr() if Rb is not None else None, k, idx_offset, B, N, math, workspace.data_ptr(),
+            workspace.numel() * workspace.element_size(), _stream(vs))
+    _lib.check(st, "ahv_verify")
+    return scores, val, idx, Rb
+
+
 def topk(scores: torch.Tensor, k: int, idx_offset: int = 0):
     """torch.max / top-k with the reference's tie rule (lowest index wins)."""
     s = _dev(scores, "scores")

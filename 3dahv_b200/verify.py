@@ -71,8 +71,6 @@ class HypothesisVerifier:
         """vol_src/vol_tgt [B,16,8,8,8]; R [N,3,3] shared or [B,N,3,3] per pair."""
         dev = vol_src.device
         W1, W2, b2 = self._weights_on(dev)
-        if tgt_feat is None:
-            tgt_feat = self.target_features(vol_tgt)
         per_pair = R.dim() == 4
         N = R.shape[1] if per_pair else R.shape[0]
         B = vol_src.shape[0]
@@ -80,8 +78,14 @@ class HypothesisVerifier:
             raise ValueError("empty hypothesis set")
         k = min(k, N)
         vs = vol_src if vol_src.dtype == torch.bfloat16 else vol_src.float()
+        ws = self._workspace(B, N, k, dev)
+        if tgt_feat is None:   # one C call for the whole step (3 launches when k == 1)
+            scores, val, idx, R_best = ops.verify(vs, vol_tgt.float(), R, W1, W2, b2, k=k, idx_offset=idx_offset,
+                                                  math=self.math, return_scores=return_scores, gather=gather,
+                                                  workspace=ws)
+            return VerifyResult(scores, val, idx, R_best)
         scores, val, idx = ops.score(vs, tgt_feat, R, W1, W2, b2, k=k, idx_offset=idx_offset, math=self.math,
-                                     return_scores=return_scores, workspace=self._workspace(B, N, k, dev))
+                                     return_scores=return_scores, workspace=ws)
         R_best = ops.gather_rotations(R, idx, idx_offset) if gather else None
         return VerifyResult(scores, val, idx, R_best)
 

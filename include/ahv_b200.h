@@ -108,6 +108,17 @@ AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat,
               float* scores, float* topk_val, int64_t* topk_idx, int k, int64_t idx_offset, int B,
               int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The whole verification step of modules/model.py:186-196 / test_co3d.py:137-146 in one call:
+ * target features of vol_tgt [B,16,8,8,8] (fp32), fused scoring of every (pair, hypothesis),
+ * selection and sampled_R[pred_index].  With AHV_MATH_TC and k==1 (the reference's torch.max) this
+ * is three launches — prologue (weight packing, per-pair scale, target features, concurrently),
+ * the fused scoring kernel with the arg-max folded into its epilogue, and a finalize kernel.
+ * scores [B,N] or NULL; topk_val/topk_idx [B,k]; R_best [B,k,3,3] or NULL. */
+AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
+                       const float* W1, const float* W2, const float* b2, const float* base, float* scores,
+                       float* topk_val, int64_t* topk_idx, float* R_best, int k, int64_t idx_offset, int B,
+                       int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream);
+
 /* torch.max / top-k over an existing score matrix (modules/model.py:195). */
 AHV_API int ahv_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* topk_val,
              int64_t* topk_idx, void* workspace, size_t workspace_bytes, void* stream);

@@ -293,3 +293,34 @@ def test_refcompat_idiom(ahv, golden):
     s, idx, Rbest = ahv.refcompat.verify(fa, vs, vt, R)
     assert _relerr(s.cpu().numpy(), g["scores"][:, :200]) <= TOL["tc"]
     assert torch.equal(Rbest, R[idx])
+
+
+@pytest.mark.parametrize("B,N", [(1, 1), (1, 3000), (3, 37), (32, 999)])
+def test_fused_verify_argmax_equals_generic_path(ahv, golden, B, N):
+    """ahv_verify with k=1 (arg-max folded into the scoring epilogue, 3 launches) must agree bit for
+    bit with scores + separate top-k, including ties and the odd-tail tile."""
+    dev = _dev()
+    w = golden["weights"]
+    gen = torch.Generator().manual_seed(B * 1000 + N)
+    vs = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+    vt = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+    R = ahv.so3.sample_rotations(N, seed=N, device=dev)
+    if N > 10:
+        R[N // 2] = R[3]                       # exact tie: the lower index must win
+    v = ahv.HypothesisVerifier(*_weights(golden, dev))
+    fused = v.score(vs, vt, R, k=1, return_scores=True)
+    fused_noscores = v.score(vs, vt, R, k=1, return_scores=False)
+    tgt = v.target_features(vt)
+    generic = v.score(vs, vt, R, k=1, return_scores=True, tgt_feat=tgt)
+    assert torch.equal(fused.scores, generic.scores)
+    assert torch.equal(fused.topk_idx, generic.topk_idx) and torch.equal(fused.topk_val, generic.topk_val)
+    assert torch.equal(fused_noscores.topk_idx, generic.topk_idx) and torch.equal(fused_noscores.R_best, generic.R_best)
+    assert torch.equal(fused.topk_idx[:, 0], fused.scores.argmax(1))
+    assert torch.equal(fused.R_best[:, 0], R[fused.topk_idx[:, 0]])
+    # per-pair rotations and idx_offset
+    Rp = torch.stack([ahv.so3.sample_rotations(N, seed=b, device=dev) for b in range(B)])
+    fp = v.score(vs, vt, Rp, k=1, return_scores=True, idx_offset=1000)
+    gp = v.score(vs, vt, Rp, k=1, return_scores=True, tgt_feat=tgt, idx_offset=1000)
+    assert torch.equal(fp.scores, gp.scores) and torch.equal(fp.topk_idx, gp.topk_idx)
+    assert torch.equal(fp.topk_idx[:, 0] - 1000, fp.scores.argmax(1))
+    assert torch.equal(fp.R_best[:, 0], Rp[torch.arange(B), fp.topk_idx[:, 0] - 1000])
