@@ -49,6 +49,24 @@ def load_peaks():
             "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the score kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/); None if the summary is absent."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_score_tc_summary.csv")))
+    if not files:
+        return None
+    rd = wr = None
+    for row in csv.reader(l for l in open(files[-1]) if not l.startswith("#")):
+        if len(row) >= 4 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row[1], 1.0)
+            v = float(row[-1]) * scale
+            rd, wr = (v, wr) if row[0].endswith("read.sum") else (rd, v)
+    return None if rd is None or wr is None else {"bytes_per_launch": rd + wr, "source": os.path.basename(files[-1]),
+                                                  "algorithmic_hbm_bytes_per_launch": HBM_BYTES_PER_HYP * PAIRS * HYPS}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
@@ -180,18 +198,17 @@ def run_ours(args):
     launches = {"n": 0}
 
     def step():
+        if world == 1:   # ahv_verify: prologue + fused score/arg-max + finalize = 3 launches
+            r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=0, gather=True)
+            launches["n"] += 3
+            return r.topk_val, r.topk_idx, r.R_best
         r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=rank * N, gather=False)
-        launches["n"] += 4                       # forward_3d2d, score, topk_slice, topk_final
-        val, idx = r.topk_val, r.topk_idx
-        if world > 1:
-            vals, idxs = ahv.dist.all_gather_topk(val, idx)
-            val, idx = ahv.ops.topk_merge(vals, idxs)
-            launches["n"] += 1
-            own = (idx >= rank * N) & (idx < (rank + 1) * N)
-            Rb = ahv.ops.gather_rotations(R, torch.where(own, idx, torch.full_like(idx, rank * N)), rank * N)
-        else:
-            Rb = ahv.ops.gather_rotations(R, idx, 0)
-        launches["n"] += 1
+        launches["n"] += 3
+        vals, idxs = ahv.dist.all_gather_topk(r.topk_val, r.topk_idx)
+        val, idx = ahv.ops.topk_merge(vals, idxs)
+        own = (idx >= rank * N) & (idx < (rank + 1) * N)
+        Rb = ahv.ops.gather_rotations(R, torch.where(own, idx, torch.full_like(idx, rank * N)), rank * N)
+        launches["n"] += 2                       # merge + winner gather (NCCL kernels not counted)
         return val, idx, Rb
 
     def barrier():
@@ -303,7 +320,7 @@ def run_ours(args):
                 "bound": "smem", "kernel": "score (fused rotate+head+correlate)", "achieved": gather_gbs,
                 "peak": smem_peak_gbs, "unit": "GB/s", "frac": gather_gbs / smem_peak_gbs,
                 "peak_source": "measured in this run (ahv_diag_smem_read, conflict-free LDS.128)",
-                "nominal_peak": nominal_smem, "kernel_ms": kernel_ms, "traffic": None,
+                "nominal_peak": nominal_smem, "kernel_ms": kernel_ms, "traffic": ncu_traffic(),
                 "algorithmic_bytes_per_unit": GATHER_BYTES_PER_HYP,
                 "alt": {
                     "hbm": {"achieved": hyp_per_s_kernel * HBM_BYTES_PER_HYP / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
