@@ -48,26 +48,38 @@ constexpr int kStages = 3;
 // ---- shared memory map (bytes) ----
 constexpr int kW1Bytes = 24 * 1024;  // 24 MMA slices x [2 chalf][4 ngroup][8][8] fp16
 constexpr int kW2Bytes = 2 * 1024;
-// A operand of conv1, two dense copies of the rotated volume in fp16 (8-row x 16-byte core matrices):
-//   copy YZ: CM(d,h,chalf) = [w][c8] at chalf*kCh + d*1024 + h*128   (views y and z)
-//   copy X : CM(d,w,chalf) = [h][c8] at chalf*kCh + d*1024 + w*128   (view x)
-// the second channel-half block is shifted by 64 B so the gather's STS.64 are conflict-free
-constexpr int kCh = 8192 + 64;
-constexpr int kCopyBytes = kCh + 8192;       // 16448
-constexpr int kStageBytes = 2 * kCopyBytes;  // 32896
+// A operand of conv1, two fp16 copies of the rotated volume (8-row x 16-byte core matrices):
+//   copy YZ: CM(d,h,chalf) = [w][c8] at chalf*yz_ch + d*yz_d + h*yz_h   (views y and z)
+//   copy X : CM(d,w,chalf) = [h][c8] at chalf*x_ch  + d*1024 + w*128    (view x)
+// Strides are chosen so that the gather's stores are bank-conflict-free for its lane map:
+//   fp32 volumes (STS.64 per 4-channel chunk): dense, second channel-half block shifted by 64 B;
+//   16-bit volumes (STS.128 per 8-channel chunk): YZ rows padded 128 -> 160 B.
+template <bool K16>
+struct Map {
+  static constexpr int yz_h = K16 ? 160 : 128;
+  static constexpr int yz_d = 8 * yz_h;
+  static constexpr int yz_ch = K16 ? 8 * yz_d : 8 * yz_d + 64;
+  static constexpr int yz_bytes = yz_ch + 8 * yz_d;
+  static constexpr int x_ch = 8192 + 64;
+  static constexpr int x_bytes = x_ch + 8192;
+  static constexpr int stage_bytes = ((yz_bytes + x_bytes + 127) / 128) * 128;
+  static constexpr int off_vol = 0;
+  static constexpr int off_w1 = off_vol + kVolSmemBytes;          // 64000
+  static constexpr int off_w2 = off_w1 + kW1Bytes;
+  static constexpr int off_a = off_w2 + kW2Bytes;
+  static constexpr int off_a2 = off_a + kStages * stage_bytes;
+  static constexpr int off_bar = off_a2 + 2 * 8192;
+  static constexpr int off_misc = off_bar + 16 * 8;               // tmem ptr, partial sums, base table
+  static constexpr int smem_bytes = off_misc + 256;
+  static_assert(off_w1 % 128 == 0 && off_a % 128 == 0 && off_a2 % 128 == 0 && off_bar % 8 == 0, "align");
+  static_assert(smem_bytes <= 232448, "shared memory budget");
+};
 constexpr int kA2Bytes = 8192;  // [4 kc][16 rowgroup][8][8] fp16
 
-constexpr int kOffVol = 0;
-constexpr int kOffW1 = kOffVol + kVolSmemBytes;       // 64000
-constexpr int kOffW2 = kOffW1 + kW1Bytes;             // 88576
-constexpr int kOffA = kOffW2 + kW2Bytes;              // 90624
-constexpr int kOffA2 = kOffA + kStages * kStageBytes; // 195840
-constexpr int kOffBar = kOffA2 + 2 * kA2Bytes;        // 212224
-constexpr int kNumBars = 3 + 3 + 2 + 2 + 2 + 2;
-constexpr int kOffMisc = kOffBar + kNumBars * 8;      // tmem ptr, partial sums, base table
-constexpr int kSmemBytes = kOffMisc + 256;
-static_assert(kOffW1 % 128 == 0 && kOffA % 128 == 0 && kOffA2 % 128 == 0 && kOffBar % 8 == 0, "align");
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+// 16-bit volumes are staged as "x-pair lines": for every (z, y, x0) of the halo'd grid one 64 B line
+// holding BOTH x taps (x0, x0+1) x 16 channels as bf16, chunk = tap*2 + chalf.  A tap pair is then
+// four LDS.128 and the gather reads half the bytes of the fp32 layout.
+static_assert(kHalo * kHalo * 9 * 64 <= kVolSmemBytes, "pair lines (900 x 64 B) fit the volume region");
 
 enum Bar { kFull = 0, kEmpty = 3, kD1Full = 6, kD1Empty = 8, kA2Full = 10, kD2Full = 12 };
 
@@ -183,6 +195,10 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
                 const float2* __restrict__ pair_scale, float* __restrict__ scores,
                 u64* __restrict__ best_keys, int B, int64_t N) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr bool K16 = sizeof(T) == 2;  // bf16 volumes: 16-bit staging
+  using M = Map<K16>;
+  constexpr int kOffVol = M::off_vol, kOffW1 = M::off_w1, kOffW2 = M::off_w2, kOffA = M::off_a, kOffA2 = M::off_a2,
+                kOffBar = M::off_bar, kOffMisc = M::off_misc, kStageBytes = M::stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Work work;
   {
@@ -237,10 +253,16 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     uint32_t koff[4], syz[4], sx[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int ck = (rot + t) & 3;       // logical channel chunk (channels 4ck..4ck+3) held in acc[t]
+      const int ck = (rot + t) & 3;       // chunk visited at step t
       koff[t] = ck * 16;
-      syz[t] = (ck >> 1) * kCh + (ck & 1) * 8 + d * 1024 + hh * 128 + w * 16;
-      sx[t] = kCopyBytes + (ck >> 1) * kCh + (ck & 1) * 8 + d * 1024 + w * 128 + hh * 16;
+      if constexpr (!K16) {               // fp32: chunk = channels 4ck..4ck+3, held in acc[t]
+        syz[t] = (ck >> 1) * M::yz_ch + (ck & 1) * 8 + d * M::yz_d + hh * M::yz_h + w * 16;
+        sx[t] = M::yz_bytes + (ck >> 1) * M::x_ch + (ck & 1) * 8 + d * 1024 + w * 128 + hh * 16;
+      } else {                            // 16-bit: accumulator t&1 holds channel half (rot+t)&1; t<2 used
+        const int ca = (rot + t) & 1;
+        syz[t] = ca * M::yz_ch + d * M::yz_d + hh * M::yz_h + w * 16;
+        sx[t] = M::yz_bytes + ca * M::x_ch + d * 1024 + w * 128 + hh * 16;
+      }
     }
     const unsigned char* volb = smem + kOffVol;
     const int gtid = threadIdx.x;  // 0..255
@@ -260,16 +282,35 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
         named_bar_sync(1, kGatherWarps * 32);  // everyone is done reading the previous volume
         const T* vg = vol_src + (size_t)it.b * kC * kVox;
         const float sc = pair_scale[it.b].x;
-        for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
-          const int v = task & 511, jj = task >> 9;
-          const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
-          const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
-          float4 o;
-          o.x = ld_vol<T>(vg + (jj * 4 + 0) * kVox + v) * sc;
-          o.y = ld_vol<T>(vg + (jj * 4 + 1) * kVox + v) * sc;
-          o.z = ld_vol<T>(vg + (jj * 4 + 2) * kVox + v) * sc;
-          o.w = ld_vol<T>(vg + (jj * 4 + 3) * kVox + v) * sc;
-          *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
+        if constexpr (!K16) {
+          for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
+            const int v = task & 511, jj = task >> 9;
+            const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
+            const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
+            float4 o;
+            o.x = ld_vol<T>(vg + (jj * 4 + 0) * kVox + v) * sc;
+            o.y = ld_vol<T>(vg + (jj * 4 + 1) * kVox + v) * sc;
+            o.z = ld_vol<T>(vg + (jj * 4 + 2) * kVox + v) * sc;
+            o.w = ld_vol<T>(vg + (jj * 4 + 3) * kVox + v) * sc;
+            *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
+          }
+        } else {
+          // every voxel goes into two pair lines: as tap 0 of pair x0h = xh and as tap 1 of pair xh-1
+          for (int task = gtid; task < 2 * kVox; task += kGatherWarps * 32) {
+            const int v = task & 511, chalf = task >> 9;
+            const int zh = (v >> 6) + 1, yh = ((v >> 3) & 7) + 1, xh = (v & 7) + 1;
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {  // power-of-two scale: exact in bf16
+              const __nv_bfloat162 two = __floats2bfloat162_rn(ld_vol<T>(vg + (chalf * 8 + 2 * e) * kVox + v) * sc,
+                                                               ld_vol<T>(vg + (chalf * 8 + 2 * e + 1) * kVox + v) * sc);
+              pk[e] = *reinterpret_cast<const uint32_t*>(&two);
+            }
+            const uint4 q4 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            unsigned char* row = smem + kOffVol + ((zh * kHalo + yh) * 9) * 64;
+            *reinterpret_cast<uint4*>(row + xh * 64 + chalf * 16) = q4;              // tap 0 of pair xh (xh <= 8)
+            *reinterpret_cast<uint4*>(row + (xh - 1) * 64 + 32 + chalf * 16) = q4;   // tap 1 of pair xh-1
+          }
         }
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
@@ -299,52 +340,107 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
           ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
           const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
           const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
-          const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
-          const int swap = (line ^ pf) & 1;  // first x tap = the one whose 64 B line has bank parity pf
-          const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
-          const unsigned char* pa = volb + (line + swap) * 64;
-          const unsigned char* pb = volb + (line + 1 - swap) * 64;
-          float wa[4], wb[4];
+          if constexpr (!K16) {
+            const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
+            const int swap = (line ^ pf) & 1;  // first x tap = the one whose 64 B line has bank parity pf
+            const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
+            const unsigned char* pa = volb + (line + swap) * 64;
+            const unsigned char* pb = volb + (line + 1 - swap) * 64;
+            float wa[4], wb[4];
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float wyz = ((c & 1) ? fy : 1.0f - fy) * ((c >> 1) ? fz : 1.0f - fz);
+              wa[c] = wyz * wxa;
+              wb[c] = wyz * wxb;
+            }
+            // 4 chunk batches of 8 LDS.128 each, software-pipelined: batch t+1 is in flight
+            // while batch t is consumed (two register buffers)
+            float4 buf[2][8];
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {  // c = dz*2 + dy
+              const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+              buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
+              buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
+            }
+  #pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (t < 3) {
+  #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+                  buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
+                  buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+                }
+              }
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  #pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float4 a = buf[t & 1][2 * c], g = buf[t & 1][2 * c + 1];
+                acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
+                acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
+                acc.x = fmaf(wb[c], g.x, acc.x); acc.y = fmaf(wb[c], g.y, acc.y);
+                acc.z = fmaf(wb[c], g.z, acc.z); acc.w = fmaf(wb[c], g.w, acc.w);
+              }
+              const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi2 = __floats2half2_rn(acc.z, acc.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
+              *reinterpret_cast<uint2*>(st + syz[t] + e * (4 * M::yz_h)) = pk;  // h += 4
+              *reinterpret_cast<uint2*>(st + sx[t] + e * 64) = pk;
+            }
+          } else {
+            // ---- 16-bit staged volume: pair lines, both x taps per line ----
+            const int pline = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * 9 + ((int)x0 + 1);
+            const int swapy = (pline ^ pf) & 1;  // first y tap = the one whose line has bank parity pf (9 is odd)
+            const unsigned char* pa = volb + (pline + swapy * 9) * 64;
+            const unsigned char* pb = volb + (pline + (1 - swapy) * 9) * 64;
+            const float wya = swapy ? fy : 1.0f - fy, wyb = swapy ? 1.0f - fy : fy;
+            float w4[4];  // c = (y order)*2 + dz
+            w4[0] = wya * (1.0f - fz); w4[1] = wya * fz; w4[2] = wyb * (1.0f - fz); w4[3] = wyb * fz;
+            float wxt[4];  // x weight of the tap that chunk (rot+t)&3 belongs to (chunk = tap*2 + chalf)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float wyz = ((c & 1) ? fy : 1.0f - fy) * ((c >> 1) ? fz : 1.0f - fz);
-            wa[c] = wyz * wxa;
-            wb[c] = wyz * wxb;
-          }
-          // 4 chunk batches of 8 LDS.128 each, software-pipelined: batch t+1 is in flight
-          // while batch t is consumed (two register buffers)
-          float4 buf[2][8];
+            for (int t = 0; t < 4; ++t) wxt[t] = (((rot + t) & 3) >> 1) ? fx : 1.0f - fx;
+            float acc[2][8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {  // c = dz*2 + dy
-            const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
-            buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
-            buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
-          }
+            for (int e2 = 0; e2 < 8; ++e2) acc[0][e2] = acc[1][e2] = 0.0f;
+            uint4 buf[2][4];
+            constexpr int kDz = kHalo * 9 * 64;
+            buf[0][0] = *reinterpret_cast<const uint4*>(pa + koff[0]);
+            buf[0][1] = *reinterpret_cast<const uint4*>(pa + koff[0] + kDz);
+            buf[0][2] = *reinterpret_cast<const uint4*>(pb + koff[0]);
+            buf[0][3] = *reinterpret_cast<const uint4*>(pb + koff[0] + kDz);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            if (t < 3) {
+            for (int t = 0; t < 4; ++t) {
+              if (t < 3) {
+                buf[(t + 1) & 1][0] = *reinterpret_cast<const uint4*>(pa + koff[t + 1]);
+                buf[(t + 1) & 1][1] = *reinterpret_cast<const uint4*>(pa + koff[t + 1] + kDz);
+                buf[(t + 1) & 1][2] = *reinterpret_cast<const uint4*>(pb + koff[t + 1]);
+                buf[(t + 1) & 1][3] = *reinterpret_cast<const uint4*>(pb + koff[t + 1] + kDz);
+              }
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
-                buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
-                buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+                const float wg = wxt[t] * w4[c];
+                const uint4 q4 = buf[t & 1][c];
+                const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {  // bf16 -> fp32 is a shift / mask
+                  acc[t & 1][2 * k2] = fmaf(wg, __uint_as_float(wd[k2] << 16), acc[t & 1][2 * k2]);
+                  acc[t & 1][2 * k2 + 1] = fmaf(wg, __uint_as_float(wd[k2] & 0xffff0000u), acc[t & 1][2 * k2 + 1]);
+                }
               }
             }
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float4 a = buf[t & 1][2 * c], g = buf[t & 1][2 * c + 1];
-              acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
-              acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
-              acc.x = fmaf(wb[c], g.x, acc.x); acc.y = fmaf(wb[c], g.y, acc.y);
-              acc.z = fmaf(wb[c], g.z, acc.z); acc.w = fmaf(wb[c], g.w, acc.w);
+            for (int a2i = 0; a2i < 2; ++a2i) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const __half2 hh2 = __floats2half2_rn(acc[a2i][2 * k2], acc[a2i][2 * k2 + 1]);
+                pk[k2] = *reinterpret_cast<const uint32_t*>(&hh2);
+              }
+              const uint4 q4 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(st + syz[a2i] + e * (4 * M::yz_h)) = q4;  // h += 4
+              *reinterpret_cast<uint4*>(st + sx[a2i] + e * 64) = q4;
             }
-            const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi2 = __floats2half2_rn(acc.z, acc.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
-            *reinterpret_cast<uint2*>(st + syz[t] + e * 512) = pk;  // h += 4
-            *reinterpret_cast<uint2*>(st + sx[t] + e * 64) = pk;
           }
         }
         fence_proxy_async();  // make this thread's A-operand stores visible to the tensor core
@@ -380,13 +476,13 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
           const uint32_t d1 = tmem + ((uint32_t)(16 * sl) << 16) + gb * 32;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view x: rows (d,h), K slice = (w=kk, c)
-            umma_f16(d1, smem_desc(a + kCopyBytes + kk * 128, kCh, 1024), smem_desc(w1s + kk * 1024, 512, 128), idesc1, kk);
+            umma_f16(d1, smem_desc(a + M::yz_bytes + kk * 128, M::x_ch, 1024), smem_desc(w1s + kk * 1024, 512, 128), idesc1, kk);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view y: rows (d,w), K slice = (h=kk, c)
-            umma_f16(d1, smem_desc(a + kk * 128, kCh, 1024), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
+            umma_f16(d1, smem_desc(a + kk * M::yz_h, M::yz_ch, M::yz_d), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view z: rows (h,w), K slice = (d=kk, c)
-            umma_f16(d1, smem_desc(a + kk * 1024, kCh, 128), smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
+            umma_f16(d1, smem_desc(a + kk * M::yz_d, M::yz_ch, M::yz_h), smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
           umma_commit(bar0 + (kEmpty + stage) * 8);  // A stage may be overwritten once these MMAs retire
         }
         umma_commit(bar0 + (kD1Full + gb) * 8);
@@ -647,6 +743,7 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
   const int64_t tiles = ((int64_t)B * N + 1) / 2;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  constexpr int kSmemBytes = Map<sizeof(T) == 2>::smem_bytes;
   AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   score_tc_kernel<T><<<grid, kThreadsTC, kSmemBytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,
                                                          b2, base, (const uint4*)sc.w_packed, sc.pair_scale, scores,

@@ -63,8 +63,7 @@ def ncu_traffic():
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row[1], 1.0)
             v = float(row[-1]) * scale
             rd, wr = (v, wr) if row[0].endswith("read.sum") else (rd, v)
-    return None if rd is None or wr is None else {"bytes_per_launch": rd + wr, "source": os.path.basename(files[-1]),
-                                                  "algorithmic_hbm_bytes_per_launch": HBM_BYTES_PER_HYP * PAIRS * HYPS}
+    return None if rd is None or wr is None else rd + wr
 
 
 class ClockSampler:
@@ -320,7 +319,7 @@ def run_ours(args):
                 "bound": "smem", "kernel": "score (fused rotate+head+correlate)", "achieved": gather_gbs,
                 "peak": smem_peak_gbs, "unit": "GB/s", "frac": gather_gbs / smem_peak_gbs,
                 "peak_source": "measured in this run (ahv_diag_smem_read, conflict-free LDS.128)",
-                "nominal_peak": nominal_smem, "kernel_ms": kernel_ms, "traffic": ncu_traffic(),
+                "nominal_peak": nominal_smem, "kernel_ms": kernel_ms, "traffic": ncu_traffic(), "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/); algorithmic HBM bytes per launch = %d" % (HBM_BYTES_PER_HYP * B * N),
                 "algorithmic_bytes_per_unit": GATHER_BYTES_PER_HYP,
                 "alt": {
                     "hbm": {"achieved": hyp_per_s_kernel * HBM_BYTES_PER_HYP / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",

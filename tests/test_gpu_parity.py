@@ -324,3 +324,39 @@ def test_fused_verify_argmax_equals_generic_path(ahv, golden, B, N):
     assert torch.equal(fp.scores, gp.scores) and torch.equal(fp.topk_idx, gp.topk_idx)
     assert torch.equal(fp.topk_idx[:, 0] - 1000, fp.scores.argmax(1))
     assert torch.equal(fp.R_best[:, 0], Rp[torch.arange(B), fp.topk_idx[:, 0] - 1000])
+
+
+def test_bf16_staged_gather_matches_oracle_on_rounded_volume(ahv, golden, oracle):
+    """bf16 volumes take the 16-bit staged gather (x-pair lines).  Against the oracle evaluated on
+    the SAME bf16-rounded volume the only error left is the fp16 conv operands: 1e-3 gate."""
+    dev = _dev()
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    vs16 = torch.from_numpy(g["vol_src"]).bfloat16()
+    R = g["R"][:700]
+    ref = oracle.score_c(vs16.float().numpy(), g["vol_tgt"], R, w["W1"], w["W2"], w["b2"])
+    for name, math in _maths(ahv):
+        v = ahv.HypothesisVerifier(*_weights(golden, dev), math=math)
+        r = v.score(vs16.to(dev), torch.from_numpy(g["vol_tgt"]).to(dev), torch.from_numpy(R).to(dev), k=1)
+        assert _relerr(r.scores.cpu().numpy(), ref) <= TOL[name], (name, _relerr(r.scores.cpu().numpy(), ref))
+        assert _top1_ok(r.scores.cpu().numpy(), ref, r.topk_idx[:, 0].cpu().numpy(), TOL[name])
+    # per-pair rotations, odd counts and a volume with large magnitude (exercises the power-of-two scale)
+    big = (vs16.float() * 3000.0).bfloat16()
+    Rp = np.stack([R[:33], R[100:133], R[200:233]])
+    refp = oracle.score_c(big.float().numpy(), g["vol_tgt"], Rp, w["W1"], w["W2"], w["b2"])
+    v = ahv.HypothesisVerifier(*_weights(golden, dev))
+    rp = v.score(big.to(dev), torch.from_numpy(g["vol_tgt"]).to(dev), torch.from_numpy(Rp).to(dev), k=1)
+    assert _relerr(rp.scores.cpu().numpy(), refp) <= TOL["tc"]
+
+
+def test_scale_invariance_of_tc_path(ahv, golden, oracle):
+    """fp32 volumes with tiny / huge magnitudes: the per-pair power-of-two pre-scale keeps the fp16
+    conv operands in range (without it 1e-4-sized volumes would go subnormal, 1e4-sized overflow)."""
+    dev = _dev()
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    R = g["R"][:300]
+    for factor in (1e-5, 1.0, 3e4):
+        vs = (g["vol_src"] * factor).astype(np.float32)
+        ref = oracle.score_c(vs, g["vol_tgt"], R, w["W1"], w["W2"], w["b2"])
+        v = ahv.HypothesisVerifier(*_weights(golden, dev))
+        r = v.score(torch.from_numpy(vs).to(dev), torch.from_numpy(g["vol_tgt"]).to(dev), torch.from_numpy(R).to(dev), k=1)
+        assert _relerr(r.scores.cpu().numpy(), ref) <= TOL["tc"], factor
