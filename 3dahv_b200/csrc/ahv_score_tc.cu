@@ -255,9 +255,9 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // 768 threads x 80 registers at launch; the MMA warpgroup gives its registers away first
+  // 768 threads x 80 registers at launch (61440); the MMA warpgroup gives its registers away first
   if (warp < kGatherWarps) {
-    reg_inc<96>();
+    reg_inc<88>();
     // =========================== GATHER ===========================
     // lane -> voxel (d = warp, h = 4e + hh, w): w = lane>>2, hh = lane&3
     const int w = lane >> 2, hh = lane & 3, d = warp & 7, grp = warp >> 3;
@@ -450,7 +450,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       }
     }
   } else if (warp >= kMmaWarp) {
-    reg_dec<40>();
+    reg_dec<32>();
     // =========================== MMA ISSUER ===========================
     if (warp == kMmaWarp && lane == 0) {
       constexpr uint32_t idesc1 = instr_desc(64, 32), idesc2 = instr_desc(128, 32);
@@ -495,7 +495,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     }
     __syncwarp();
   } else {
-    reg_inc<88>();  // 16*32*96 + 4*32*88 + 4*32*40 = 65536
+    reg_inc<96>();  // setmaxnreg only redistributes the CTA's own allocation: 16*32*88 + 4*32*96 + 4*32*32 = 768*80
     // =========================== EPILOGUE ===========================
     const int s = warp - kEpiWarp0;       // TMEM sub-partition = warp % 4
     const int slot = lane >> 4;           // which hypothesis of the tile
