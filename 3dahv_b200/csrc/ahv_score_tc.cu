@@ -39,11 +39,10 @@ namespace ahv {
 
 namespace tc {
 
-constexpr int kGatherWarps = 16;  // two groups of 8: group g fills the stages of hypotheses with slot g
-constexpr int kGroupWarps = 8;
-constexpr int kEpiWarp0 = 16;     // 4 epilogue warps; warp % 4 = TMEM sub-partition
-constexpr int kMmaWarp = 20;
-constexpr int kThreadsTC = 24 * 32;  // warps 21-23 idle: they only complete the MMA warp's warpgroup for setmaxnreg
+constexpr int kGatherWarps = 8;
+constexpr int kEpiWarp0 = 8;
+constexpr int kMmaWarp = 12;
+constexpr int kThreadsTC = 13 * 32;
 constexpr int kStages = 3;
 
 // ---- shared memory map (bytes) ----
@@ -133,11 +132,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// register re-balancing between warp-specialised roles (whole warpgroups only)
-template <int kRegs>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -177,16 +171,11 @@ struct TileIter {
     next += cnt;
     return true;
   }
-  // (pair, first hypothesis, count) of the tile the next advance() will produce; at the very end it
-  // returns the current tile again (a harmless, valid address for the rotation prefetch)
-  __device__ __forceinline__ void peek_tile(int& pb, int64_t& pn, int& pc) const {
-    if (next >= hi) { pb = b; pn = n0; pc = cnt > 0 ? cnt : 1; return; }
-    int64_t se = seg_end;
-    pb = b;
-    if (next >= se) { ++pb; se += N; }
-    pn = next - (se - N);
-    const int64_t end = se < hi ? se : hi;
-    pc = (end - next >= 2) ? 2 : 1;
+  // (pair, hypothesis) of the item following this tile, or the tile's own first item at the very end
+  __device__ __forceinline__ void peek(int& pb, int64_t& pn) const {
+    if (next >= hi) { pb = b; pn = n0; }
+    else if (next >= seg_end) { pb = b + 1; pn = 0; }
+    else { pb = b; pn = next - (seg_end - N); }
   }
 };
 
@@ -226,7 +215,6 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc);
   float* partial = reinterpret_cast<float*>(smem + kOffMisc + 16);  // [2 tilebuf][2 slot][4 warps]
   float* sbase = reinterpret_cast<float*>(smem + kOffMisc + 96);    // 8 base coordinates
-  float* sb2 = reinterpret_cast<float*>(smem + kOffMisc + 128);     // conv2 bias (32 floats)
 
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < kVolSmemBytes / 16; i += kThreadsTC)
@@ -234,10 +222,9 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   for (int i = threadIdx.x; i < (kW1Bytes + kW2Bytes) / 16; i += kThreadsTC)
     reinterpret_cast<uint4*>(smem + kOffW1)[i] = w_packed[i];
   if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
-  if (threadIdx.x >= 32 && threadIdx.x < 64) sb2[threadIdx.x - 32] = b2[threadIdx.x - 32];
   if (warp == kMmaWarp) {
     if (lane == 0) {
-      for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGroupWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
+      for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar0 + (kD1Full + i) * 8, 1);
         mbar_init(bar0 + (kD1Empty + i) * 8, 4);
@@ -255,12 +242,10 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // 768 threads x 80 registers at launch (61440); the MMA warpgroup gives its registers away first
   if (warp < kGatherWarps) {
-    reg_inc<88>();
     // =========================== GATHER ===========================
     // lane -> voxel (d = warp, h = 4e + hh, w): w = lane>>2, hh = lane&3
-    const int w = lane >> 2, hh = lane & 3, d = warp & 7, grp = warp >> 3;
+    const int w = lane >> 2, hh = lane & 3, d = warp;
     const int pf = w & 1;                 // bank parity this lane reads first
     const int rot = ((w & 3) + hh) & 3;   // chunk rotation: lanes of one LDS phase hit 8 distinct bank groups
     const float bx = sbase[w], bz = sbase[d];
@@ -280,20 +265,17 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       }
     }
     const unsigned char* volb = smem + kOffVol;
-    const int gtid = threadIdx.x;  // 0..511
+    const int gtid = threadIdx.x;  // 0..255
     TileIter it(work);
     int cur_b = -1;
-    uint32_t h = grp;  // hypothesis counter of this CTA (stage = h % 3); this group does h = 2*tile + grp
+    uint32_t h = 0;  // hypothesis counter of this CTA (stage = h % 3)
     float Rn[9];
-    auto fetch_R = [&](int fb, int64_t fn) {
-      const float* Rg = R + (r_per_pair ? ((size_t)fb * N + fn) : (size_t)fn) * 9;
+    {
+      const int b0 = (int)(work.lo / N);
+      const int64_t n0 = work.lo - (int64_t)b0 * N;
+      const float* Rg = R + (r_per_pair ? ((size_t)b0 * N + n0) : (size_t)n0) * 9;
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
-    };
-    {
-      int fb; int64_t fn; int fc;
-      it.peek_tile(fb, fn, fc);
-      fetch_R(fb, fn + (grp < fc ? grp : 0));  // odd tail: slot 1 recomputes the valid hypothesis
     }
     while (it.advance()) {
       if (it.b != cur_b) {
@@ -333,14 +315,17 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
       }
-      {
+      for (int sl = 0; sl < 2; ++sl, ++h) {
         float Rr[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) Rr[e] = Rn[e];
-        {  // prefetch this group's rotation of the NEXT tile (hides the L2 round trip behind this gather)
-          int nb; int64_t nn; int nc;
-          it.peek_tile(nb, nn, nc);
-          fetch_R(nb, nn + (grp < nc ? grp : 0));
+        {  // prefetch the next hypothesis' rotation (hides the L2 round trip behind this gather)
+          int nb; int64_t nn;
+          if (sl == 0) { nb = it.b; nn = it.n0 + (it.cnt > 1 ? 1 : 0); }
+          else it.peek(nb, nn);
+          const float* Rg = R + (r_per_pair ? ((size_t)nb * N + nn) : (size_t)nn) * 9;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
         }
         const uint32_t stage = h % kStages, use = h / kStages;
         if (use > 0) mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1);
@@ -368,20 +353,29 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
               wa[c] = wyz * wxa;
               wb[c] = wyz * wxb;
             }
-            // 4 chunk batches of 8 LDS.128 (4 warps per scheduler cover the load latency)
-#pragma unroll
+            // 4 chunk batches of 8 LDS.128 each, software-pipelined: batch t+1 is in flight
+            // while batch t is consumed (two register buffers)
+            float4 buf[2][8];
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {  // c = dz*2 + dy
+              const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+              buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
+              buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
+            }
+  #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              float4 buf[8];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {  // c = dz*2 + dy
-                const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
-                buf[2 * c] = *reinterpret_cast<const float4*>(pa + koff[t] + off);
-                buf[2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t] + off);
+              if (t < 3) {
+  #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+                  buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
+                  buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+                }
               }
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+  #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float4 a = buf[2 * c], g = buf[2 * c + 1];
+                const float4 a = buf[t & 1][2 * c], g = buf[t & 1][2 * c + 1];
                 acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
                 acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
                 acc.x = fmaf(wb[c], g.x, acc.x); acc.y = fmaf(wb[c], g.y, acc.y);
@@ -409,18 +403,24 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
             float acc[2][8];
 #pragma unroll
             for (int e2 = 0; e2 < 8; ++e2) acc[0][e2] = acc[1][e2] = 0.0f;
+            uint4 buf[2][4];
             constexpr int kDz = kHalo * 9 * 64;
+            buf[0][0] = *reinterpret_cast<const uint4*>(pa + koff[0]);
+            buf[0][1] = *reinterpret_cast<const uint4*>(pa + koff[0] + kDz);
+            buf[0][2] = *reinterpret_cast<const uint4*>(pb + koff[0]);
+            buf[0][3] = *reinterpret_cast<const uint4*>(pb + koff[0] + kDz);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              uint4 buf[4];
-              buf[0] = *reinterpret_cast<const uint4*>(pa + koff[t]);
-              buf[1] = *reinterpret_cast<const uint4*>(pa + koff[t] + kDz);
-              buf[2] = *reinterpret_cast<const uint4*>(pb + koff[t]);
-              buf[3] = *reinterpret_cast<const uint4*>(pb + koff[t] + kDz);
+              if (t < 3) {
+                buf[(t + 1) & 1][0] = *reinterpret_cast<const uint4*>(pa + koff[t + 1]);
+                buf[(t + 1) & 1][1] = *reinterpret_cast<const uint4*>(pa + koff[t + 1] + kDz);
+                buf[(t + 1) & 1][2] = *reinterpret_cast<const uint4*>(pb + koff[t + 1]);
+                buf[(t + 1) & 1][3] = *reinterpret_cast<const uint4*>(pb + koff[t + 1] + kDz);
+              }
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const float wg = wxt[t] * w4[c];
-                const uint4 q4 = buf[c];
+                const uint4 q4 = buf[t & 1][c];
                 const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
                 for (int k2 = 0; k2 < 4; ++k2) {  // bf16 -> fp32 is a shift / mask
@@ -446,13 +446,11 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
         fence_proxy_async();  // make this thread's A-operand stores visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + (kFull + stage) * 8);
-        h += 2;
       }
     }
-  } else if (warp >= kMmaWarp) {
-    reg_dec<32>();
+  } else if (warp == kMmaWarp) {
     // =========================== MMA ISSUER ===========================
-    if (warp == kMmaWarp && lane == 0) {
+    if (lane == 0) {
       constexpr uint32_t idesc1 = instr_desc(64, 32), idesc2 = instr_desc(128, 32);
       const uint32_t w1s = s_base + kOffW1, w2s = s_base + kOffW2;
       TileIter it(work);
@@ -495,13 +493,14 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     }
     __syncwarp();
   } else {
-    reg_inc<96>();  // setmaxnreg only redistributes the CTA's own allocation: 16*32*88 + 4*32*96 + 4*32*32 = 768*80
     // =========================== EPILOGUE ===========================
     const int s = warp - kEpiWarp0;       // TMEM sub-partition = warp % 4
     const int slot = lane >> 4;           // which hypothesis of the tile
     const int pos = 16 * s + (lane & 15); // position p*8+q of the folded plane
     const uint32_t row = 32 * s + lane;   // TMEM lane == row of the conv2 A operand
-    float tg[kO];
+    float b2r[kO], tg[kO];
+#pragma unroll
+    for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
     TileIter it(work);
     int cur_b = -1;
     float inv_s = 1.0f;
@@ -524,7 +523,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       float ss = 0.0f, dt = 0.0f;
 #pragma unroll
       for (int o = 0; o < kO; ++o) {
-        const float v = fmaf(__uint_as_float(r[o]), pinv, sb2[o]);  // undo the pair scale, add bias (smem broadcast)
+        const float v = fmaf(__uint_as_float(r[o]), pinv, b2r[o]);  // undo the pair scale, add bias
         ss = fmaf(v, v, ss);
         dt = fmaf(v, tg[o], dt);
       }
