@@ -330,9 +330,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
           for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
         }
         const uint32_t stage = h % kStages, use = h / kStages;
-        // the stage is only needed at the first store: the empty-barrier round trip is issued after the
-        // first voxel's loads and FMAs so that they overlap it
-        bool need_wait = use > 0;
+        if (use > 0) mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1);
         unsigned char* st = smem + kOffA + stage * kStageBytes;
 #pragma unroll 1
         for (int e = 0; e < 2; ++e) {
@@ -389,7 +387,6 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
               uint2 pk;
               pk.x = *reinterpret_cast<const uint32_t*>(&lo);
               pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
-              if (t == 0 && need_wait) { mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1); need_wait = false; }
               *reinterpret_cast<uint2*>(st + syz[t] + e * (4 * M::yz_h)) = pk;  // h += 4
               *reinterpret_cast<uint2*>(st + sx[t] + e * 64) = pk;
             }
@@ -438,7 +435,6 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
                   acc[t & 1][k2] = __hfma2(wg, *reinterpret_cast<const __half2*>(&wd[k2]), acc[t & 1][k2]);
               }
             }
-            if (need_wait) { mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1); need_wait = false; }
 #pragma unroll
             for (int a2i = 0; a2i < 2; ++a2i) {
               const uint4 q4 = make_uint4(*reinterpret_cast<const uint32_t*>(&acc[a2i][0]),
