@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib3dahv_b200.so")
 
 AHV_OK, AHV_EINVAL, AHV_ENOTSUP, AHV_ECUDA, AHV_EWORKSPACE = 0, -1, -2, -3, -4
 VOL_F32, VOL_BF16 = 0, 1
-MATH_TC, MATH_FP32 = 0, 1
+MATH_TC, MATH_FP32, MATH_TC_F16GATHER = 0, 1, 2
 
 _vp, _i, _i64, _u64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_size_t
 

@@ -116,7 +116,7 @@ AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat,
               int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 0 || N < 0 || N > 0x7fffffffLL) return AHV_EINVAL;
   if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
-  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32) return AHV_EINVAL;
+  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32 && math_mode != AHV_MATH_TC_F16GATHER) return AHV_EINVAL;
   if (k < 0 || k > kMaxK) return AHV_EINVAL;
   if (k > 0 && (!topk_val || !topk_idx)) return AHV_EINVAL;
   if ((int64_t)B * N > 0 && (!vol_src || !tgt_feat || !R || !W1 || !W2 || !b2 || !base))
@@ -145,7 +145,7 @@ AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat,
                            N, s);
   else
     st = launch_score_tc(vol_src, vol_dtype, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, sc, B, N,
-                         ws_tc, need_tc, s);
+                         ws_tc, need_tc, s, math_mode == AHV_MATH_TC_F16GATHER);
   if (st != AHV_OK) return st;
   if (k > 0) st = launch_topk(sc, B, N, k, idx_offset, topk_val, topk_idx, ws_topk, need_topk, s);
   return st;
@@ -157,7 +157,7 @@ AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt,
                        int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream) {
   if (B < 0 || N < 0 || N > 0x7fffffffLL || k < 1 || k > kMaxK) return AHV_EINVAL;
   if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
-  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32) return AHV_EINVAL;
+  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32 && math_mode != AHV_MATH_TC_F16GATHER) return AHV_EINVAL;
   if ((int64_t)B * N > 0 && (!vol_src || !vol_tgt || !R || !W1 || !W2 || !b2 || !base || !topk_val || !topk_idx))
     return AHV_EINVAL;
   if (!aligned16(vol_src) || !aligned16(vol_tgt) || !aligned16(R) || !aligned16(W1) || !aligned16(W2) ||
@@ -173,10 +173,10 @@ AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt,
   const size_t off_topk = align_up((size_t)B * (size_t)N * sizeof(float), 256);
   const size_t off_tc = off_topk + align_up(topk_workspace_bytes(B, N, k), 256);
   void* ws_tc = ws + off_tc;
-  if (math_mode == AHV_MATH_TC && k == 1)  // three launches, nothing but 40 B per hypothesis touches HBM
+  if (math_mode != AHV_MATH_FP32 && k == 1)  // three launches, nothing but 40 B per hypothesis touches HBM
     return launch_verify_tc_argmax(vol_src, vol_dtype, vol_tgt, R, r_per_pair != 0, W1, W2, b2, base, scores,
                                    topk_val, topk_idx, R_best, idx_offset, B, N, ws_tc,
-                                   workspace_bytes - off_tc, s);
+                                   workspace_bytes - off_tc, s, math_mode == AHV_MATH_TC_F16GATHER);
   float* tgt = scratch_tgt_feat(ws_tc, B);
   st = launch_forward_3d2d(vol_tgt, W1, W2, b2, tgt, B, s);
   if (st != AHV_OK) return st;

@@ -96,14 +96,14 @@ int launch_score_fp32(const void* vol_src, int vol_dtype, const float* tgt_feat,
 int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
                     int r_per_pair, const float* W1, const float* W2, const float* b2,
                     const float* base, float* scores, int B, int64_t N, void* ws, size_t ws_bytes,
-                    cudaStream_t s);
+                    cudaStream_t s, bool f16_gather);
 size_t score_tc_workspace_bytes(int B, int64_t N);
 float* scratch_tgt_feat(void* ws, int B);  // [B,32,64] slot inside the tensor-core scratch
 int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R,
                             int r_per_pair, const float* W1, const float* W2, const float* b2,
                             const float* base, float* scores, float* best_val, int64_t* best_idx,
                             float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
-                            cudaStream_t s);
+                            cudaStream_t s, bool f16_gather);
 int launch_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* val,
                 int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t topk_workspace_bytes(int B, int64_t N, int k);

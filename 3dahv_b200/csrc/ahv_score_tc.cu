@@ -189,7 +189,7 @@ template <>
 __device__ __forceinline__ float ld_vol<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 // ------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool K16>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_feat,
                 const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
@@ -197,7 +197,6 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
                 const float2* __restrict__ pair_scale, float* __restrict__ scores,
                 u64* __restrict__ best_keys, int B, int64_t N) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr bool K16 = sizeof(T) == 2;  // bf16 volumes: 16-bit staging
   using M = Map<K16>;
   constexpr int kOffVol = M::off_vol, kOffW1 = M::off_w1, kOffW2 = M::off_w2, kOffA = M::off_a, kOffA2 = M::off_a2,
                 kOffBar = M::off_bar, kOffMisc = M::off_misc, kStageBytes = M::stage_bytes;
@@ -303,7 +302,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
             const int zh = (v >> 6) + 1, yh = ((v >> 3) & 7) + 1, xh = (v & 7) + 1;
             uint32_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {  // bf16 (8-bit mantissa) x power-of-two scale -> fp16 is exact
+            for (int e = 0; e < 4; ++e) {  // bf16 inputs (8-bit mantissa) x power-of-two scale -> fp16 exactly; fp32 inputs are rounded
               const __half2 two = __floats2half2_rn(ld_vol<T>(vg + (chalf * 8 + 2 * e) * kVox + v) * sc,
                                                     ld_vol<T>(vg + (chalf * 8 + 2 * e + 1) * kVox + v) * sc);
               pk[e] = *reinterpret_cast<const uint32_t*>(&two);
@@ -728,7 +727,7 @@ __host__ inline Scratch carve(void* ws, int B) {
   return sc;
 }
 
-template <typename T>
+template <typename T, bool K16>
 int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_in, const float* R,
                  int r_per_pair, const float* W1, const float* W2, const float* b2, const float* base,
                  float* scores, bool want_argmax, int B, int64_t N, const Scratch& sc, cudaStream_t s) {
@@ -746,9 +745,9 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
   const int64_t tiles = ((int64_t)B * N + 1) / 2;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  constexpr int kSmemBytes = Map<sizeof(T) == 2>::smem_bytes;
-  AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  score_tc_kernel<T><<<grid, kThreadsTC, kSmemBytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,
+  constexpr int kSmemBytes = Map<K16>::smem_bytes;
+  AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  score_tc_kernel<T, K16><<<grid, kThreadsTC, kSmemBytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,
                                                          b2, base, (const uint4*)sc.w_packed, sc.pair_scale, scores,
                                                          want_argmax ? sc.best_keys : nullptr, B, N);
   AHV_CUDA_OK(cudaGetLastError());
@@ -764,19 +763,31 @@ size_t score_tc_workspace_bytes(int B, int64_t N) {
 
 float* scratch_tgt_feat(void* ws, int B) { return tc::carve(ws, B).tgt_feat; }
 
+// dispatch on (volume dtype, gather precision): bf16 volumes always use the 16-bit staged gather
+// (exact staging); fp32 volumes use it only when the caller opts in (AHV_MATH_TC_F16GATHER)
+static int dispatch(const void* vol_src, int vol_dtype, bool f16_gather, const float* vol_tgt,
+                    const float* tgt_feat, const float* R, int r_per_pair, const float* W1, const float* W2,
+                    const float* b2, const float* base, float* scores, bool want_argmax, int B, int64_t N,
+                    const tc::Scratch& sc, cudaStream_t s) {
+  if (vol_dtype == AHV_VOL_BF16)
+    return tc::launch_typed<__nv_bfloat16, true>((const __nv_bfloat16*)vol_src, vol_tgt, tgt_feat, R, r_per_pair, W1,
+                                                 W2, b2, base, scores, want_argmax, B, N, sc, s);
+  if (f16_gather)
+    return tc::launch_typed<float, true>((const float*)vol_src, vol_tgt, tgt_feat, R, r_per_pair, W1, W2, b2, base,
+                                         scores, want_argmax, B, N, sc, s);
+  return tc::launch_typed<float, false>((const float*)vol_src, vol_tgt, tgt_feat, R, r_per_pair, W1, W2, b2, base,
+                                        scores, want_argmax, B, N, sc, s);
+}
+
 // scores only (target features supplied by the caller)
 int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
                     int r_per_pair, const float* W1, const float* W2, const float* b2,
                     const float* base, float* scores, int B, int64_t N, void* ws, size_t ws_bytes,
-                    cudaStream_t s) {
+                    cudaStream_t s, bool f16_gather) {
   if ((int64_t)B * N == 0) return AHV_OK;
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
-  const tc::Scratch sc = tc::carve(ws, B);
-  if (vol_dtype == AHV_VOL_F32)
-    return tc::launch_typed<float>((const float*)vol_src, nullptr, tgt_feat, R, r_per_pair, W1, W2, b2, base,
-                                   scores, false, B, N, sc, s);
-  return tc::launch_typed<__nv_bfloat16>((const __nv_bfloat16*)vol_src, nullptr, tgt_feat, R, r_per_pair, W1, W2,
-                                         b2, base, scores, false, B, N, sc, s);
+  return dispatch(vol_src, vol_dtype, f16_gather, nullptr, tgt_feat, R, r_per_pair, W1, W2, b2, base, scores, false,
+                  B, N, tc::carve(ws, B), s);
 }
 
 // the whole verification step with arg-max selection in three launches:
@@ -785,17 +796,12 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
                             int r_per_pair, const float* W1, const float* W2, const float* b2,
                             const float* base, float* scores, float* best_val, int64_t* best_idx,
                             float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool f16_gather) {
   if ((int64_t)B * N == 0) return AHV_OK;
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   const tc::Scratch sc = tc::carve(ws, B);
-  int st;
-  if (vol_dtype == AHV_VOL_F32)
-    st = tc::launch_typed<float>((const float*)vol_src, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2, base, scores,
-                                 true, B, N, sc, s);
-  else
-    st = tc::launch_typed<__nv_bfloat16>((const __nv_bfloat16*)vol_src, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2,
-                                         base, scores, true, B, N, sc, s);
+  int st = dispatch(vol_src, vol_dtype, f16_gather, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2, base, scores, true,
+                    B, N, sc, s);
   if (st != AHV_OK) return st;
   tc::tc_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(sc.best_keys, R, r_per_pair, idx_offset, B, N, best_val,
                                                          best_idx, R_best);

@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import MATH_FP32, MATH_TC, VOL_BF16, VOL_F32
+from ._lib import MATH_FP32, MATH_TC, MATH_TC_F16GATHER, VOL_BF16, VOL_F32
 
 _BASE_CPU = None
 _BASE_DEV = {}

@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import torch
 
 from . import ops
-from ._lib import MATH_FP32, MATH_TC
+from ._lib import MATH_FP32, MATH_TC, MATH_TC_F16GATHER
 
 DEFAULT_MATH = MATH_TC
 

@@ -48,9 +48,13 @@ enum { AHV_VOL_F32 = 0, AHV_VOL_BF16 = 1 };
  *                 tensor cores with fp32 accumulation in TMEM — the fast path;
  *   AHV_MATH_FP32 plain fp32 FFMA on CUDA cores — the bit-tight verification
  *                 mode (about 1e-6 relative to the reference).
- * Trilinear resampling, normalisation, correlation and selection are fp32 in
- * both modes. */
-enum { AHV_MATH_TC = 0, AHV_MATH_FP32 = 1 };
+ *   AHV_MATH_TC_F16GATHER  opt-in fast mode: as AHV_MATH_TC, but the source volume is
+ *                 staged in shared memory as (scaled) fp16 and interpolated with packed
+ *                 HFMA2, halving the shared-memory gather traffic.  bf16 volumes always
+ *                 take this path (their staging is exact).  About 2e-4 relative.
+ * Normalisation, correlation and selection are fp32 in every mode; trilinear resampling is
+ * fp32 except in the f16-gather path. */
+enum { AHV_MATH_TC = 0, AHV_MATH_FP32 = 1, AHV_MATH_TC_F16GATHER = 2 };
 
 AHV_API int ahv_version(void);
 AHV_API const char* ahv_status_string(int status);

@@ -12,7 +12,7 @@ ap = argparse.ArgumentParser(); ap.add_argument("--quick", action="store_true");
 args = ap.parse_args()
 ahv = importlib.import_module("3dahv_b200")
 dev = torch.device("cuda", 0)
-math = {"tc": ahv.MATH_TC, "fp32": ahv.MATH_FP32}[args.math]
+math = {"tc": ahv.MATH_TC, "fp32": ahv.MATH_FP32, "tc_f16gather": ahv.MATH_TC_F16GATHER}[args.math]
 Ns = [1000, 10000, 100000] if args.quick else [1000, 10000, 100000, 1000000]
 Bs = [1, 16, 256] if args.quick else [1, 4, 16, 64, 256]
 W1, W2, b2, vs_all, vt_all, normals = bench.synthetic_inputs(torch, max(Bs), max(Ns))

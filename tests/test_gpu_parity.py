@@ -360,3 +360,18 @@ def test_scale_invariance_of_tc_path(ahv, golden, oracle):
         v = ahv.HypothesisVerifier(*_weights(golden, dev))
         r = v.score(torch.from_numpy(vs).to(dev), torch.from_numpy(g["vol_tgt"]).to(dev), torch.from_numpy(R).to(dev), k=1)
         assert _relerr(r.scores.cpu().numpy(), ref) <= TOL["tc"], factor
+
+
+def test_f16_gather_fast_mode_within_fp32_gate(ahv, golden):
+    """Opt-in AHV_MATH_TC_F16GATHER on fp32 volumes: fp16-staged volume + packed HFMA2 interpolation
+    still meets the fp32 configuration's 1e-3 gate against the reference's own scores."""
+    dev = _dev()
+    g = golden["shared_n3000_b3"]
+    v = ahv.HypothesisVerifier(*_weights(golden, dev), math=ahv.MATH_TC_F16GATHER)
+    r = v.score(torch.from_numpy(g["vol_src"]).to(dev), torch.from_numpy(g["vol_tgt"]).to(dev),
+                torch.from_numpy(g["R"]).to(dev), k=1, return_scores=True)
+    s = r.scores.cpu().numpy()
+    err = _relerr(s, g["scores"])
+    assert err <= 1e-3, err
+    assert _top1_ok(s, g["scores"], r.topk_idx[:, 0].cpu().numpy(), 1e-3)
+    assert np.array_equal(r.topk_idx[:, 0].cpu().numpy(), s.argmax(1))
