@@ -33,6 +33,8 @@
 // The source volume is pre-scaled per pair by a power of two (exact) so fp16
 // can neither overflow nor go subnormal; the scale is undone after conv2
 // (ReLU and the bias-free conv1 are positively homogeneous).
+#include <cstdlib>
+
 #include "ahv_head_fp32.cuh"
 
 namespace ahv {
@@ -172,6 +174,17 @@ struct TileIter {
     cnt = (end - next >= 2) ? 2 : 1;
     next += cnt;
     return true;
+  }
+  // (pair, first hypothesis, count) of the tile the next advance() will produce; at the very end the
+  // current tile again (a harmless, valid address for the rotation prefetch)
+  __device__ __forceinline__ void peek_tile(int& pb, int64_t& pn, int& pc) const {
+    if (next >= hi) { pb = b; pn = n0; pc = cnt > 0 ? cnt : 1; return; }
+    int64_t se = seg_end;
+    pb = b;
+    if (next >= se) { ++pb; se += N; }
+    pn = next - (se - N);
+    const int64_t end = se < hi ? se : hi;
+    pc = (end - next >= 2) ? 2 : 1;
   }
   // (pair, hypothesis) of the item following this tile, or the tile's own first item at the very end
   __device__ __forceinline__ void peek(int& pb, int64_t& pn) const {
@@ -603,6 +616,386 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   }
 }
 
+// ==============================================================================================
+// TS variant (fp32 volumes): view x of conv1 never touches shared memory.  Each gather lane owns one
+// accumulator row (slot, d, h) - i.e. one TMEM lane - walks the 8 voxels along w, and writes the
+// fp16 channels of every voxel (a) once into the YZ copy (views y and z, K-major core matrices,
+// 144-byte row pitch so the STS.64 are conflict-free for this lane map) and (b) with tcgen05.st
+// straight into TMEM as the A operand of view x, which the MMA warp consumes in the TS form
+// (tcgen05.mma [d], [a_tmem], b_desc).  A and D of one M=64 tile share the lane offset (0 or 16),
+// verified by experiments/ts_mma_probe.cu.  Compared with the SS kernel this removes one 16 KB
+// operand copy (stores) and one 16 KB operand read per hypothesis from the shared-memory pipe.
+struct MapTS {
+  static constexpr int yz_h = 144, yz_d = 8 * yz_h, yz_ch = 8 * yz_d, yz_bytes = 2 * yz_ch;  // 18432 per hypothesis
+  static constexpr int tile_bytes = 2 * yz_bytes;
+  static constexpr int off_vol = 0;
+  static constexpr int off_w1 = off_vol + kVolSmemBytes;
+  static constexpr int off_w2 = off_w1 + kW1Bytes;
+  static constexpr int off_a = off_w2 + kW2Bytes;
+  static constexpr int off_a2 = off_a + kStages * tile_bytes;
+  static constexpr int off_bar = off_a2 + 2 * kA2Bytes;
+  static constexpr int off_misc = off_bar + 16 * 8;
+  static constexpr int smem_bytes = off_misc + 256;
+  static constexpr int tmem_cols = 512;      // D1[2] 0..63, D2[2] 64..127, A_x[3] 128 + 64*stage
+  static constexpr int tmem_ax = 128;
+  static_assert(off_a % 128 == 0 && off_a2 % 128 == 0 && off_bar % 8 == 0, "align");
+  static_assert(smem_bytes <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreadsTC, 1)
+score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ tgt_feat,
+                   const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
+                   const float* __restrict__ base, const uint4* __restrict__ w_packed,
+                   const float2* __restrict__ pair_scale, float* __restrict__ scores,
+                   u64* __restrict__ best_keys, int B, int64_t N) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using M = MapTS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Work work;
+  {
+    const int64_t total = (int64_t)B * N;
+    work.lo = total * blockIdx.x / gridDim.x;
+    work.hi = total * (blockIdx.x + 1) / gridDim.x;
+    work.N = N;
+  }
+  if (work.lo >= work.hi) return;
+
+  float* vol = reinterpret_cast<float*>(smem + M::off_vol);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar0 = s_base + M::off_bar;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + M::off_misc);
+  float* partial = reinterpret_cast<float*>(smem + M::off_misc + 16);  // [2 tilebuf][2 slot][4 warps]
+  float* sbase = reinterpret_cast<float*>(smem + M::off_misc + 96);    // 8 base coordinates
+
+  for (int i = threadIdx.x; i < kVolSmemBytes / 16; i += kThreadsTC)
+    reinterpret_cast<uint4*>(vol)[i] = make_uint4(0, 0, 0, 0);  // halo stays zero for the whole kernel
+  for (int i = threadIdx.x; i < (kW1Bytes + kW2Bytes) / 16; i += kThreadsTC)
+    reinterpret_cast<uint4*>(smem + M::off_w1)[i] = w_packed[i];
+  if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar0 + (kD1Full + i) * 8, 1);
+        mbar_init(bar0 + (kD1Empty + i) * 8, 4);
+        mbar_init(bar0 + (kA2Full + i) * 8, 4);
+        mbar_init(bar0 + (kD2Full + i) * 8, 1);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), M::tmem_cols);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < kGatherWarps) {
+    // =========================== GATHER ===========================
+    // lane -> accumulator row: slot = lane>>4 (hypothesis of the tile), d = 2*sub + ((lane>>3)&1), h = lane&7;
+    // the warp's TMEM sub-partition is warp&3, warps w and w+4 split the w axis
+    const int sub = warp & 3, whalf = warp >> 2;
+    const int slot = lane >> 4, dlo = (lane >> 3) & 1, h_ = lane & 7, d = 2 * sub + dlo;
+    const int pf = (lane >> 2) & 1;            // bank parity this lane reads first
+    const int rot = ((lane & 3) + dlo) & 3;    // chunk rotation
+    const float by = sbase[h_], bz = sbase[d];
+    uint32_t koff[4], syz[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ck = (rot + t) & 3;
+      koff[t] = ck * 16;
+      syz[t] = slot * M::yz_bytes + (ck >> 1) * M::yz_ch + (ck & 1) * 8 + d * M::yz_d + h_ * M::yz_h;
+    }
+    const unsigned char* volb = smem + M::off_vol;
+    const int gtid = threadIdx.x;
+    TileIter it(work);
+    int cur_b = -1;
+    uint32_t g = 0;
+    float Rn[9];
+    auto fetch_R = [&](int fb, int64_t fn) {
+      const float* Rg = R + (r_per_pair ? ((size_t)fb * N + fn) : (size_t)fn) * 9;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
+    };
+    {
+      int fb; int64_t fn; int fc;
+      it.peek_tile(fb, fn, fc);
+      fetch_R(fb, fn + (slot < fc ? slot : 0));
+    }
+    while (it.advance()) {
+      if (it.b != cur_b) {
+        named_bar_sync(1, kGatherWarps * 32);
+        const float* vg = vol_src + (size_t)it.b * kC * kVox;
+        const float sc = pair_scale[it.b].x;
+        for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
+          const int v = task & 511, jj = task >> 9;
+          const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
+          const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
+          float4 o;
+          o.x = __ldg(vg + (jj * 4 + 0) * kVox + v) * sc;
+          o.y = __ldg(vg + (jj * 4 + 1) * kVox + v) * sc;
+          o.z = __ldg(vg + (jj * 4 + 2) * kVox + v) * sc;
+          o.w = __ldg(vg + (jj * 4 + 3) * kVox + v) * sc;
+          *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
+        }
+        named_bar_sync(1, kGatherWarps * 32);
+        cur_b = it.b;
+      }
+      float Rr[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rr[e] = Rn[e];
+      {  // prefetch this lane's rotation of the next tile
+        int nb; int64_t nn; int nc;
+        it.peek_tile(nb, nn, nc);
+        fetch_R(nb, nn + (slot < nc ? slot : 0));
+      }
+      const uint32_t stage = g % kStages, use = g / kStages;
+      if (use > 0) mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1);
+      unsigned char* st = smem + M::off_a + stage * M::tile_bytes;
+      const uint32_t ax = tmem + ((uint32_t)(32 * sub) << 16) + M::tmem_ax + stage * 64;
+      // grid = R @ (x, y, z): y and z are fixed per lane, x walks with w
+      const float pgx = fmaf(Rr[2], bz, Rr[1] * by), pgy = fmaf(Rr[5], bz, Rr[4] * by), pgz = fmaf(Rr[8], bz, Rr[7] * by);
+#pragma unroll 1
+      for (int wi = 0; wi < 4; ++wi) {
+        const int w = whalf * 4 + wi;
+        const float bx = sbase[w];
+        float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
+        ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
+        const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
+        const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
+        const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
+        const int swap = (line ^ pf) & 1;
+        const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
+        const unsigned char* pa = volb + (line + swap) * 64;
+        const unsigned char* pb = volb + (line + 1 - swap) * 64;
+        float wa[4], wb[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float wyz = ((c & 1) ? fy : 1.0f - fy) * ((c >> 1) ? fz : 1.0f - fz);
+          wa[c] = wyz * wxa;
+          wb[c] = wyz * wxb;
+        }
+        float4 buf[2][8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+          buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
+          buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
+        }
+        uint2 pk[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (t < 3) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+              buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
+              buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+            }
+          }
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 a = buf[t & 1][2 * c], q = buf[t & 1][2 * c + 1];
+            acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
+            acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
+            acc.x = fmaf(wb[c], q.x, acc.x); acc.y = fmaf(wb[c], q.y, acc.y);
+            acc.z = fmaf(wb[c], q.z, acc.z); acc.w = fmaf(wb[c], q.w, acc.w);
+          }
+          const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi2 = __floats2half2_rn(acc.z, acc.w);
+          pk[t].x = *reinterpret_cast<const uint32_t*>(&lo);
+          pk[t].y = *reinterpret_cast<const uint32_t*>(&hi2);
+          *reinterpret_cast<uint2*>(st + syz[t] + w * 16) = pk[t];  // YZ copy: row w of core matrix (d,h,chalf)
+        }
+        // view x: un-rotate the chunks (chunk c was produced at step (c - rot) & 3) and store the 16 channels
+        // of this voxel as K slice w of this lane's accumulator row in TMEM
+        uint2 s1[4], o4[4];
+        const bool r1 = rot & 1, r2 = rot & 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          s1[c].x = r1 ? pk[(c + 3) & 3].x : pk[c].x;
+          s1[c].y = r1 ? pk[(c + 3) & 3].y : pk[c].y;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          o4[c].x = r2 ? s1[(c + 2) & 3].x : s1[c].x;
+          o4[c].y = r2 ? s1[(c + 2) & 3].y : s1[c].y;
+        }
+        const uint32_t regs[8] = {o4[0].x, o4[0].y, o4[1].x, o4[1].y, o4[2].x, o4[2].y, o4[3].x, o4[3].y};
+        tmem_st8(ax + w * 8, regs);
+      }
+      tmem_st_wait();
+      fence_proxy_async();  // YZ stores -> async proxy
+      tc_fence_before();    // TMEM stores -> tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + (kFull + stage) * 8);
+      ++g;
+    }
+  } else if (warp == kMmaWarp) {
+    // =========================== MMA ISSUER ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = instr_desc(64, 32), idesc2 = instr_desc(128, 32);
+      const uint32_t w1s = s_base + M::off_w1, w2s = s_base + M::off_w2;
+      TileIter it(work);
+      uint32_t g = 0;
+      auto conv2 = [&](uint32_t gg) {
+        const uint32_t gb = gg & 1, u = gg >> 1;
+        mbar_wait(bar0 + (kA2Full + gb) * 8, u & 1);
+        tc_fence_after();
+        const uint32_t a2 = s_base + M::off_a2 + gb * kA2Bytes;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          umma_f16(tmem + 64 + gb * 32, smem_desc(a2 + i * 4096, 2048, 128), smem_desc(w2s + i * 1024, 512, 128), idesc2, i);
+        umma_commit(bar0 + (kD2Full + gb) * 8);
+      };
+      while (it.advance()) {
+        const uint32_t gb = g & 1, u = g >> 1;
+        if (u > 0) mbar_wait(bar0 + (kD1Empty + gb) * 8, (u - 1) & 1);
+        const uint32_t stage = g % kStages, use = g / kStages;
+        mbar_wait(bar0 + (kFull + stage) * 8, use & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const uint32_t lane_off = (uint32_t)(16 * sl) << 16;
+          const uint32_t d1 = tmem + lane_off + gb * 32;
+          const uint32_t axs = tmem + lane_off + M::tmem_ax + stage * 64;
+          const uint32_t a = s_base + M::off_a + stage * M::tile_bytes + sl * M::yz_bytes;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // view x from TMEM: rows (d,h), K slice = (w=kk, c)
+            umma_f16_ts(d1, axs + kk * 8, smem_desc(w1s + kk * 1024, 512, 128), idesc1, kk);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // view y: rows (d,w), K slice = (h=kk, c)
+            umma_f16(d1, smem_desc(a + kk * M::yz_h, M::yz_ch, M::yz_d), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // view z: rows (h,w), K slice = (d=kk, c)
+            umma_f16(d1, smem_desc(a + kk * M::yz_d, M::yz_ch, M::yz_h), smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
+        }
+        umma_commit(bar0 + (kEmpty + stage) * 8);
+        umma_commit(bar0 + (kD1Full + gb) * 8);
+        if (g > 0) conv2(g - 1);
+        ++g;
+      }
+      conv2(g - 1);
+    }
+    __syncwarp();
+  } else {
+    // =========================== EPILOGUE (identical to the SS kernel) ===========================
+    const int s = warp - kEpiWarp0;
+    const int slot = lane >> 4;
+    const int pos = 16 * s + (lane & 15);
+    const uint32_t row = 32 * s + lane;
+    float b2r[kO], tg[kO];
+#pragma unroll
+    for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
+    TileIter it(work);
+    int cur_b = -1;
+    float inv_s = 1.0f;
+    uint32_t g = 0;
+    int prev_b = 0, prev_cnt = 0;
+    int64_t prev_n0 = 0;
+    float prev_inv = 1.0f;
+    int key_b = -1;
+    u64 key_best = 0;
+    auto phase_b = [&](uint32_t gg, int pb, int64_t pn0, int pcnt, float pinv) {
+      const uint32_t gb = gg & 1, u = gg >> 1;
+      mbar_wait(bar0 + (kD2Full + gb) * 8, u & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + 64 + gb * 32, r);
+      tmem_ld_wait();
+      float ss = 0.0f, dt = 0.0f;
+#pragma unroll
+      for (int o = 0; o < kO; ++o) {
+        const float v = fmaf(__uint_as_float(r[o]), pinv, b2r[o]);
+        ss = fmaf(v, v, ss);
+        dt = fmaf(v, tg[o], dt);
+      }
+      float cosv = dt / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) cosv += __shfl_xor_sync(0xffffffffu, cosv, o);
+      if ((lane & 15) == 0) partial[(gb * 2 + slot) * 4 + s] = cosv;
+      tc_fence_before();
+      named_bar_sync(2, 128);
+      if (s == 0 && lane < pcnt) {
+        const float* pp = partial + (gb * 2 + lane) * 4;
+        const float tot = ((pp[0] + pp[1]) + pp[2]) + pp[3];
+        const float sc = tot * (1.0f / 64.0f);
+        if (scores) scores[(size_t)pb * N + pn0 + lane] = sc;
+        if (best_keys) {
+          const u64 key = make_key(sc, (uint32_t)(pn0 + lane));
+          if (pb != key_b) {
+            if (key_b >= 0) atomicMax(best_keys + key_b, key_best);
+            key_b = pb;
+            key_best = key;
+          } else if (key > key_best) {
+            key_best = key;
+          }
+        }
+      }
+    };
+    while (it.advance()) {
+      const uint32_t gb = g & 1, u = g >> 1;
+      mbar_wait(bar0 + (kD1Full + gb) * 8, u & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + gb * 32, r);
+      tmem_ld_wait();
+      unsigned char* a2 = smem + M::off_a2 + gb * kA2Bytes + row * 16;
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+        uint32_t wq[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[kc * 8 + 2 * e]), 0.0f),
+                                               fmaxf(__uint_as_float(r[kc * 8 + 2 * e + 1]), 0.0f));
+          wq[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(a2 + kc * 2048) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar0 + (kA2Full + gb) * 8);
+        mbar_arrive(bar0 + (kD1Empty + gb) * 8);
+      }
+      if (g > 0) phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+      if (it.b != cur_b) {
+        cur_b = it.b;
+        inv_s = pair_scale[cur_b].y;
+#pragma unroll
+        for (int o = 0; o < kO; ++o) tg[o] = __ldg(tgt_feat + ((size_t)cur_b * kO + o) * kP + pos);
+      }
+      prev_b = it.b; prev_n0 = it.n0; prev_cnt = it.cnt; prev_inv = inv_s;
+      ++g;
+    }
+    phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+    if (best_keys && key_b >= 0) atomicMax(best_keys + key_b, key_best);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, M::tmem_cols);
+  }
+}
+
 // ---- prologue: one launch, three independent jobs running concurrently -------------------
 //   block 0        : pack W1/W2 to fp16 in the UMMA B-operand layouts; clear the arg-max keys
 //   blocks 1..B    : per-pair power-of-two scale
@@ -745,6 +1138,17 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
   const int64_t tiles = ((int64_t)B * N + 1) / 2;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  if constexpr (sizeof(T) == 4 && !K16) {
+    static const bool use_ts = [] { const char* e = getenv("AHV_TC_VARIANT"); return !(e && e[0] == 's'); }();
+    if (use_ts) {
+      AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
+      score_tc_ts_kernel<<<grid, kThreadsTC, MapTS::smem_bytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,
+                                                                     b2, base, (const uint4*)sc.w_packed, sc.pair_scale, scores,
+                                                                     want_argmax ? sc.best_keys : nullptr, B, N);
+      AHV_CUDA_OK(cudaGetLastError());
+      return AHV_OK;
+    }
+  }
   constexpr int kSmemBytes = Map<K16>::smem_bytes;
   AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   score_tc_kernel<T, K16><<<grid, kThreadsTC, kSmemBytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,

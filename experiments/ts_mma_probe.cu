@@ -12,7 +12,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
   return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-constexpr uint32_t instr_desc(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
 __global__ void __launch_bounds__(128, 1) probe(float* out /*[128][32]*/, int a_lane_off_slot1) {
   __shared__ __align__(128) unsigned char bsm[1024];  // B: [chalf][ngroup][8][8] fp16, N=32, K=16
