@@ -632,13 +632,13 @@ struct MapTS {
   static constexpr int off_w1 = off_vol + kVolSmemBytes;
   static constexpr int off_w2 = off_w1 + kW1Bytes;
   static constexpr int off_a = off_w2 + kW2Bytes;
-  static constexpr int off_a2 = off_a + kStages * tile_bytes;
-  static constexpr int off_bar = off_a2 + 2 * kA2Bytes;
+  static constexpr int off_bar = off_a + kStages * tile_bytes;
   static constexpr int off_misc = off_bar + 16 * 8;
   static constexpr int smem_bytes = off_misc + 256;
-  static constexpr int tmem_cols = 512;      // D1[2] 0..63, D2[2] 64..127, A_x[3] 128 + 64*stage
+  static constexpr int tmem_cols = 512;      // D1[2] 0..63, D2[2] 64..127, A_x[3] 128 + 64*stage, A2[2] 448 + 16*buf
   static constexpr int tmem_ax = 128;
-  static_assert(off_a % 128 == 0 && off_a2 % 128 == 0 && off_bar % 8 == 0, "align");
+  static constexpr int tmem_a2 = 448;
+  static_assert(off_a % 128 == 0 && off_bar % 8 == 0, "align");
   static_assert(smem_bytes <= 232448, "shared memory budget");
 };
 
@@ -652,6 +652,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -857,10 +864,9 @@ score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ 
         const uint32_t gb = gg & 1, u = gg >> 1;
         mbar_wait(bar0 + (kA2Full + gb) * 8, u & 1);
         tc_fence_after();
-        const uint32_t a2 = s_base + M::off_a2 + gb * kA2Bytes;
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-          umma_f16(tmem + 64 + gb * 32, smem_desc(a2 + i * 4096, 2048, 128), smem_desc(w2s + i * 1024, 512, 128), idesc2, i);
+        for (int i = 0; i < 2; ++i)  // conv2: A = ReLU(conv1) rows in TMEM (written by the epilogue), M = 128
+          umma_f16_ts(tmem + 64 + gb * 32, tmem + M::tmem_a2 + gb * 16 + i * 8, smem_desc(w2s + i * 1024, 512, 128), idesc2, i);
         umma_commit(bar0 + (kD2Full + gb) * 8);
       };
       while (it.advance()) {
@@ -898,7 +904,6 @@ score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ 
     const int s = warp - kEpiWarp0;
     const int slot = lane >> 4;
     const int pos = 16 * s + (lane & 15);
-    const uint32_t row = 32 * s + lane;
     float b2r[kO], tg[kO];
 #pragma unroll
     for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
@@ -955,19 +960,14 @@ score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ 
       uint32_t r[32];
       tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + gb * 32, r);
       tmem_ld_wait();
-      unsigned char* a2 = smem + M::off_a2 + gb * kA2Bytes + row * 16;
+      uint32_t wq[16];  // ReLU -> fp16, 32 channels of this thread's row = 16 TMEM columns of conv2's A operand
 #pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        uint32_t wq[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[kc * 8 + 2 * e]), 0.0f),
-                                               fmaxf(__uint_as_float(r[kc * 8 + 2 * e + 1]), 0.0f));
-          wq[e] = *reinterpret_cast<const uint32_t*>(&hh);
-        }
-        *reinterpret_cast<uint4*>(a2 + kc * 2048) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+      for (int e = 0; e < 16; ++e) {
+        const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * e]), 0.0f), fmaxf(__uint_as_float(r[2 * e + 1]), 0.0f));
+        wq[e] = *reinterpret_cast<const uint32_t*>(&hh);
       }
-      fence_proxy_async();
+      tmem_st16(tmem + ((uint32_t)(32 * s) << 16) + M::tmem_a2 + gb * 16, wq);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
