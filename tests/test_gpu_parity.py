@@ -375,3 +375,31 @@ def test_f16_gather_fast_mode_within_fp32_gate(ahv, golden):
     assert err <= 1e-3, err
     assert _top1_ok(s, g["scores"], r.topk_idx[:, 0].cpu().numpy(), 1e-3)
     assert np.array_equal(r.topk_idx[:, 0].cpu().numpy(), s.argmax(1))
+
+
+def test_ss_variant_still_matches(golden):
+    """The SS fp32 kernel (both conv1 operand copies in shared memory) stays selectable with
+    AHV_TC_VARIANT=ss; run it in a fresh process and compare with the goldens."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import importlib, os, sys, numpy as np, torch
+sys.path.insert(0, ROOT)
+ahv = importlib.import_module("3dahv_b200")
+dev = torch.device("cuda", 0)
+g = dict(np.load(os.path.join(ROOT, "tests/golden/shared_n3000_b3.npz"))); w = dict(np.load(os.path.join(ROOT, "tests/golden/weights.npz")))
+T = lambda a: torch.from_numpy(a).to(dev)
+v = ahv.HypothesisVerifier(T(w["W1"]), T(w["W2"]), T(w["b2"]))
+r = v.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=1, return_scores=True)
+s = r.scores.cpu().numpy()
+err = float(np.max(np.abs(s - g["scores"]) / np.abs(g["scores"])))
+assert err <= 1e-3, err
+assert np.array_equal(r.topk_idx[:, 0].cpu().numpy(), s.argmax(1))
+print("SS-OK", err)
+'''.replace("ROOT", repr(root))
+    env = dict(os.environ, AHV_TC_VARIANT="ss")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "SS-OK" in out.stdout, out.stderr[-1500:]
