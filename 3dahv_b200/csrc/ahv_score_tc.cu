@@ -662,8 +662,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+template <typename T, bool K16>
 __global__ void __launch_bounds__(kThreadsTC, 1)
-score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ tgt_feat,
+score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_feat,
                    const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
                    const float* __restrict__ base, const uint4* __restrict__ w_packed,
                    const float2* __restrict__ pair_scale, float* __restrict__ scores,
@@ -726,7 +727,10 @@ score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ 
     for (int t = 0; t < 4; ++t) {
       const int ck = (rot + t) & 3;
       koff[t] = ck * 16;
-      syz[t] = slot * M::yz_bytes + (ck >> 1) * M::yz_ch + (ck & 1) * 8 + d * M::yz_d + h_ * M::yz_h;
+      if constexpr (!K16)  // fp32: chunk ck = channels 4ck..4ck+3 (8 B of fp16)
+        syz[t] = slot * M::yz_bytes + (ck >> 1) * M::yz_ch + (ck & 1) * 8 + d * M::yz_d + h_ * M::yz_h;
+      else                 // 16-bit: accumulator t&1 holds channel half (rot+t)&1 (16 B of fp16); t < 2 used
+        syz[t] = slot * M::yz_bytes + ((rot + t) & 1) * M::yz_ch + d * M::yz_d + h_ * M::yz_h;
     }
     const unsigned char* volb = smem + M::off_vol;
     const int gtid = threadIdx.x;
@@ -747,18 +751,37 @@ score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ 
     while (it.advance()) {
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);
-        const float* vg = vol_src + (size_t)it.b * kC * kVox;
+        const T* vg = vol_src + (size_t)it.b * kC * kVox;
         const float sc = pair_scale[it.b].x;
-        for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
-          const int v = task & 511, jj = task >> 9;
-          const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
-          const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
-          float4 o;
-          o.x = __ldg(vg + (jj * 4 + 0) * kVox + v) * sc;
-          o.y = __ldg(vg + (jj * 4 + 1) * kVox + v) * sc;
-          o.z = __ldg(vg + (jj * 4 + 2) * kVox + v) * sc;
-          o.w = __ldg(vg + (jj * 4 + 3) * kVox + v) * sc;
-          *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
+        if constexpr (!K16) {
+          for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
+            const int v = task & 511, jj = task >> 9;
+            const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
+            const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
+            float4 o;
+            o.x = ld_vol<T>(vg + (jj * 4 + 0) * kVox + v) * sc;
+            o.y = ld_vol<T>(vg + (jj * 4 + 1) * kVox + v) * sc;
+            o.z = ld_vol<T>(vg + (jj * 4 + 2) * kVox + v) * sc;
+            o.w = ld_vol<T>(vg + (jj * 4 + 3) * kVox + v) * sc;
+            *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
+          }
+        } else {
+          // x-pair lines (see the SS kernel): every voxel is tap 0 of pair xh and tap 1 of pair xh-1
+          for (int task = gtid; task < 2 * kVox; task += kGatherWarps * 32) {
+            const int v = task & 511, chalf = task >> 9;
+            const int zh = (v >> 6) + 1, yh = ((v >> 3) & 7) + 1, xh = (v & 7) + 1;
+            uint32_t pk8[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 two = __floats2half2_rn(ld_vol<T>(vg + (chalf * 8 + 2 * e) * kVox + v) * sc,
+                                                    ld_vol<T>(vg + (chalf * 8 + 2 * e + 1) * kVox + v) * sc);
+              pk8[e] = *reinterpret_cast<const uint32_t*>(&two);
+            }
+            const uint4 q4 = make_uint4(pk8[0], pk8[1], pk8[2], pk8[3]);
+            unsigned char* rowp = smem + M::off_vol + ((zh * kHalo + yh) * 9) * 64;
+            *reinterpret_cast<uint4*>(rowp + xh * 64 + chalf * 16) = q4;
+            *reinterpret_cast<uint4*>(rowp + (xh - 1) * 64 + 32 + chalf * 16) = q4;
+          }
         }
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
@@ -785,66 +808,126 @@ score_tc_ts_kernel(const float* __restrict__ vol_src, const float* __restrict__ 
         ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
         const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
         const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
-        const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
-        const int swap = (line ^ pf) & 1;
-        const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
-        const unsigned char* pa = volb + (line + swap) * 64;
-        const unsigned char* pb = volb + (line + 1 - swap) * 64;
-        float wa[4], wb[4];
+        if constexpr (!K16) {
+          const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
+          const int swap = (line ^ pf) & 1;
+          const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
+          const unsigned char* pa = volb + (line + swap) * 64;
+          const unsigned char* pb = volb + (line + 1 - swap) * 64;
+          float wa[4], wb[4];
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float wyz = ((c & 1) ? fy : 1.0f - fy) * ((c >> 1) ? fz : 1.0f - fz);
+            wa[c] = wyz * wxa;
+            wb[c] = wyz * wxb;
+          }
+          float4 buf[2][8];
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+            buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
+            buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
+          }
+          uint2 pk[4];
+  #pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t < 3) {
+  #pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+                buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
+                buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+              }
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 a = buf[t & 1][2 * c], q = buf[t & 1][2 * c + 1];
+              acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
+              acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
+              acc.x = fmaf(wb[c], q.x, acc.x); acc.y = fmaf(wb[c], q.y, acc.y);
+              acc.z = fmaf(wb[c], q.z, acc.z); acc.w = fmaf(wb[c], q.w, acc.w);
+            }
+            const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi2 = __floats2half2_rn(acc.z, acc.w);
+            pk[t].x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk[t].y = *reinterpret_cast<const uint32_t*>(&hi2);
+            *reinterpret_cast<uint2*>(st + syz[t] + w * 16) = pk[t];  // YZ copy: row w of core matrix (d,h,chalf)
+          }
+          // view x: un-rotate the chunks (chunk c was produced at step (c - rot) & 3) and store the 16 channels
+          // of this voxel as K slice w of this lane's accumulator row in TMEM
+          uint2 s1[4], o4[4];
+          const bool r1 = rot & 1, r2 = rot & 2;
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            s1[c].x = r1 ? pk[(c + 3) & 3].x : pk[c].x;
+            s1[c].y = r1 ? pk[(c + 3) & 3].y : pk[c].y;
+          }
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            o4[c].x = r2 ? s1[(c + 2) & 3].x : s1[c].x;
+            o4[c].y = r2 ? s1[(c + 2) & 3].y : s1[c].y;
+          }
+          const uint32_t regs[8] = {o4[0].x, o4[0].y, o4[1].x, o4[1].y, o4[2].x, o4[2].y, o4[3].x, o4[3].y};
+          tmem_st8(ax + w * 8, regs);
+        } else {
+          const int pline = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * 9 + ((int)x0 + 1);
+          const int swapy = (pline ^ pf) & 1;
+          const unsigned char* pa = volb + (pline + swapy * 9) * 64;
+          const unsigned char* pb = volb + (pline + (1 - swapy) * 9) * 64;
+          const float wya = swapy ? fy : 1.0f - fy, wyb = swapy ? 1.0f - fy : fy;
+          const __half2 wy2[2] = {__float2half2_rn(wya), __float2half2_rn(wyb)};
+          const __half2 wz2[2] = {__float2half2_rn(1.0f - fz), __float2half2_rn(fz)};
+          const __half2 wx2[2] = {__float2half2_rn(1.0f - fx), __float2half2_rn(fx)};
+          __half2 w4[4], wxt[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float wyz = ((c & 1) ? fy : 1.0f - fy) * ((c >> 1) ? fz : 1.0f - fz);
-          wa[c] = wyz * wxa;
-          wb[c] = wyz * wxb;
-        }
-        float4 buf[2][8];
+          for (int c = 0; c < 4; ++c) w4[c] = __hmul2(wy2[c >> 1], wz2[c & 1]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
-          buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
-          buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
-        }
-        uint2 pk[4];
+          for (int t = 0; t < 4; ++t) wxt[t] = (((rot + t) & 3) >> 1) ? wx2[1] : wx2[0];
+          __half2 acc[2][4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (t < 3) {
+          for (int e2 = 0; e2 < 4; ++e2) acc[0][e2] = acc[1][e2] = __float2half2_rn(0.0f);
+          uint4 buf[2][4];
+          constexpr int kDz = kHalo * 9 * 64;
+          buf[0][0] = *reinterpret_cast<const uint4*>(pa + koff[0]);
+          buf[0][1] = *reinterpret_cast<const uint4*>(pa + koff[0] + kDz);
+          buf[0][2] = *reinterpret_cast<const uint4*>(pb + koff[0]);
+          buf[0][3] = *reinterpret_cast<const uint4*>(pb + koff[0] + kDz);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t < 3) {
+              buf[(t + 1) & 1][0] = *reinterpret_cast<const uint4*>(pa + koff[t + 1]);
+              buf[(t + 1) & 1][1] = *reinterpret_cast<const uint4*>(pa + koff[t + 1] + kDz);
+              buf[(t + 1) & 1][2] = *reinterpret_cast<const uint4*>(pb + koff[t + 1]);
+              buf[(t + 1) & 1][3] = *reinterpret_cast<const uint4*>(pb + koff[t + 1] + kDz);
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
-              buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
-              buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+              const __half2 wg = __hmul2(wxt[t], w4[c]);
+              const uint4 q4 = buf[t & 1][c];
+              const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2)
+                acc[t & 1][k2] = __hfma2(wg, *reinterpret_cast<const __half2*>(&wd[k2]), acc[t & 1][k2]);
             }
           }
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          uint32_t a0[4], a1[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 a = buf[t & 1][2 * c], q = buf[t & 1][2 * c + 1];
-            acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
-            acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
-            acc.x = fmaf(wb[c], q.x, acc.x); acc.y = fmaf(wb[c], q.y, acc.y);
-            acc.z = fmaf(wb[c], q.z, acc.z); acc.w = fmaf(wb[c], q.w, acc.w);
+          for (int k2 = 0; k2 < 4; ++k2) {
+            a0[k2] = *reinterpret_cast<const uint32_t*>(&acc[0][k2]);
+            a1[k2] = *reinterpret_cast<const uint32_t*>(&acc[1][k2]);
           }
-          const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi2 = __floats2half2_rn(acc.z, acc.w);
-          pk[t].x = *reinterpret_cast<const uint32_t*>(&lo);
-          pk[t].y = *reinterpret_cast<const uint32_t*>(&hi2);
-          *reinterpret_cast<uint2*>(st + syz[t] + w * 16) = pk[t];  // YZ copy: row w of core matrix (d,h,chalf)
-        }
-        // view x: un-rotate the chunks (chunk c was produced at step (c - rot) & 3) and store the 16 channels
-        // of this voxel as K slice w of this lane's accumulator row in TMEM
-        uint2 s1[4], o4[4];
-        const bool r1 = rot & 1, r2 = rot & 2;
+          *reinterpret_cast<uint4*>(st + syz[0] + w * 16) = make_uint4(a0[0], a0[1], a0[2], a0[3]);
+          *reinterpret_cast<uint4*>(st + syz[1] + w * 16) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+          // view x: acc[0] holds channel half (rot&1); put the halves in channel order and store to TMEM
+          const bool sw = rot & 1;
+          uint32_t regs[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          s1[c].x = r1 ? pk[(c + 3) & 3].x : pk[c].x;
-          s1[c].y = r1 ? pk[(c + 3) & 3].y : pk[c].y;
+          for (int k2 = 0; k2 < 4; ++k2) {
+            regs[k2] = sw ? a1[k2] : a0[k2];
+            regs[4 + k2] = sw ? a0[k2] : a1[k2];
+          }
+          tmem_st8(ax + w * 8, regs);
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          o4[c].x = r2 ? s1[(c + 2) & 3].x : s1[c].x;
-          o4[c].y = r2 ? s1[(c + 2) & 3].y : s1[c].y;
-        }
-        const uint32_t regs[8] = {o4[0].x, o4[0].y, o4[1].x, o4[1].y, o4[2].x, o4[2].y, o4[3].x, o4[3].y};
-        tmem_st8(ax + w * 8, regs);
       }
       tmem_st_wait();
       fence_proxy_async();  // YZ stores -> async proxy
@@ -1138,13 +1221,13 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
   const int64_t tiles = ((int64_t)B * N + 1) / 2;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  if constexpr (sizeof(T) == 4 && !K16) {
+  {
     static const bool use_ts = [] { const char* e = getenv("AHV_TC_VARIANT"); return !(e && e[0] == 's'); }();
     if (use_ts) {
-      AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
-      score_tc_ts_kernel<<<grid, kThreadsTC, MapTS::smem_bytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,
-                                                                     b2, base, (const uint4*)sc.w_packed, sc.pair_scale, scores,
-                                                                     want_argmax ? sc.best_keys : nullptr, B, N);
+      AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
+      score_tc_ts_kernel<T, K16><<<grid, kThreadsTC, MapTS::smem_bytes, s>>>(
+          vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair, b2, base, (const uint4*)sc.w_packed, sc.pair_scale,
+          scores, want_argmax ? sc.best_keys : nullptr, B, N);
       AHV_CUDA_OK(cudaGetLastError());
       return AHV_OK;
     }
