@@ -245,6 +245,22 @@ def run_ours(args):
     torch.cuda.synchronize()
     kernel_ms = sum(a.elapsed_time(b_) for a, b_ in kev) / args.steps
 
+    # other arithmetic modes on the same workload (informational; the headline stays fp32 volumes + AHV_MATH_TC)
+    other = {}
+    if rank == 0:
+        def _rate(src, m):
+            for _ in range(2):
+                ahv.ops.score(src, tgt, R, verifier.W1, verifier.W2, verifier.b2, k=0, math=m, return_scores=False, workspace=ws)
+            a2, b2_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2.record()
+            for _ in range(3):
+                ahv.ops.score(src, tgt, R, verifier.W1, verifier.W2, verifier.b2, k=0, math=m, return_scores=False, workspace=ws)
+            b2_.record()
+            torch.cuda.synchronize()
+            return B * N * 3 / (a2.elapsed_time(b2_) * 1e-3)
+        other["bf16_volumes_tc"] = _rate(vs.bfloat16(), ahv.MATH_TC)
+        other["fp32_volumes_tc_f16gather"] = _rate(vs, ahv.MATH_TC_F16GATHER)
+
     # measured shared-memory read peak (no such figure in MEASURED_PEAKS.json)
     import ctypes
     nbytes = ctypes.c_ulonglong(0)
@@ -312,6 +328,7 @@ def run_ours(args):
             "voxel_samples_per_s": value * 512,
             "clocks": clocks,
             "latency_p50_per_pair": latency,
+            "other_modes_hyp_pairs_per_s": other,
             "e2e": {"value": units_per_step * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "api": "ahv_predict_host (C ABI, pinned host buffers)"},
             "gpu_launches": n_launch,

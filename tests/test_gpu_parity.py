@@ -398,7 +398,10 @@ s = r.scores.cpu().numpy()
 err = float(np.max(np.abs(s - g["scores"]) / np.abs(g["scores"])))
 assert err <= 1e-3, err
 assert np.array_equal(r.topk_idx[:, 0].cpu().numpy(), s.argmax(1))
-print("SS-OK", err)
+rb = v.score(T(g["vol_src"]).bfloat16(), T(g["vol_tgt"]), T(g["R"][:500]), k=1, return_scores=True)   # 16-bit gather, SS form
+errb = float(np.max(np.abs(rb.scores.cpu().numpy() - g["scores"][:, :500]) / np.abs(g["scores"][:, :500])))
+assert errb <= 1e-2, errb
+print("SS-OK", err, errb)
 '''.replace("ROOT", repr(root))
     env = dict(os.environ, AHV_TC_VARIANT="ss")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
