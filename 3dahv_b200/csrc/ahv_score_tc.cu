@@ -1,38 +1,38 @@
-// Fused hypothesis-and-verification kernel on tcgen05 tensor cores (AHV_MATH_TC).
+// Fused hypothesis-and-verification kernels on tcgen05 tensor cores (AHV_MATH_TC*).
 //
-// Replaces modules/model.py:186-193 (rotate_volume -> forward_3d2d -> correlate
-// -> mean) for every (pair, hypothesis) without materialising anything in HBM:
-// algorithmic HBM traffic is 36 B of rotation in and 4 B of score out.
+// Replace modules/model.py:186-193 (rotate_volume -> forward_3d2d -> correlate -> mean) for every
+// (pair, hypothesis) without materialising anything in HBM: algorithmic HBM traffic is 36 B of
+// rotation in and 4 B of score out (nothing at all when only the arg-max is requested).
 //
-// One persistent CTA per SM, 13 warps, warp-specialised:
-//   warps 0-7   GATHER   trilinear resampling (utils.py:113-131) of the source
-//                        volume held in shared memory (fp32, zero halo, channel
-//                        innermost, 64 B per voxel line).  One lane per output
-//                        voxel, all 16 channels; warp w owns the slab d = w.  The
-//                        four 16-byte channel chunks of a line are visited in a
-//                        per-lane rotated order and the two x taps in bank-parity
-//                        order, which makes every LDS.128 phase conflict-free by
-//                        construction.  Results are rounded to fp16 and written
-//                        as the tri-plane A operand of conv1 in UMMA K-major
-//                        core-matrix layout:
-//                        copy YZ  [chalf][d][h][w][c8]  serves views y and z,
-//                        copy X   [chalf][d][w][h][c8]  serves view x.
-//   warp  12    MMA      one elected thread issues tcgen05.mma (kind::f16, fp32
-//                        accumulate in TMEM): conv1 = 24 x (M=64,N=32,K=16) per
-//                        hypothesis, two hypotheses interleaved in the two
-//                        16-lane halves of each TMEM sub-partition; conv2 =
-//                        2 x (M=128,N=32,K=16) per hypothesis pair.
-//   warps 8-11  EPILOGUE tcgen05.ld D1 -> ReLU -> fp16 -> smem A2 (conv2 operand);
-//                        tcgen05.ld D2 -> +bias -> L2 norm -> dot with the target
-//                        features (registers) -> mean over 64 positions -> score.
-// Pipelines (mbarrier): A-operand stages full/empty (3 hypotheses deep), TMEM
-// D1 full/empty, A2 full, D2 full (double-buffered per hypothesis pair).
+// One persistent CTA per SM, 13 warps, warp-specialised (both kernels):
+//   warps 0-7   GATHER   trilinear resampling (utils.py:113-131) of the source volume held in shared
+//                        memory (zero halo, channel innermost).  One lane per output voxel, all 16
+//                        channels.  The 16-byte chunks of a voxel line are visited in a per-lane
+//                        rotated order and the two taps that sit in adjacent lines in bank-parity
+//                        order, which makes every LDS.128 phase conflict-free by construction.
+//                        Results are rounded to fp16 and become the tri-plane A operand of conv1.
+//   warp  12    MMA      one elected thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
+//                        conv1 = 24 x (M=64,N=32,K=16) per hypothesis - slice (view,k) multiplies the
+//                        16 channels at a fixed k, so the rearrange/cat of modules/modules.py:115-118
+//                        is pure descriptor arithmetic - two hypotheses interleaved in the two 16-lane
+//                        halves of each TMEM sub-partition; conv2 = 2 x (M=128,N=32,K=16) per pair.
+//   warps 8-11  EPILOGUE tcgen05.ld D1 -> ReLU -> fp16 -> conv2 operand; tcgen05.ld D2 -> +bias ->
+//                        L2 norm -> dot with the target features (registers) -> mean over 64
+//                        positions -> score (+ running arg-max key, one atomicMax per CTA and pair).
+// Pipelines (mbarrier): A-operand stages full/empty (3 deep), TMEM D1 full/empty, A2 full, D2 full.
 //
-// Precision: gather, normalisation and correlation are fp32; the two 1x1 convs
-// use fp16 operands (10-bit mantissa = TF32-equivalent) with fp32 accumulation.
-// The source volume is pre-scaled per pair by a power of two (exact) so fp16
-// can neither overflow nor go subnormal; the scale is undone after conv2
-// (ReLU and the bias-free conv1 are positively homogeneous).
+//   score_tc_ts_kernel  (default)  view x of conv1 and conv2's A operand go register -> TMEM
+//                        (tcgen05.st) and are consumed in the TS form of tcgen05.mma; only the YZ
+//                        operand copy lives in shared memory; a stage is a hypothesis pair.
+//   score_tc_kernel     (AHV_TC_VARIANT=ss)  both operand copies (YZ and X) and A2 in shared memory,
+//                        SS form only; a stage is one hypothesis.
+// Both exist for fp32-staged volumes (fp32 FFMA interpolation) and for 16-bit staged volumes
+// (K16: bf16 inputs or AHV_MATH_TC_F16GATHER; x-pair lines, packed HFMA2 interpolation).
+//
+// Precision: normalisation and correlation are fp32; the two 1x1 convs use fp16 operands (10-bit
+// mantissa = TF32-equivalent) with fp32 accumulation.  The source volume is pre-scaled per pair by a
+// power of two (exact) so fp16 can neither overflow nor go subnormal; the scale is undone after
+// conv2 (ReLU and the bias-free conv1 are positively homogeneous).
 #include <cstdlib>
 
 #include "ahv_head_fp32.cuh"

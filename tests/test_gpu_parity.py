@@ -406,3 +406,30 @@ print("SS-OK", err, errb)
     env = dict(os.environ, AHV_TC_VARIANT="ss")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "SS-OK" in out.stdout, out.stderr[-1500:]
+
+
+def test_non_finite_inputs_do_not_hang_or_fault(ahv, golden):
+    """NaN / Inf in rotations or volumes must neither hang the pipeline nor read out of bounds:
+    coordinates are clamped with NaN-dropping min/max and the scale ignores non-finite maxima."""
+    dev = _dev()
+    g = golden["shared_n3000_b3"]
+    vs, vt = torch.from_numpy(g["vol_src"]).to(dev), torch.from_numpy(g["vol_tgt"]).to(dev)
+    R = torch.from_numpy(g["R"][:65]).to(dev).clone()
+    R[3] = float("nan")
+    R[7, 0, 0] = float("inf")
+    R[9] = 1e30
+    for math in (ahv.MATH_TC, ahv.MATH_FP32, ahv.MATH_TC_F16GATHER):
+        v = ahv.HypothesisVerifier(*_weights(golden, dev), math=math)
+        r = v.score(vs, vt, R, k=1, return_scores=True)
+        torch.cuda.synchronize()
+        ok = torch.ones(65, dtype=torch.bool, device=dev)
+        ok[[3, 7, 9]] = False
+        assert torch.isfinite(r.scores[:, ok]).all()
+        clean = v.score(vs, vt, R[ok].contiguous(), k=1, return_scores=True)
+        assert torch.equal(r.scores[:, ok], clean.scores)          # bad hypotheses do not disturb the others
+        assert ((r.topk_idx >= 0) & (r.topk_idx < 65)).all()
+    bad = vs.clone()
+    bad[1, 3, 2, 2, 2] = float("inf")
+    r = ahv.HypothesisVerifier(*_weights(golden, dev)).score(bad, vt, R[:8].contiguous(), k=1, return_scores=True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(r.scores[0]).all() and torch.isfinite(r.scores[2]).all()
