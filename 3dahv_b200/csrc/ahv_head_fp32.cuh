@@ -27,11 +27,11 @@ struct Fp32Smem {
 __device__ __forceinline__ void stage_weights(Fp32Smem& sm, const float* __restrict__ W1,
                                               const float* __restrict__ W2,
                                               const float* __restrict__ base) {
-  for (int i = threadIdx.x; i < kO * kK; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kO * kK; i += kThreads) {
     const int k = i >> 5, o = i & 31;  // consecutive lanes -> consecutive smem words (the 48 KB read is L2-served)
     sm.w1t[i] = __ldg(W1 + o * kK + k);
   }
-  for (int i = threadIdx.x; i < kO * kO; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kO * kO; i += kThreads) {
     int o = i / kO, c = i % kO;
     sm.w2s[((o % 8) * 4 + o / 8) * kH1Row + c] = W2[i];
   }
@@ -61,7 +61,7 @@ __device__ __forceinline__ void stage_volume(float* __restrict__ vol, const T* _
 // plain (un-rotated) volume [16][512] -> rotA / rotT (forward_3d2d on its own)
 template <typename T>
 __device__ __forceinline__ void load_plain_volume(Fp32Smem& sm, const T* __restrict__ vol_g) {
-  for (int i = threadIdx.x; i < kC * kVox; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kC * kVox; i += kThreads) {
     int c = i >> 9, v = i & 511;
     int d = v >> 6, h = (v >> 3) & 7, w = v & 7;
     float x = to_f32<T>(vol_g[i]);
@@ -155,65 +155,6 @@ __device__ __forceinline__ void forward_3d2d_block(Fp32Smem& sm, const T* __rest
   const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (modules/modules.py:122)
 #pragma unroll
   for (int oo = 0; oo < 8; ++oo) feat_out[(cg2 * 8 + oo) * kP + pos] = v[oo] * inv;
-}
-
-// Latency variant for a 1024-thread CTA: conv1's K=384 is split four ways (thread = 256*ks + t takes
-// 12 of the 48 (view, channel) blocks), partial sums meet in shared memory (sm.vol is free in callers
-// that only compute features), then threads 0..255 finish exactly like forward_3d2d_block.  The
-// summation order differs from the 256-thread version (4 partial sums), i.e. results agree to ~1e-7.
-template <typename T>
-__device__ __forceinline__ void forward_3d2d_block_ksplit4(Fp32Smem& sm, const T* __restrict__ vol_g,
-                                                           const float* b2r, float* __restrict__ feat_out) {
-  const int ks = threadIdx.x >> 8, t = threadIdx.x & 255;
-  __syncthreads();
-  load_plain_volume<T>(sm, vol_g);
-  __syncthreads();
-  {
-    const int cg = t & 15, pg = t >> 4;
-    const int p = pg >> 1, q0 = (pg & 1) * 4;
-    float acc[4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0f;
-    const float* wbase = sm.w1t + 2 * cg;
-#pragma unroll 1
-    for (int blk = ks * 12; blk < ks * 12 + 12; ++blk) {
-      const int view = blk >> 4, c = blk & 15;
-      const float* a0 = (view == 0 ? sm.rotT : sm.rotA) + (view == 2 ? p * 8 + q0 : p * kRotD + q0) + c * kRotC;
-      const int kstride = (view == 2) ? kRotD : 8;
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const float4 a = *reinterpret_cast<const float4*>(a0 + kk * kstride);
-        const float2 w = *reinterpret_cast<const float2*>(wbase + (view * 128 + c * 8 + kk) * kO);
-        acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
-        acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
-        acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]);
-        acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]);
-      }
-    }
-    float* part = sm.vol + ks * (kP * kH1Row);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float2*>(part + (p * 8 + q0 + i) * kH1Row + 2 * cg) = make_float2(acc[i][0], acc[i][1]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kP * kO; i += blockDim.x) {
-    const int pos = i >> 5, o = i & 31, at = pos * kH1Row + o;
-    const float v = ((sm.vol[at] + sm.vol[kP * kH1Row + at]) + sm.vol[2 * kP * kH1Row + at]) + sm.vol[3 * kP * kH1Row + at];
-    sm.h1s[at] = fmaxf(v, 0.0f);
-  }
-  __syncthreads();
-  if (threadIdx.x < 256) {
-    const int pos = threadIdx.x >> 2, cg2 = threadIdx.x & 3;
-    float v[8];
-    conv2_bias(sm, b2r, v);
-    float ss = 0.0f;
-#pragma unroll
-    for (int oo = 0; oo < 8; ++oo) ss = fmaf(v[oo], v[oo], ss);
-    ss = quad_sum(ss);
-    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-    for (int oo = 0; oo < 8; ++oo) feat_out[(cg2 * 8 + oo) * kP + pos] = v[oo] * inv;
-  }
 }
 
 }  // namespace ahv

@@ -1084,10 +1084,8 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
 //   blocks 1..B    : per-pair power-of-two scale
 //   blocks B+1..2B : target features forward_3d2d(vol_tgt[b]) (modules/model.py:191), fp32 FFMA
 // w_packed: conv1 B operand, 24 slices j=(view,kk): [chalf][ngroup][n%8][c%8] fp16, then conv2's.
-constexpr int kPrologueThreads = 1024;
-
 template <typename T>
-__global__ void __launch_bounds__(kPrologueThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 tc_prologue_kernel(const T* __restrict__ vol_src, const float* __restrict__ vol_tgt,
                    const float* __restrict__ W1, const float* __restrict__ W2,
                    const float* __restrict__ b2, __half* __restrict__ w_packed,
@@ -1098,18 +1096,18 @@ tc_prologue_kernel(const T* __restrict__ vol_src, const float* __restrict__ vol_
   __shared__ float l1max_s;
   const int t = threadIdx.x;
   if (blockIdx.x == 0) {
-    for (int i = t; i < kO * kK; i += kPrologueThreads) {
+    for (int i = t; i < kO * kK; i += kThreads) {
       const int n = i / kK, k = i % kK;
       const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7;
       const int j = view * 8 + kk;
       w_packed[j * 512 + (c >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (c & 7)] = __float2half_rn(W1[i]);
     }
-    for (int i = t; i < kO * kO; i += kPrologueThreads) {
+    for (int i = t; i < kO * kO; i += kThreads) {
       const int n = i / kO, k = i % kO;
       w_packed[kW1Bytes / 2 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2half_rn(W2[i]);
     }
     if (best_keys)
-      for (int i = t; i < B; i += kPrologueThreads) best_keys[i] = 0ull;
+      for (int i = t; i < B; i += kThreads) best_keys[i] = 0ull;
     return;
   }
   if ((int)blockIdx.x > B) {  // target features
@@ -1119,11 +1117,10 @@ tc_prologue_kernel(const T* __restrict__ vol_src, const float* __restrict__ vol_
     float b2r[8];
 #pragma unroll
     for (int oo = 0; oo < 8; ++oo) b2r[oo] = b2[(t & 3) * 8 + oo];
-    forward_3d2d_block_ksplit4<float>(sm, vol_tgt + (size_t)b * kC * kVox, b2r, tgt_feat + (size_t)b * kO * kP);
+    forward_3d2d_block<float>(sm, vol_tgt + (size_t)b * kC * kVox, b2r, tgt_feat + (size_t)b * kO * kP);
     return;
   }
   const int b = blockIdx.x - 1;
-  if (t >= 256) return;  // the scale job is small: one quarter of the CTA does it (no __syncthreads below is CTA-wide)
   // largest L1 norm of a W1 row bounds |conv1 output| / max|V|
   float l1 = 0.0f;
   {
@@ -1135,22 +1132,22 @@ tc_prologue_kernel(const T* __restrict__ vol_src, const float* __restrict__ vol_
 #pragma unroll
     for (int o2 = 8; o2 < 32; o2 <<= 1) l1 = fmaxf(l1, __shfl_xor_sync(0xffffffffu, l1, o2));
     if ((t & 31) == 0) red[t >> 5] = l1;
-    named_bar_sync(3, 256);
+    __syncthreads();
     if (t == 0) {
       float m = red[0];
       for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
       l1max_s = m;
     }
-    named_bar_sync(3, 256);
+    __syncthreads();
   }
   float mx = 0.0f;
   const T* v = vol_src + (size_t)b * kC * kVox;
-  for (int i = t; i < kC * kVox; i += 256) mx = fmaxf(mx, fabsf(ld_vol<T>(v + i)));
+  for (int i = t; i < kC * kVox; i += kThreads) mx = fmaxf(mx, fabsf(ld_vol<T>(v + i)));
 #pragma unroll
   for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-  named_bar_sync(3, 256);
+  __syncthreads();
   if ((t & 31) == 0) red[t >> 5] = mx;
-  named_bar_sync(3, 256);
+  __syncthreads();
   if (t == 0) {
     float m = red[0];
     for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
@@ -1217,7 +1214,7 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   const size_t pro_smem = vol_tgt ? sizeof(Fp32Smem) : 0;
   AHV_CUDA_OK(cudaFuncSetAttribute(tc_prologue_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(Fp32Smem)));
-  tc_prologue_kernel<T><<<pro_blocks, kPrologueThreads, pro_smem, s>>>(vol_src, vol_tgt, W1, W2, b2, sc.w_packed,
+  tc_prologue_kernel<T><<<pro_blocks, kThreads, pro_smem, s>>>(vol_src, vol_tgt, W1, W2, b2, sc.w_packed,
                                                               sc.pair_scale, want_argmax ? sc.best_keys : nullptr,
                                                               sc.tgt_feat, B);
   AHV_CUDA_OK(cudaGetLastError());
