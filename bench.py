@@ -321,6 +321,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "dtype_detail": "fp32 volumes, trilinear gather / normalise / correlate in fp32; the two 1x1 convs use fp16 "
+                            "operands (10-bit mantissa, TF32-equivalent) with fp32 accumulation on tcgen05; scores within "
+                            "1.3e-4 relative of the reference's fp32 CPU path (gate 1e-3)",
             "config": {"workload": f"CO3D config 2 (BASELINE.json configs[1]): B={B} pairs x N={N} hypotheses per GPU, "
                                    f"fp32 volumes, shared rotation set, top-{k}; N>1 = weak scaling over hypothesis shards "
                                    f"+ NCCL all-gather of top-k", "pairs": B, "hypotheses_per_gpu": N, "math": args.math,

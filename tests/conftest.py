@@ -24,9 +24,23 @@ def golden():
     return out
 
 
+def _ensure_built():
+    """Tests may run before the driver's build(): compile the library in-tree if it is missing
+    (test convenience only - the product loader itself fails loudly on a missing library)."""
+    lib = os.path.join(ROOT, "3dahv_b200", "lib3dahv_b200.so")
+    if not os.path.exists(lib):
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("ahv_build", os.path.join(ROOT, "3dahv_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+
+
 @pytest.fixture(scope="session")
 def ahv():
     """The product package (loads lib3dahv_b200.so lazily)."""
+    _ensure_built()
     return importlib.import_module("3dahv_b200")
 
 
