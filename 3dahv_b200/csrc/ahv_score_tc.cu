@@ -800,63 +800,53 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       const uint32_t ax = tmem + ((uint32_t)(32 * sub) << 16) + M::tmem_ax + stage * 64;
       // grid = R @ (x, y, z): y and z are fixed per lane, x walks with w
       const float pgx = fmaf(Rr[2], bz, Rr[1] * by), pgy = fmaf(Rr[5], bz, Rr[4] * by), pgz = fmaf(Rr[8], bz, Rr[7] * by);
-      if constexpr (!K16) {
-        // fp32 gather, software-pipelined ACROSS voxels: the taps of voxel w+1 are computed and its first
-        // load batch is issued before the last batch of voxel w is consumed, so the LSU pipe does not
-        // drain at voxel boundaries
-        struct Taps { const unsigned char *pa, *pb; float wa[4], wb[4]; };
-        auto make_taps = [&](int w) {
-          const float bx = sbase[w];
-          float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
-          ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
-          const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
-          const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
+#pragma unroll 1
+      for (int wi = 0; wi < 4; ++wi) {
+        const int w = whalf * 4 + wi;
+        const float bx = sbase[w];
+        float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
+        ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
+        const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
+        const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
+        if constexpr (!K16) {
           const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
-          const int swap = (line ^ pf) & 1;  // first x tap = the one whose 64 B line has bank parity pf
+          const int swap = (line ^ pf) & 1;
           const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
-          Taps tp;
-          tp.pa = volb + (line + swap) * 64;
-          tp.pb = volb + (line + 1 - swap) * 64;
-#pragma unroll
+          const unsigned char* pa = volb + (line + swap) * 64;
+          const unsigned char* pb = volb + (line + 1 - swap) * 64;
+          float wa[4], wb[4];
+  #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float wyz = ((c & 1) ? fy : 1.0f - fy) * ((c >> 1) ? fz : 1.0f - fz);
-            tp.wa[c] = wyz * wxa;
-            tp.wb[c] = wyz * wxb;
+            wa[c] = wyz * wxa;
+            wb[c] = wyz * wxb;
           }
-          return tp;
-        };
-        float4 buf[2][8];
-        auto load_batch = [&](float4* dst, const Taps& tp, int t) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {  // c = dz*2 + dy
+          float4 buf[2][8];
+  #pragma unroll
+          for (int c = 0; c < 4; ++c) {
             const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
-            dst[2 * c] = *reinterpret_cast<const float4*>(tp.pa + koff[t] + off);
-            dst[2 * c + 1] = *reinterpret_cast<const float4*>(tp.pb + koff[t] + off);
+            buf[0][2 * c] = *reinterpret_cast<const float4*>(pa + koff[0] + off);
+            buf[0][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[0] + off);
           }
-        };
-        Taps cur = make_taps(whalf * 4);
-        load_batch(buf[0], cur, 0);
-#pragma unroll
-        for (int wi = 0; wi < 4; ++wi) {
-          const int w = whalf * 4 + wi;
-          Taps nxt = cur;
           uint2 pk[4];
-#pragma unroll
+  #pragma unroll
           for (int t = 0; t < 4; ++t) {
             if (t < 3) {
-              load_batch(buf[(t + 1) & 1], cur, t + 1);
-            } else if (wi < 3) {
-              nxt = make_taps(w + 1);
-              load_batch(buf[0], nxt, 0);
+  #pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int off = ((c >> 1) * kHalo * kHalo + (c & 1) * kHalo) * 64;
+                buf[(t + 1) & 1][2 * c] = *reinterpret_cast<const float4*>(pa + koff[t + 1] + off);
+                buf[(t + 1) & 1][2 * c + 1] = *reinterpret_cast<const float4*>(pb + koff[t + 1] + off);
+              }
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+  #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float4 a = buf[t & 1][2 * c], q = buf[t & 1][2 * c + 1];
-              acc.x = fmaf(cur.wa[c], a.x, acc.x); acc.y = fmaf(cur.wa[c], a.y, acc.y);
-              acc.z = fmaf(cur.wa[c], a.z, acc.z); acc.w = fmaf(cur.wa[c], a.w, acc.w);
-              acc.x = fmaf(cur.wb[c], q.x, acc.x); acc.y = fmaf(cur.wb[c], q.y, acc.y);
-              acc.z = fmaf(cur.wb[c], q.z, acc.z); acc.w = fmaf(cur.wb[c], q.w, acc.w);
+              acc.x = fmaf(wa[c], a.x, acc.x); acc.y = fmaf(wa[c], a.y, acc.y);
+              acc.z = fmaf(wa[c], a.z, acc.z); acc.w = fmaf(wa[c], a.w, acc.w);
+              acc.x = fmaf(wb[c], q.x, acc.x); acc.y = fmaf(wb[c], q.y, acc.y);
+              acc.z = fmaf(wb[c], q.z, acc.z); acc.w = fmaf(wb[c], q.w, acc.w);
             }
             const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi2 = __floats2half2_rn(acc.z, acc.w);
             pk[t].x = *reinterpret_cast<const uint32_t*>(&lo);
@@ -867,30 +857,19 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
           // of this voxel as K slice w of this lane's accumulator row in TMEM
           uint2 s1[4], o4[4];
           const bool r1 = rot & 1, r2 = rot & 2;
-#pragma unroll
+  #pragma unroll
           for (int c = 0; c < 4; ++c) {
             s1[c].x = r1 ? pk[(c + 3) & 3].x : pk[c].x;
             s1[c].y = r1 ? pk[(c + 3) & 3].y : pk[c].y;
           }
-#pragma unroll
+  #pragma unroll
           for (int c = 0; c < 4; ++c) {
             o4[c].x = r2 ? s1[(c + 2) & 3].x : s1[c].x;
             o4[c].y = r2 ? s1[(c + 2) & 3].y : s1[c].y;
           }
           const uint32_t regs[8] = {o4[0].x, o4[0].y, o4[1].x, o4[1].y, o4[2].x, o4[2].y, o4[3].x, o4[3].y};
           tmem_st8(ax + w * 8, regs);
-          cur = nxt;
-        }
-      } else {
-#pragma unroll 1
-      for (int wi = 0; wi < 4; ++wi) {
-        const int w = whalf * 4 + wi;
-        const float bx = sbase[w];
-        float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
-        ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
-        const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
-        const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
-        {
+        } else {
           const int pline = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * 9 + ((int)x0 + 1);
           const int swapy = (pline ^ pf) & 1;
           const unsigned char* pa = volb + (pline + swapy * 9) * 64;
@@ -949,7 +928,6 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
           }
           tmem_st8(ax + w * 8, regs);
         }
-      }
       }
       tmem_st_wait();
       fence_proxy_async();  // YZ stores -> async proxy
