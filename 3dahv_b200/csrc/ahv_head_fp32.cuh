@@ -10,10 +10,11 @@ constexpr int kThreads = 256;
 constexpr int kRotD = 72;          // padded (h,w) plane
 constexpr int kRotC = kS * kRotD;  // 576 floats per channel
 constexpr int kH1Row = 36;
+constexpr int kW1Pitch = 34;         // transposed W1 rows padded 32 -> 34 floats: coalesced staging, conflict-free float2 reads
 
 struct Fp32Smem {
   float vol[kLines * kC];
-  float w1t[kK * kO];
+  float w1t[kK * kW1Pitch];
   float rotA[kC * kRotC];
   float rotT[kC * kRotC];
   float h1s[kP * kH1Row];
@@ -28,8 +29,8 @@ __device__ __forceinline__ void stage_weights(Fp32Smem& sm, const float* __restr
                                               const float* __restrict__ W2,
                                               const float* __restrict__ base) {
   for (int i = threadIdx.x; i < kO * kK; i += kThreads) {
-    const int k = i >> 5, o = i & 31;  // consecutive lanes -> consecutive smem words (the 48 KB read is L2-served)
-    sm.w1t[i] = __ldg(W1 + o * kK + k);
+    const int o = i / kK, k = i - o * kK;  // coalesced read of W1[o][k]; store banks (2k + o) mod 32: 2-way at worst
+    sm.w1t[k * kW1Pitch + o] = __ldg(W1 + i);
   }
   for (int i = threadIdx.x; i < kO * kO; i += kThreads) {
     int o = i / kO, c = i % kO;
@@ -90,7 +91,7 @@ __device__ __forceinline__ void conv1_relu(Fp32Smem& sm) {
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         const float4 a = *reinterpret_cast<const float4*>(a0 + c * kRotC + kk * kstride);
-        const float2 w = *reinterpret_cast<const float2*>(wbase + (view * 128 + c * 8 + kk) * kO);
+        const float2 w = *reinterpret_cast<const float2*>(wbase + (view * 128 + c * 8 + kk) * kW1Pitch);
         acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
         acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
         acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]);
