@@ -433,3 +433,63 @@ def test_non_finite_inputs_do_not_hang_or_fault(ahv, golden):
     r = ahv.HypothesisVerifier(*_weights(golden, dev)).score(bad, vt, R[:8].contiguous(), k=1, return_scores=True)
     torch.cuda.synchronize()
     assert torch.isfinite(r.scores[0]).all() and torch.isfinite(r.scores[2]).all()
+
+
+@pytest.mark.parametrize("B,N", [(64, 3), (200, 1), (7, 2), (150, 5), (33, 17), (2, 149), (3, 296)])
+@pytest.mark.parametrize("voldt", ["f32", "bf16"])
+def test_many_pairs_tiny_hypothesis_sets(ahv, golden, B, N, voldt):
+    """Every CTA range crosses pair boundaries and most tiles are odd tails: stresses volume
+    re-staging, the per-pair arg-max flush and the two-hypothesis tiling.  The fp32 CUDA-core
+    kernel (independent code path) is the on-device reference."""
+    dev = _dev()
+    gen = torch.Generator().manual_seed(B * 131 + N)
+    vs = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+    vt = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+    if voldt == "bf16":
+        vs = vs.bfloat16()
+    for per_pair in (False, True):
+        R = ahv.so3.sample_rotations(B * N if per_pair else N, seed=N + B, device=dev)
+        R = R.reshape(B, N, 3, 3).contiguous() if per_pair else R
+        ref = ahv.HypothesisVerifier(*_weights(golden, dev), math=ahv.MATH_FP32).score(vs, vt, R, k=1, return_scores=True)
+        got = ahv.HypothesisVerifier(*_weights(golden, dev), math=ahv.MATH_TC).score(vs, vt, R, k=1, return_scores=True)
+        tol = 1e-3 if voldt == "f32" else 2e-3      # bf16 volumes: fp16 interpolation adds ~1e-4 on top
+        rel = ((got.scores - ref.scores).abs() / ref.scores.abs().clamp_min(1e-6)).max().item()
+        assert rel <= tol, (per_pair, rel)
+        assert torch.equal(got.topk_idx[:, 0], got.scores.argmax(1))
+        assert torch.equal(got.topk_val[:, 0], got.scores.max(1).values)
+        noscore = ahv.HypothesisVerifier(*_weights(golden, dev)).score(vs, vt, R, k=1, return_scores=False)
+        assert torch.equal(noscore.topk_idx, got.topk_idx) and torch.equal(noscore.R_best, got.R_best)
+        k2 = min(3, N)
+        multi = ahv.HypothesisVerifier(*_weights(golden, dev)).score(vs, vt, R, k=k2, return_scores=True)
+        assert torch.equal(multi.scores, got.scores)
+        tv, _ = torch.topk(got.scores, k2, dim=1)
+        assert torch.equal(multi.topk_val, tv)
+
+
+def test_graphed_verifier_matches_eager(ahv, golden):
+    dev = _dev()
+    g = golden["shared_n3000_b3"]
+    T = lambda a: torch.from_numpy(a).to(dev)
+    v = ahv.HypothesisVerifier(*_weights(golden, dev))
+    eager = v.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=1, return_scores=False)
+    gv = ahv.GraphedVerifier(v, 3, 3000, k=1, device=dev)
+    out = gv(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]))
+    torch.cuda.synchronize()
+    assert torch.equal(out.topk_idx, eager.topk_idx) and torch.equal(out.topk_val, eager.topk_val)
+    assert torch.equal(out.R_best, eager.R_best)
+    # replay with new inputs
+    out2 = gv(T(g["vol_src"]).flip(0), T(g["vol_tgt"]).flip(0))
+    torch.cuda.synchronize()
+    assert torch.equal(out2.topk_idx, eager.topk_idx.flip(0))
+
+
+def test_predict_host_topk_and_per_pair(ahv, golden):
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    T = torch.from_numpy
+    Rp = T(np.stack([g["R"][:100], g["R"][100:200], g["R"][200:300]]))
+    scores, val, idx, Rb = ahv.ops.predict_host(T(g["vol_src"]), T(g["vol_tgt"]), Rp, T(w["W1"]), T(w["W2"]), T(w["b2"]),
+                                                k=5, return_scores=True)
+    tv, ti = torch.topk(scores, 5, dim=1)
+    assert torch.equal(val, tv)
+    assert torch.equal(Rb, torch.gather(Rp, 1, idx[..., None, None].expand(-1, -1, 3, 3)))
+    assert _relerr(scores[0].numpy(), g["scores"][0, :100]) <= 1e-3
