@@ -187,9 +187,22 @@ def run_ours(args):
     math = {"tc": ahv.MATH_TC, "fp32": ahv.MATH_FP32}[args.math]
 
     B, N, k = args.pairs, args.hyps, TOPK
-    W1, W2, b2, vs_h, vt_h, normals_h = synthetic_inputs(torch, B, N * world)
-    # this rank's shard of the N*world rotation set (global index offset = rank*N)
-    normals_h = normals_h[rank * N:(rank + 1) * N].contiguous()
+    strong = args.config == 3
+    if strong:
+        # BASELINE config 3: 128 pairs, bf16 volumes, ONE 50 000-hypothesis set sharded over the ranks
+        B = 128 if args.pairs == PAIRS else args.pairs
+        total_hyps = args.hyps
+        lo, hi = ahv.dist.shard_bounds(total_hyps, rank, world)
+        N = hi - lo
+        W1, W2, b2, vs_h, vt_h, normals_h = synthetic_inputs(torch, B, total_hyps)
+        normals_h = normals_h[lo:hi].contiguous()
+        vs_h = vs_h.bfloat16()
+        shard_lo = lo
+    else:
+        W1, W2, b2, vs_h, vt_h, normals_h = synthetic_inputs(torch, B, N * world)
+        # this rank's shard of the N*world rotation set (global index offset = rank*N)
+        normals_h = normals_h[rank * N:(rank + 1) * N].contiguous()
+        shard_lo = rank * N
     verifier = ahv.HypothesisVerifier(W1.to(dev), W2.to(dev), b2.to(dev), math=math)
     vs, vt = vs_h.to(dev), vt_h.to(dev)
     R = ahv.ops.rotations_from_normals(normals_h.to(dev))
@@ -201,12 +214,12 @@ def run_ours(args):
             r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=0, gather=True)
             launches["n"] += 3
             return r.topk_val, r.topk_idx, r.R_best
-        r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=rank * N, gather=False)
+        r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=shard_lo, gather=False)
         launches["n"] += 3
         vals, idxs = ahv.dist.all_gather_topk(r.topk_val, r.topk_idx)
         val, idx = ahv.ops.topk_merge(vals, idxs)
-        own = (idx >= rank * N) & (idx < (rank + 1) * N)
-        Rb = ahv.ops.gather_rotations(R, torch.where(own, idx, torch.full_like(idx, rank * N)), rank * N)
+        own = (idx >= shard_lo) & (idx < shard_lo + N)
+        Rb = ahv.ops.gather_rotations(R, torch.where(own, idx, torch.full_like(idx, shard_lo)), shard_lo)
         launches["n"] += 2                       # merge + winner gather (NCCL kernels not counted)
         return val, idx, Rb
 
@@ -247,7 +260,7 @@ def run_ours(args):
 
     # other arithmetic modes on the same workload (informational; the headline stays fp32 volumes + AHV_MATH_TC)
     other = {}
-    if rank == 0:
+    if rank == 0 and not strong:
         def _rate(src, m):
             for _ in range(2):
                 ahv.ops.score(src, tgt, R, verifier.W1, verifier.W2, verifier.b2, k=0, math=m, return_scores=False, workspace=ws)
@@ -279,7 +292,7 @@ def run_ours(args):
 
     # p50 per-pair latency, B=1: CUDA-graph replay of the whole step, CUDA events
     latency = {}
-    if rank == 0:
+    if rank == 0 and not strong:
         import statistics as _st
         for n_lat in (3000, 50000):
             gv = ahv.GraphedVerifier(verifier, 1, n_lat, k=1, device=dev)
@@ -293,7 +306,7 @@ def run_ours(args):
             latency[f"N={n_lat}"] = {"p50_us": _st.median(a.elapsed_time(b_) for a, b_ in lev) * 1e3, "calls": 100}
 
     # e2e: host buffers through the C ABI (H2D + compute + D2H inside the timed region)
-    vs_p, vt_p = vs_h.pin_memory(), vt_h.pin_memory()
+    vs_p, vt_p = vs_h.float().pin_memory(), vt_h.pin_memory()
     R_p = R.cpu().pin_memory()
     for _ in range(2):
         ahv.ops.predict_host(vs_p, vt_p, R_p, W1, W2, b2, k=k, math=math, device=dev)
@@ -312,21 +325,25 @@ def run_ours(args):
     total_ms, e2e_s, kernel_ms = t.tolist()
     if rank == 0:
         peaks = load_peaks()
-        units_per_step = B * N * world
+        units_per_step = B * args.hyps if strong else B * N * world
         value = units_per_step * args.steps / (total_ms * 1e-3)
         hyp_per_s_kernel = B * N / (kernel_ms * 1e-3)              # one GPU's kernel
-        gather_gbs = hyp_per_s_kernel * GATHER_BYTES_PER_HYP / 1e9
+        gather_bytes = GATHER_BYTES_PER_HYP // 2 if strong else GATHER_BYTES_PER_HYP   # 16-bit staged volume: 256 B per voxel sample
+        gather_gbs = hyp_per_s_kernel * gather_bytes / 1e9
         nominal_smem = sms * 128 * peaks["sm_max_mhz"] * 1e6 / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16 volumes" if strong else "f32",
+            "data": "synthetic",
             "dtype_detail": "fp32 volumes, trilinear gather / normalise / correlate in fp32; the two 1x1 convs use fp16 "
                             "operands (10-bit mantissa, TF32-equivalent) with fp32 accumulation on tcgen05; scores within "
                             "1.3e-4 relative of the reference's fp32 CPU path (gate 1e-3)",
-            "config": {"workload": f"CO3D config 2 (BASELINE.json configs[1]): B={B} pairs x N={N} hypotheses per GPU, "
-                                   f"fp32 volumes, shared rotation set, top-{k}; N>1 = weak scaling over hypothesis shards "
-                                   f"+ NCCL all-gather of top-k", "pairs": B, "hypotheses_per_gpu": N, "math": args.math,
+            "config": {"workload": (f"Objaverse config 3 (BASELINE.json configs[2]): B={B} pairs, bf16 volumes, one set of "
+                                    f"{args.hyps} hypotheses sharded over {world} GPU(s), NCCL all-gather of top-{k}") if strong else
+                                   (f"CO3D config 2 (BASELINE.json configs[1]): B={B} pairs x N={N} hypotheses per GPU, "
+                                    f"fp32 volumes, shared rotation set, top-{k}; N>1 = weak scaling over hypothesis shards "
+                                    f"+ NCCL all-gather of top-k"), "pairs": B, "hypotheses_per_gpu": N, "math": args.math,
                        "l2": "flushed between timed steps (256 MiB memset, untimed)"},
             "voxel_samples_per_s": value * 512,
             "clocks": clocks,
@@ -340,7 +357,7 @@ def run_ours(args):
                 "peak": smem_peak_gbs, "unit": "GB/s", "frac": gather_gbs / smem_peak_gbs,
                 "peak_source": "measured in this run (ahv_diag_smem_read, conflict-free LDS.128)",
                 "nominal_peak": nominal_smem, "kernel_ms": kernel_ms, "traffic": ncu_traffic(), "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/); algorithmic HBM bytes per launch = %d" % (HBM_BYTES_PER_HYP * B * N),
-                "algorithmic_bytes_per_unit": GATHER_BYTES_PER_HYP,
+                "algorithmic_bytes_per_unit": gather_bytes,
                 "alt": {
                     "hbm": {"achieved": hyp_per_s_kernel * HBM_BYTES_PER_HYP / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": hyp_per_s_kernel * HBM_BYTES_PER_HYP / 1e9 / peaks["hbm_gbs"]},
@@ -368,6 +385,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS)
     ap.add_argument("--hyps", type=int, default=HYPS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", type=int, choices=[2, 3], default=2,
+                    help="2 (default): BASELINE configs[1], weak scaling; 3: configs[2], bf16 volumes, hypothesis set sharded (strong)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
