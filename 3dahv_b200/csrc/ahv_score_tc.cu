@@ -886,24 +886,23 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
           __half2 acc[2][4];
 #pragma unroll
           for (int e2 = 0; e2 < 4; ++e2) acc[0][e2] = acc[1][e2] = __float2half2_rn(0.0f);
-          uint4 buf[2][4];
+          // all 16 LDS.128 of the voxel are issued before the first HFMA2: this path is latency-bound,
+          // not bandwidth-bound, and 64 data registers are affordable here
+          uint4 buf[4][4];
           constexpr int kDz = kHalo * 9 * 64;
-          buf[0][0] = *reinterpret_cast<const uint4*>(pa + koff[0]);
-          buf[0][1] = *reinterpret_cast<const uint4*>(pa + koff[0] + kDz);
-          buf[0][2] = *reinterpret_cast<const uint4*>(pb + koff[0]);
-          buf[0][3] = *reinterpret_cast<const uint4*>(pb + koff[0] + kDz);
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            if (t < 3) {
-              buf[(t + 1) & 1][0] = *reinterpret_cast<const uint4*>(pa + koff[t + 1]);
-              buf[(t + 1) & 1][1] = *reinterpret_cast<const uint4*>(pa + koff[t + 1] + kDz);
-              buf[(t + 1) & 1][2] = *reinterpret_cast<const uint4*>(pb + koff[t + 1]);
-              buf[(t + 1) & 1][3] = *reinterpret_cast<const uint4*>(pb + koff[t + 1] + kDz);
-            }
+            buf[t][0] = *reinterpret_cast<const uint4*>(pa + koff[t]);
+            buf[t][1] = *reinterpret_cast<const uint4*>(pa + koff[t] + kDz);
+            buf[t][2] = *reinterpret_cast<const uint4*>(pb + koff[t]);
+            buf[t][3] = *reinterpret_cast<const uint4*>(pb + koff[t] + kDz);
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const __half2 wg = __hmul2(wxt[t], w4[c]);
-              const uint4 q4 = buf[t & 1][c];
+              const uint4 q4 = buf[t][c];
               const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
               for (int k2 = 0; k2 < 4; ++k2)
