@@ -800,15 +800,15 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       const uint32_t ax = tmem + ((uint32_t)(32 * sub) << 16) + M::tmem_ax + stage * 64;
       // grid = R @ (x, y, z): y and z are fixed per lane, x walks with w
       const float pgx = fmaf(Rr[2], bz, Rr[1] * by), pgy = fmaf(Rr[5], bz, Rr[4] * by), pgz = fmaf(Rr[8], bz, Rr[7] * by);
+      if constexpr (!K16) {
 #pragma unroll 1
-      for (int wi = 0; wi < 4; ++wi) {
-        const int w = whalf * 4 + wi;
-        const float bx = sbase[w];
-        float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
-        ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
-        const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
-        const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
-        if constexpr (!K16) {
+        for (int wi = 0; wi < 4; ++wi) {
+          const int w = whalf * 4 + wi;
+          const float bx = sbase[w];
+          float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
+          ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
+          const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
+          const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
           const int line = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * kHalo + ((int)x0 + 1);
           const int swap = (line ^ pf) & 1;
           const float wxa = swap ? fx : 1.0f - fx, wxb = swap ? 1.0f - fx : fx;
@@ -869,63 +869,81 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
           }
           const uint32_t regs[8] = {o4[0].x, o4[0].y, o4[1].x, o4[1].y, o4[2].x, o4[2].y, o4[3].x, o4[3].y};
           tmem_st8(ax + w * 8, regs);
-        } else {
-          const int pline = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * 9 + ((int)x0 + 1);
-          const int swapy = (pline ^ pf) & 1;
-          const unsigned char* pa = volb + (pline + swapy * 9) * 64;
-          const unsigned char* pb = volb + (pline + (1 - swapy) * 9) * 64;
-          const float wya = swapy ? fy : 1.0f - fy, wyb = swapy ? 1.0f - fy : fy;
-          const __half2 wy2[2] = {__float2half2_rn(wya), __float2half2_rn(wyb)};
-          const __half2 wz2[2] = {__float2half2_rn(1.0f - fz), __float2half2_rn(fz)};
-          const __half2 wx2[2] = {__float2half2_rn(1.0f - fx), __float2half2_rn(fx)};
-          __half2 w4[4], wxt[4];
+        }
+      } else {
+        // 16-bit staged volume (x-pair lines, packed HFMA2).  This path is bound by per-warp dependency
+        // latency, not by bandwidth, so each lane interleaves TWO voxels (w, w+1): twice the independent
+        // instruction streams per warp.
+        constexpr int kDz = kHalo * 9 * 64;
+#pragma unroll 1
+        for (int wp = 0; wp < 2; ++wp) {
+          const unsigned char *pa[2], *pb[2];
+          __half2 w4[2][4], wxt[2][4], acc[2][2][4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) w4[c] = __hmul2(wy2[c >> 1], wz2[c & 1]);
+          for (int v = 0; v < 2; ++v) {
+            const float bx = sbase[whalf * 4 + wp * 2 + v];
+            float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
+            ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
+            const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
+            const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
+            const int pline = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * 9 + ((int)x0 + 1);
+            const int swapy = (pline ^ pf) & 1;  // first y tap = the one whose line has bank parity pf (9 is odd)
+            pa[v] = volb + (pline + swapy * 9) * 64;
+            pb[v] = volb + (pline + (1 - swapy) * 9) * 64;
+            const float wya = swapy ? fy : 1.0f - fy, wyb = swapy ? 1.0f - fy : fy;
+            const __half2 wy2[2] = {__float2half2_rn(wya), __float2half2_rn(wyb)};
+            const __half2 wz2[2] = {__float2half2_rn(1.0f - fz), __float2half2_rn(fz)};
+            const __half2 wx2[2] = {__float2half2_rn(1.0f - fx), __float2half2_rn(fx)};
 #pragma unroll
-          for (int t = 0; t < 4; ++t) wxt[t] = (((rot + t) & 3) >> 1) ? wx2[1] : wx2[0];
-          __half2 acc[2][4];
+            for (int c = 0; c < 4; ++c) w4[v][c] = __hmul2(wy2[c >> 1], wz2[c & 1]);
 #pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) acc[0][e2] = acc[1][e2] = __float2half2_rn(0.0f);
-          // all 16 LDS.128 of the voxel are issued before the first HFMA2: this path is latency-bound,
-          // not bandwidth-bound, and 64 data registers are affordable here
-          uint4 buf[4][4];
-          constexpr int kDz = kHalo * 9 * 64;
+            for (int t = 0; t < 4; ++t) wxt[v][t] = (((rot + t) & 3) >> 1) ? wx2[1] : wx2[0];  // tap of chunk (rot+t)&3
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            buf[t][0] = *reinterpret_cast<const uint4*>(pa + koff[t]);
-            buf[t][1] = *reinterpret_cast<const uint4*>(pa + koff[t] + kDz);
-            buf[t][2] = *reinterpret_cast<const uint4*>(pb + koff[t]);
-            buf[t][3] = *reinterpret_cast<const uint4*>(pb + koff[t] + kDz);
+            for (int e2 = 0; e2 < 4; ++e2) acc[v][0][e2] = acc[v][1][e2] = __float2half2_rn(0.0f);
           }
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
+            uint4 buf[2][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const __half2 wg = __hmul2(wxt[t], w4[c]);
-              const uint4 q4 = buf[t][c];
-              const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-              for (int k2 = 0; k2 < 4; ++k2)
-                acc[t & 1][k2] = __hfma2(wg, *reinterpret_cast<const __half2*>(&wd[k2]), acc[t & 1][k2]);
+            for (int v = 0; v < 2; ++v) {
+              buf[v][0] = *reinterpret_cast<const uint4*>(pa[v] + koff[t]);
+              buf[v][1] = *reinterpret_cast<const uint4*>(pa[v] + koff[t] + kDz);
+              buf[v][2] = *reinterpret_cast<const uint4*>(pb[v] + koff[t]);
+              buf[v][3] = *reinterpret_cast<const uint4*>(pb[v] + koff[t] + kDz);
             }
-          }
-          uint32_t a0[4], a1[4];
 #pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2) {
-            a0[k2] = *reinterpret_cast<const uint32_t*>(&acc[0][k2]);
-            a1[k2] = *reinterpret_cast<const uint32_t*>(&acc[1][k2]);
-          }
-          *reinterpret_cast<uint4*>(st + syz[0] + w * 16) = make_uint4(a0[0], a0[1], a0[2], a0[3]);
-          *reinterpret_cast<uint4*>(st + syz[1] + w * 16) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
-          // view x: acc[0] holds channel half (rot&1); put the halves in channel order and store to TMEM
-          const bool sw = rot & 1;
-          uint32_t regs[8];
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int k2 = 0; k2 < 4; ++k2) {
-            regs[k2] = sw ? a1[k2] : a0[k2];
-            regs[4 + k2] = sw ? a0[k2] : a1[k2];
+              for (int v = 0; v < 2; ++v) {
+                const __half2 wg = __hmul2(wxt[v][t], w4[v][c]);
+                const uint4 q4 = buf[v][c];
+                const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2)
+                  acc[v][t & 1][k2] = __hfma2(wg, *reinterpret_cast<const __half2*>(&wd[k2]), acc[v][t & 1][k2]);
+              }
           }
-          tmem_st8(ax + w * 8, regs);
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int w = whalf * 4 + wp * 2 + v;
+            uint32_t a0[4], a1[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              a0[k2] = *reinterpret_cast<const uint32_t*>(&acc[v][0][k2]);
+              a1[k2] = *reinterpret_cast<const uint32_t*>(&acc[v][1][k2]);
+            }
+            *reinterpret_cast<uint4*>(st + syz[0] + w * 16) = make_uint4(a0[0], a0[1], a0[2], a0[3]);
+            *reinterpret_cast<uint4*>(st + syz[1] + w * 16) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+            // view x: acc[.][0] holds channel half (rot&1); put the halves in channel order and store to TMEM
+            const bool sw = rot & 1;
+            uint32_t regs[8];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) {
+              regs[k2] = sw ? a1[k2] : a0[k2];
+              regs[4 + k2] = sw ? a0[k2] : a1[k2];
+            }
+            tmem_st8(ax + w * 8, regs);
+          }
         }
       }
       tmem_st_wait();
