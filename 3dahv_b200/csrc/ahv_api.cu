@@ -66,6 +66,14 @@ AHV_API int ahv_rotate_volume(const float* vol, int vol_per_rotation, const floa
   return launch_rotate_volume(vol, vol_per_rotation != 0, R, base, out, n, (cudaStream_t)stream);
 }
 
+AHV_API int ahv_rotate_volume_backward(const float* grad_out, int vol_per_rotation, const float* R,
+                                       const float* base, float* grad_vol, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!grad_out || !R || !base || !grad_vol))) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_rotate_volume_bwd(grad_out, vol_per_rotation != 0, R, base, grad_vol, n, (cudaStream_t)stream);
+}
+
 AHV_API int ahv_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                      float* feat, int64_t m, void* stream) {
   if (m < 0 || (m > 0 && (!vol || !W1 || !W2 || !b2 || !feat))) return AHV_EINVAL;

@@ -88,6 +88,8 @@ int launch_so3_sample(uint64_t seed, int64_t first, float* R, int64_t n, cudaStr
 int launch_so3_grid(int64_t n_total, int64_t first, float* R, int64_t count, cudaStream_t s);
 int launch_rotate_volume(const float* vol, int per_rot, const float* R, const float* base,
                          float* out, int64_t n, cudaStream_t s);
+int launch_rotate_volume_bwd(const float* grad_out, int per_rot, const float* R, const float* base,
+                             float* grad_vol, int64_t n, cudaStream_t s);
 int launch_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                         float* feat, int64_t m, cudaStream_t s);
 int launch_score_fp32(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,

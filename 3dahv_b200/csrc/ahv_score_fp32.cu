@@ -186,6 +186,80 @@ rotate_volume_kernel(const float* __restrict__ vol, int per_rot, const float* __
   }
 }
 
+// ---- rotate_volume backward (training variant) --------------
+// grad_vol += scatter of grad_out through the same 8 trilinear taps the forward used
+// (the adjoint of utils.py:113-131 with respect to the volume).  One CTA handles
+// `rot_per_cta` rotations; with a shared volume their contributions meet in shared
+// memory (ATOMS) and are flushed once per CTA with global atomics.
+__global__ void __launch_bounds__(kThreads, 1)
+rotate_volume_bwd_kernel(const float* __restrict__ grad_out, int per_rot, const float* __restrict__ R,
+                         const float* __restrict__ base, float* __restrict__ grad_vol, int64_t n,
+                         int rot_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* acc = reinterpret_cast<float*>(smem_raw);  // [1000 lines][16 ch] halo'd like the forward volume
+  float* sbase = acc + kLines * kC;
+  float* sR = sbase + 8;
+  if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
+  const int64_t first = (int64_t)blockIdx.x * rot_per_cta;
+  for (int r = 0; r < rot_per_cta; ++r) {
+    const int64_t i = first + r;
+    if (i >= n) break;
+    if (per_rot || r == 0) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < kLines * kC; e += kThreads) acc[e] = 0.0f;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) sR[threadIdx.x] = R[i * 9 + threadIdx.x];
+    __syncthreads();
+    float Rr[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rr[e] = sR[e];
+    for (int task = threadIdx.x; task < 4 * kVox; task += kThreads) {
+      const int v = task & 511, j = task >> 9;
+      const int d = v >> 6, h = (v >> 3) & 7, w = v & 7;
+      Tap t = make_tap(Rr, sbase[w], sbase[h], sbase[d]);
+      const float* go = grad_out + ((size_t)i * kC + j * 4) * kVox + v;
+      const float g0 = go[0], g1 = go[kVox], g2 = go[2 * kVox], g3 = go[3 * kVox];
+      float* p = acc + t.line * kC + j * 4;
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx) {
+            const float wgt = (dx ? t.fx : 1.0f - t.fx) * (dy ? t.fy : 1.0f - t.fy) * (dz ? t.fz : 1.0f - t.fz);
+            float* q = p + (dz * kHalo * kHalo + dy * kHalo + dx) * kC;
+            atomicAdd(q + 0, wgt * g0); atomicAdd(q + 1, wgt * g1);
+            atomicAdd(q + 2, wgt * g2); atomicAdd(q + 3, wgt * g3);
+          }
+    }
+    const bool flush = per_rot || r == rot_per_cta - 1 || i + 1 >= n;
+    if (flush) {
+      __syncthreads();
+      float* gv = grad_vol + (per_rot ? (size_t)i * kC * kVox : 0);
+      for (int e = threadIdx.x; e < kC * kVox; e += kThreads) {
+        const int c = e >> 9, v = e & 511;
+        const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
+        const float val = acc[(((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1)) * kC + c];  // halo lines are discarded
+        if (per_rot) gv[e] = val;
+        else if (val != 0.0f) atomicAdd(gv + e, val);
+      }
+    }
+  }
+}
+
+int launch_rotate_volume_bwd(const float* grad_out, int per_rot, const float* R, const float* base,
+                             float* grad_vol, int64_t n, cudaStream_t s) {
+  if (n == 0) return AHV_OK;
+  const int rpc = per_rot ? 1 : 8;
+  const int64_t grid = (n + rpc - 1) / rpc;
+  const size_t smem = (kLines * kC + 8 + 12) * sizeof(float);
+  AHV_CUDA_OK(cudaFuncSetAttribute(rotate_volume_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rotate_volume_bwd_kernel<<<(unsigned)grid, kThreads, smem, s>>>(grad_out, per_rot, R, base, grad_vol, n, rpc);
+  AHV_CUDA_OK(cudaGetLastError());
+  return AHV_OK;
+}
+
 // ---- launchers --------------------------------------------------------------
 static int sm_count() {
   int dev = 0, sms = 0;

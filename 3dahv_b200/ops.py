@@ -93,6 +93,22 @@ def rotate_volume(volume: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def rotate_volume_backward(grad_out: torch.Tensor, R: torch.Tensor, per_rotation: bool) -> torch.Tensor:
+    """Adjoint of rotate_volume w.r.t. the volume: [n,16,8,8,8] -> [16,8,8,8] (shared volume, summed)
+    or [n,16,8,8,8] (one volume per rotation)."""
+    g, R = _dev(grad_out, "grad_out"), _dev(R, "R")
+    n = R.shape[0]
+    if tuple(g.shape) != (n, 16, 8, 8, 8):
+        raise ValueError("grad_out must be [n,16,8,8,8]")
+    out = (torch.empty(n, 16, 8, 8, 8, device=g.device, dtype=torch.float32) if per_rotation
+           else torch.zeros(16, 8, 8, 8, device=g.device, dtype=torch.float32))
+    base = base_coords(g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().ahv_rotate_volume_backward(g.data_ptr(), int(per_rotation), R.data_ptr(), base.data_ptr(),
+                                                         out.data_ptr(), n, _stream(g)), "ahv_rotate_volume_backward")
+    return out
+
+
 def forward_3d2d(vol: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
     """Feature_Aligner.forward_3d2d (modules/modules.py:112-124): [m,16,8,8,8] -> [m,32,64]."""
     v = _dev(vol, "vol")

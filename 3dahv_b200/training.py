@@ -1,0 +1,113 @@
+"""Training variant of the hypothesis-and-verification step.
+
+The reference trains with `infoNCE_loss` (modules/model.py:43-63): per-pair rotation sets
+`[B,N,3,3]`, `rotate_volume` -> `forward_3d2d` -> similarity -> softmax over hypotheses with
+temperature 0.1, all under PyTorch autograd (≈420 KB of saved activations per hypothesis).
+
+Here the forward scores come from the fused CUDA kernel (nothing saved), and the backward pass
+recomputes chunk by chunk with bounded memory: the trilinear resampling and its adjoint are the
+library's own kernels (`ahv_rotate_volume`, `ahv_rotate_volume_backward`), the small verification
+head (two 1x1 convolutions, ReLU, L2 normalise) is differentiated by PyTorch on the recomputed
+chunk.  Gradients flow to the source volumes, the target volumes (through their features), W1, W2
+and b2 — i.e. to everything upstream of the hot path (`forward_2d3d`, the backbone).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import MATH_FP32, MATH_TC
+
+
+class _RotateVolume(torch.autograd.Function):
+    """utils.rotate_volume (utils.py:113-131) with a gradient w.r.t. the volume (rotations are data)."""
+
+    @staticmethod
+    def forward(ctx, volume, R):
+        ctx.per_rot = volume.dim() == 5
+        ctx.save_for_backward(R)
+        return ops.rotate_volume(volume.detach(), R)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (R,) = ctx.saved_tensors
+        return ops.rotate_volume_backward(grad_out.contiguous(), R, ctx.per_rot), None
+
+
+def rotate_volume(volume: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
+    """Differentiable (w.r.t. `volume`) GPU rotate_volume: [16,8,8,8] or [n,16,8,8,8] with R [n,3,3]."""
+    return _RotateVolume.apply(volume, R)
+
+
+def head_torch(vol: torch.Tensor, W1, W2, b2) -> torch.Tensor:
+    """Feature_Aligner.forward_3d2d (modules/modules.py:112-124) in differentiable torch ops."""
+    m = vol.shape[0]
+    x = vol.permute(0, 1, 4, 2, 3).reshape(m, 128, 8, 8)
+    y = vol.permute(0, 1, 3, 2, 4).reshape(m, 128, 8, 8)
+    z = vol.reshape(m, 128, 8, 8)
+    t = torch.cat([x, y, z], dim=1)
+    t = F.conv2d(t, W1.reshape(32, 384, 1, 1))
+    t = F.conv2d(F.relu(t), W2.reshape(32, 32, 1, 1), b2)
+    return F.normalize(t, p=2, dim=1).flatten(2)
+
+
+class _VerifyScores(torch.autograd.Function):
+    """scores[b,n] of modules/model.py:53-56; forward fused, backward chunked recomputation."""
+
+    @staticmethod
+    def forward(ctx, vol_src, vol_tgt, R, W1, W2, b2, math, chunk):
+        tgt = ops.forward_3d2d(vol_tgt.detach().float(), W1.detach(), W2.detach(), b2.detach())
+        scores, _, _ = ops.score(vol_src.detach().float(), tgt, R, W1.detach(), W2.detach(), b2.detach(), k=0, math=math,
+                                 return_scores=True)
+        ctx.save_for_backward(vol_src, vol_tgt, R, W1, W2, b2)
+        ctx.chunk = chunk
+        return scores
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        vol_src, vol_tgt, R, W1, W2, b2 = ctx.saved_tensors
+        B = vol_src.shape[0]
+        per_pair = R.dim() == 4
+        N = R.shape[1] if per_pair else R.shape[0]
+        with torch.enable_grad():
+            vs = vol_src.detach().float().requires_grad_(True)
+            vt = vol_tgt.detach().float().requires_grad_(True)
+            w1, w2, bb = (t.detach().float().requires_grad_(True) for t in (W1, W2, b2))
+            tgt = head_torch(vt, w1, w2, bb)                                # [B,32,64]
+            total = None
+            for b in range(B):
+                Rb = R[b] if per_pair else R
+                for a in range(0, N, ctx.chunk):
+                    Rc = Rb[a:a + ctx.chunk].contiguous()
+                    f = head_torch(rotate_volume(vs[b], Rc), w1, w2, bb)   # recomputed, freed after this chunk
+                    s = (f * tgt[b][None]).sum(dim=1).mean(dim=-1)
+                    part = (s * grad_scores[b, a:a + ctx.chunk]).sum()
+                    # backward per chunk keeps the live graph at chunk size; tgt's graph is retained until the end
+                    gs = torch.autograd.grad(part, [vs, w1, w2, bb, tgt], retain_graph=True, allow_unused=True)
+                    total = gs if total is None else tuple(x + y if (x is not None and y is not None) else (x if y is None else y)
+                                                           for x, y in zip(total, gs))
+            g_vs, g_w1, g_w2, g_b, g_tgt = total
+            # through the target features to vol_tgt and (again) the head weights
+            gt = torch.autograd.grad(tgt, [vt, w1, w2, bb], grad_outputs=g_tgt, allow_unused=True)
+            g_vt = gt[0]
+            g_w1, g_w2, g_b = g_w1 + gt[1], g_w2 + gt[2], g_b + gt[3]
+        return g_vs, g_vt, None, g_w1.reshape(W1.shape), g_w2.reshape(W2.shape), g_b, None, None
+
+
+def verification_scores(vol_src, vol_tgt, R, W1, W2, b2, math: int = MATH_TC, chunk: int = 1024) -> torch.Tensor:
+    """Differentiable pred_sim [B,N] (modules/model.py:53-56 / :193).  R [N,3,3] or [B,N,3,3]."""
+    return _VerifyScores.apply(vol_src, vol_tgt, R.contiguous(), W1, W2, b2, math, chunk)
+
+
+def infonce_loss(scores: torch.Tensor, sampled_R: torch.Tensor, gt_delta_R: torch.Tensor, acc_thr_deg: float,
+                 temperature: float = 0.1) -> torch.Tensor:
+    """modules/model.py:43-63 given the scores: positives = hypotheses within `acc_thr_deg` of the
+    ground-truth rotation; loss_b = -log(sum_pos e^{s/T} / sum_all e^{s/T}).  Returns [B]."""
+    with torch.no_grad():
+        gt_sim = ((sampled_R.flatten(2) * gt_delta_R.reshape(-1, 1, 9)).sum(-1).clamp(-1, 3) - 1) / 2
+        positive = (180.0 * torch.arccos(gt_sim) / math.pi) <= acc_thr_deg
+    e = torch.exp(scores / temperature)
+    return -torch.log((e * positive).sum(-1) / e.sum(-1).clamp(min=1e-8))

@@ -85,6 +85,13 @@ AHV_API int ahv_so3_grid(int64_t n_total, int64_t first_index, float* R, int64_t
 AHV_API int ahv_rotate_volume(const float* vol, int vol_per_rotation, const float* R, const float* base,
                       float* out, int64_t n, void* stream);
 
+/* Gradient of ahv_rotate_volume with respect to the volume (training variant, the autograd path of
+ * utils.py:113-131 inside infoNCE_loss, modules/model.py:53): grad_out [n,16,8,8,8] is scattered
+ * through the same trilinear taps.  vol_per_rotation==0: contributions of all n rotations are ADDED
+ * into grad_vol [16,8,8,8] (caller zeroes it); ==1: grad_vol [n,16,8,8,8] is overwritten. */
+AHV_API int ahv_rotate_volume_backward(const float* grad_out, int vol_per_rotation, const float* R,
+                                       const float* base, float* grad_vol, int64_t n, void* stream);
+
 /* Feature_Aligner.forward_3d2d (modules/modules.py:112-124): tri-plane fold,
  * conv1x1 384->32, ReLU, conv1x1 32->32 + bias, L2 normalise over channels.
  * vol [m,16,8,8,8] -> feat [m,32,64].  W1 [32,384], W2 [32,32], b2 [32]

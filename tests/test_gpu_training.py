@@ -1,0 +1,92 @@
+"""GPU: training variant — gradients of the verification scores and the InfoNCE
+loss against PyTorch autograd through the oracle's differentiable restatement on the CPU."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_reference(oracle, vs, vt, R, W1, W2, b2, grad_scores):
+    vs, vt, W1, W2, b2 = (t.detach().clone().double().requires_grad_(True) for t in (vs, vt, W1, W2, b2))
+    B = vs.shape[0]
+    per_pair = R.dim() == 4
+    tgt = oracle.forward_3d2d_torch(vt, W1, W2, b2)
+    rows = []
+    for b in range(B):
+        Rb = (R[b] if per_pair else R).double()
+        rot = oracle.rotate_volume_torch(vs[b][None].expand(Rb.shape[0], -1, -1, -1, -1), Rb)
+        f = oracle.forward_3d2d_torch(rot, W1, W2, b2)
+        rows.append((f * tgt[b][None]).sum(dim=1).mean(dim=-1))
+    s = torch.stack(rows)
+    (s * grad_scores.double()).sum().backward()
+    return s.detach(), [t.grad for t in (vs, vt, W1, W2, b2)]
+
+
+@pytest.mark.parametrize("per_pair", [False, True])
+def test_score_gradients_match_autograd_of_the_oracle(ahv, golden, oracle, per_pair):
+    dev = torch.device("cuda", 0)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    T = torch.from_numpy
+    B, N = 2, 40
+    vs, vt = T(g["vol_src"][:B]), T(g["vol_tgt"][:B])
+    R = T(g["R"][: B * N]).reshape(B, N, 3, 3) if per_pair else T(g["R"][:N])
+    W1, W2, b2 = T(w["W1"]), T(w["W2"]), T(w["b2"])
+    gs = torch.randn(B, N, generator=torch.Generator().manual_seed(3))
+    ref_s, ref_g = _cpu_reference(oracle, vs, vt, R, W1, W2, b2, gs)
+
+    leaves = [t.to(dev).requires_grad_(True) for t in (vs, vt, W1, W2, b2)]
+    s = ahv.training.verification_scores(leaves[0], leaves[1], R.to(dev), leaves[2], leaves[3], leaves[4],
+                                         math=ahv.MATH_FP32, chunk=16)
+    assert torch.allclose(s.detach().cpu().double(), ref_s, rtol=2e-5, atol=0)
+    (s * gs.to(dev)).sum().backward()
+    for name, leaf, ref in zip(("vol_src", "vol_tgt", "W1", "W2", "b2"), leaves, ref_g):
+        got = leaf.grad.detach().cpu().double()
+        scale = ref.abs().max().item()
+        assert torch.allclose(got, ref, rtol=0, atol=2e-4 * scale), (name, (got - ref).abs().max().item(), scale)
+
+
+def test_rotate_volume_backward_is_the_adjoint(ahv, golden):
+    """<rotate(v), g> == <v, rotate_backward(g)> for random v, g (shared and per-rotation volumes)."""
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator().manual_seed(0)
+    R = ahv.so3.sample_rotations(50, seed=4, device=dev)
+    v = torch.randn(16, 8, 8, 8, generator=gen).to(dev)
+    gout = torch.randn(50, 16, 8, 8, 8, generator=gen).to(dev)
+    lhs = (ahv.ops.rotate_volume(v, R) * gout).sum().item()
+    rhs = (v * ahv.ops.rotate_volume_backward(gout, R, per_rotation=False)).sum().item()
+    assert abs(lhs - rhs) <= 2e-4 * abs(lhs)
+    vn = torch.randn(50, 16, 8, 8, 8, generator=gen).to(dev)
+    lhs = (ahv.ops.rotate_volume(vn, R) * gout).sum().item()
+    rhs = (vn * ahv.ops.rotate_volume_backward(gout, R, per_rotation=True)).sum().item()
+    assert abs(lhs - rhs) <= 2e-4 * abs(lhs)
+
+
+def test_infonce_loss_and_training_step_direction(ahv, golden):
+    """modules/model.py:43-63: the loss value matches the formula, and one SGD step on the head
+    weights along the computed gradient lowers it."""
+    dev = torch.device("cuda", 0)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    T = lambda a: torch.from_numpy(a).to(dev)
+    B, N = 3, 256
+    vs, vt = T(g["vol_src"]), T(g["vol_tgt"])
+    gt = ahv.so3.sample_rotations(B, seed=9, device=dev)
+    Rs = torch.cat([gt[:, None], ahv.so3.sample_rotations(B * (N - 1), seed=10, device=dev).reshape(B, N - 1, 3, 3)], 1).contiguous()
+    W1, W2, b2 = (T(w[k]).clone().requires_grad_(True) for k in ("W1", "W2", "b2"))
+
+    def loss_fn():
+        s = ahv.training.verification_scores(vs, vt, Rs, W1, W2, b2, chunk=128)
+        return ahv.training.infonce_loss(s, Rs, gt, acc_thr_deg=15.0), s
+
+    loss, s = loss_fn()
+    e = torch.exp(s.detach() / 0.1)
+    sim = ((Rs.flatten(2) * gt.reshape(-1, 1, 9)).sum(-1).clamp(-1, 3) - 1) / 2
+    pos = torch.rad2deg(torch.arccos(sim)) <= 15.0
+    assert pos[:, 0].all()                                   # the ground truth (index 0) is always a positive
+    assert torch.allclose(loss.detach(), -torch.log((e * pos).sum(-1) / e.sum(-1)), rtol=1e-5)
+    loss.mean().backward()
+    with torch.no_grad():
+        for p in (W1, W2, b2):
+            p -= 0.05 * p.grad / p.grad.norm().clamp_min(1e-12)
+    new_loss, _ = loss_fn()
+    assert new_loss.mean().item() < loss.mean().item()
