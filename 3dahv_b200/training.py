@@ -48,10 +48,12 @@ def head_torch(vol: torch.Tensor, W1, W2, b2) -> torch.Tensor:
     x = vol.permute(0, 1, 4, 2, 3).reshape(m, 128, 8, 8)
     y = vol.permute(0, 1, 3, 2, 4).reshape(m, 128, 8, 8)
     z = vol.reshape(m, 128, 8, 8)
-    t = torch.cat([x, y, z], dim=1)
-    t = F.conv2d(t, W1.reshape(32, 384, 1, 1))
-    t = F.conv2d(F.relu(t), W2.reshape(32, 32, 1, 1), b2)
-    return F.normalize(t, p=2, dim=1).flatten(2)
+    t = torch.cat([x, y, z], dim=1).flatten(2)                       # [m,384,64]
+    # the 1x1 convolutions as matmuls: fp32 at torch's default "highest" matmul precision (cuDNN's
+    # default for convolutions would be TF32)
+    t = torch.matmul(W1.reshape(32, 384), t)
+    t = torch.matmul(W2.reshape(32, 32), F.relu(t)) + b2[None, :, None]
+    return F.normalize(t, p=2, dim=1)
 
 
 class _VerifyScores(torch.autograd.Function):
