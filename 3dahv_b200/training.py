@@ -79,16 +79,17 @@ class _VerifyScores(torch.autograd.Function):
             vt = vol_tgt.detach().float().requires_grad_(True)
             w1, w2, bb = (t.detach().float().requires_grad_(True) for t in (W1, W2, b2))
             tgt = head_torch(vt, w1, w2, bb)                                # [B,32,64]
+            tgt_leaf = tgt.detach().requires_grad_(True)                    # cut here: tgt's own graph is walked once, below
             total = None
             for b in range(B):
                 Rb = R[b] if per_pair else R
                 for a in range(0, N, ctx.chunk):
                     Rc = Rb[a:a + ctx.chunk].contiguous()
                     f = head_torch(rotate_volume(vs[b], Rc), w1, w2, bb)   # recomputed, freed after this chunk
-                    s = (f * tgt[b][None]).sum(dim=1).mean(dim=-1)
+                    s = (f * tgt_leaf[b][None]).sum(dim=1).mean(dim=-1)
                     part = (s * grad_scores[b, a:a + ctx.chunk]).sum()
-                    # backward per chunk keeps the live graph at chunk size; tgt's graph is retained until the end
-                    gs = torch.autograd.grad(part, [vs, w1, w2, bb, tgt], retain_graph=True, allow_unused=True)
+                    # backward per chunk keeps the live graph at chunk size
+                    gs = torch.autograd.grad(part, [vs, w1, w2, bb, tgt_leaf], allow_unused=True)
                     total = gs if total is None else tuple(x + y if (x is not None and y is not None) else (x if y is None else y)
                                                            for x, y in zip(total, gs))
             g_vs, g_w1, g_w2, g_b, g_tgt = total
