@@ -76,15 +76,25 @@ class EstimatorBase(_Base):
         return self.verifier().score(img_feat_src, img_feat_tgt, R, k=1, return_scores=True).scores
 
     def infoNCE_loss(self, img_feat_1, img_feat_2, sampled_R, gt_delta_R):
-        """Forward value of modules/model.py:43-63 (inference only — training and its
-        backward pass are out of scope of this build)."""
-        with torch.no_grad():
-            acc = self.cfg["DATA"]["ACC_THR"]
-            gt_sim = ((sampled_R.flatten(2) * gt_delta_R.reshape(-1, 1, 9)).sum(-1).clamp(-1, 3) - 1) / 2
-            positive = (180 * torch.arccos(gt_sim) / math.pi) <= acc
-            sim = self.score_rotations(img_feat_1, img_feat_2, sampled_R.contiguous())
-            e = torch.exp(sim / 0.1)
-            return -torch.log((e * positive).sum(-1) / e.sum(-1).clamp(min=1e-8))
+        """modules/model.py:43-63 — per-pair hypothesis sets [B,N,3,3] with the ground truth at index 0.
+        Differentiable: the scores come from the fused kernel, their backward pass recomputes chunk by
+        chunk (3dahv_b200.training); gradients reach the volumes (hence the lifting and the backbone)
+        and the verification head.  Returns the per-sample loss [B]."""
+        head = self.feature_aligner.feature_embedding_2d
+        tr = _ahv().training
+        scores = tr.verification_scores(img_feat_1, img_feat_2, sampled_R.contiguous(), head[0].weight, head[2].weight,
+                                        head[2].bias)
+        return tr.infonce_loss(scores, sampled_R, gt_delta_R, self.cfg["DATA"]["ACC_THR"])
 
-    def training_step(self, batch, batch_idx):
-        raise NotImplementedError("training is out of scope of the B200 hot-path build (SURVEY.md §8f-3)")
+    def _sample_training_rotations(self, gt_R):
+        """modules/model.py:101-103: B*(N-1) random rotations per batch, ground truth prepended at index 0."""
+        B = gt_R.shape[0]
+        with torch.no_grad():
+            Rs = _ahv().so3.random_rotations(B * (self.num_rota - 1), device=gt_R.device).reshape(B, self.num_rota - 1, 3, 3)
+            return torch.cat([gt_R[:, None], Rs], dim=1)
+
+    def _optimizers(self, backbone_lr_scale: float, step_size: int):
+        lr = float(self.cfg["TRAIN"]["LR"])
+        opt = torch.optim.AdamW([{"params": self.feature_aligner.parameters(), "lr": lr},
+                                 {"params": self.feature_extractor.parameters(), "lr": backbone_lr_scale * lr}], eps=1e-5)
+        return [opt], [torch.optim.lr_scheduler.StepLR(opt, step_size=step_size, gamma=0.1)]

@@ -30,6 +30,29 @@ class Estimator(EstimatorBase):
         feat_tgt = self.feature_extraction(img_tgt)
         return self.feature_aligner.forward_2d3d(feat_src, feat_tgt, random_mask=False, mask_ratio=0.0)
 
+    def training_step(self, batch, batch_idx):
+        """modules/model.py:78-116 (InfoNCE over per-pair hypothesis sets, invalid pairs masked out)."""
+        mask_src, mask_tgt = batch["src_mask"], batch["ref_mask"]
+        img_src, img_tgt = batch["src_img"], batch["ref_img"]
+        if self.cfg["DATA"]["BG"] is False:
+            img_src, img_tgt = img_src * mask_src, img_tgt * mask_tgt
+        gt_R = self._gt_rotations(batch["src_R"], batch["ref_R"])
+        vol_src, vol_tgt = self.feature_aligner.forward_2d3d(
+            self.feature_extraction(img_src), self.feature_extraction(img_tgt),
+            random_mask=self.cfg["TRAIN"]["MASK"], mask_ratio=self.cfg["TRAIN"]["MASK_RATIO"])
+        self.Rs = self._sample_training_rotations(gt_R)
+        thr = self.cfg["DATA"]["SIZE_THR"]
+        valid = ((mask_src.flatten(1).sum(dim=-1) > thr) * (mask_tgt.flatten(1).sum(dim=-1) > thr)).float()
+        if "dis_init" in batch.keys():
+            valid = valid * (batch["dis_init"] < self.cfg["DATA"]["VIEW_THR"]).float()
+        loss = self.infoNCE_loss(vol_src, vol_tgt, self.Rs, gt_R) * valid
+        loss = loss.sum() / valid.sum().clamp(min=1e-8)
+        self.log("train_loss", loss.item(), on_step=True, on_epoch=True, prog_bar=True, logger=True, sync_dist=True)
+        return loss
+
+    def configure_optimizers(self):
+        return self._optimizers(backbone_lr_scale=0.1, step_size=20)      # modules/model.py:212-219
+
     @torch.no_grad()
     def predict(self, img_src, mask_src, img_tgt, mask_tgt, sampled_R=None, k: int = 1):
         """Batched inference entry (new): images -> best rotation(s) per pair, no host syncs."""

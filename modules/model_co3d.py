@@ -24,6 +24,21 @@ class Estimator(EstimatorBase):
         feat_tgt = self.feature_extraction(img_tgt)
         return self.feature_aligner.forward_2d3d(feat_src, feat_tgt, random_mask=False, mask_ratio=0)
 
+    def training_step(self, batch, batch_idx):
+        """modules/model_co3d.py:71-96."""
+        img_src, img_tgt = batch["image"][:, 0], batch["image"][:, 1]
+        gt_R = batch["relative_rotation"].squeeze(1)
+        vol_src, vol_tgt = self.feature_aligner.forward_2d3d(
+            self.feature_extraction(img_src), self.feature_extraction(img_tgt),
+            random_mask=self.cfg["TRAIN"]["MASK"], mask_ratio=self.cfg["TRAIN"]["MASK_RATIO"])
+        sampled_R = self._sample_training_rotations(gt_R)
+        loss = self.infoNCE_loss(vol_src, vol_tgt, sampled_R, gt_R).mean()
+        self.log("train_loss", loss.item(), on_step=True, on_epoch=True, prog_bar=True, logger=True, sync_dist=True)
+        return loss
+
+    def configure_optimizers(self):
+        return self._optimizers(backbone_lr_scale=1.0, step_size=200)     # modules/model_co3d.py:98-104
+
     @torch.no_grad()
     def predict(self, img_src, img_tgt, sampled_R=None, k: int = 1):
         vol_src, vol_tgt = self.forward(img_src, img_tgt)

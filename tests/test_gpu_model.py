@@ -111,3 +111,35 @@ def test_refine_improves_or_keeps_score(ahv, golden):
     assert torch.all(val >= first.topk_val[:, 0] - 1e-6)
     assert cand.shape == (3, 8 * 32, 3, 3)
     assert torch.allclose(Rb @ Rb.transpose(1, 2), torch.eye(3, device=dev).expand(3, 3, 3), atol=1e-5)
+
+
+def test_training_step_backpropagates_to_backbone_and_head(ahv):
+    """modules/model.py:78-116 / model_co3d.py:71-96: one optimisation step lowers the InfoNCE loss."""
+    from modules.model import Estimator
+    from modules.model_co3d import Estimator as EstimatorCo3d
+
+    dev = torch.device("cuda", 0)
+    cfg = _cfg(64)
+    cfg["TRAIN"] = {"MASK": True, "MASK_RATIO": 0.25, "LR": 1e-3}
+    torch.manual_seed(0)
+    m = Estimator(cfg, feature_extractor=_TinyBackbone()).to(dev).train()
+    batch = _batch(dev)
+    opt = m.configure_optimizers()[0][0]
+    torch.manual_seed(1)
+    loss0 = m.training_step(batch, 0)
+    assert loss0.requires_grad and torch.isfinite(loss0)
+    opt.zero_grad()
+    loss0.backward()
+    head = m.feature_aligner.feature_embedding_2d
+    for p in (head[0].weight, head[2].weight, head[2].bias, m.feature_extractor.proj.weight,
+              m.feature_aligner.feature_embedding_3d.conv1.weight):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
+    assert m.Rs.shape == (3, 64, 3, 3)
+    # CO3D flavour
+    c = EstimatorCo3d(cfg, feature_extractor=_TinyBackbone()).to(dev).train()
+    gt = torch.linalg.qr(torch.randn(3, 3, 3))[0].to(dev)
+    b2 = {"image": torch.stack([batch["src_img"], batch["ref_img"]], 1), "relative_rotation": gt[:, None]}
+    loss = c.training_step(b2, 0)
+    loss.backward()
+    assert torch.isfinite(loss) and c.feature_aligner.feature_embedding_2d[0].weight.grad.abs().sum() > 0
+    assert len(c.configure_optimizers()[0][0].param_groups) == 2

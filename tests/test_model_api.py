@@ -87,7 +87,8 @@ def test_estimator_api_surface():
     m = Estimator(_cfg(), feature_extractor=_TinyBackbone()).eval()
     for attr in ("cfg", "num_rota", "feature_extractor", "feature_aligner", "step_outputs", "gt_dis", "pred_Rs"):
         assert hasattr(m, attr)
-    for fn in ("feature_extraction", "forward", "validation_step", "test_step", "infoNCE_loss", "predict"):
+    for fn in ("feature_extraction", "forward", "validation_step", "test_step", "training_step", "configure_optimizers",
+               "infoNCE_loss", "predict"):
         assert callable(getattr(m, fn))
     img = torch.rand(2, 3, 64, 64)
     mask = torch.ones(2, 1, 64, 64)
