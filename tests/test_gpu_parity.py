@@ -493,3 +493,34 @@ def test_predict_host_topk_and_per_pair(ahv, golden):
     assert torch.equal(val, tv)
     assert torch.equal(Rb, torch.gather(Rp, 1, idx[..., None, None].expand(-1, -1, 3, 3)))
     assert _relerr(scores[0].numpy(), g["scores"][0, :100]) <= 1e-3
+
+
+def test_bitwise_determinism_and_soak(ahv, golden):
+    """The pipeline has no data-dependent scheduling in its arithmetic: repeated runs are bit-identical.
+    Then a soak over random (pairs, hypotheses, volume dtype, rotation layout) shapes vs the fp32 path."""
+    dev = _dev()
+    gen = torch.Generator().manual_seed(77)
+    B, N = 32, 20000
+    vs = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+    vt = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+    R = ahv.so3.sample_rotations(N, seed=5, device=dev)
+    v = ahv.HypothesisVerifier(*_weights(golden, dev))
+    first = v.score(vs, vt, R, k=1, return_scores=True)
+    for _ in range(5):
+        again = v.score(vs, vt, R, k=1, return_scores=True)
+        assert torch.equal(again.scores, first.scores) and torch.equal(again.topk_idx, first.topk_idx)
+    b16 = v.score(vs.bfloat16(), vt, R, k=1, return_scores=True)
+    assert torch.equal(v.score(vs.bfloat16(), vt, R, k=1, return_scores=True).scores, b16.scores)
+    rng = np.random.default_rng(2024)
+    ref_v = ahv.HypothesisVerifier(*_weights(golden, dev), math=ahv.MATH_FP32)
+    for it in range(24):
+        b, n = int(rng.integers(1, 40)), int(rng.integers(1, 700))
+        per_pair = bool(rng.integers(0, 2))
+        src = vs[:b].bfloat16() if rng.integers(0, 2) else vs[:b]
+        Rr = ahv.so3.sample_rotations(b * n if per_pair else n, seed=it, device=dev)
+        Rr = Rr.reshape(b, n, 3, 3).contiguous() if per_pair else Rr
+        got = v.score(src, vt[:b], Rr, k=1, return_scores=True)
+        ref = ref_v.score(src, vt[:b], Rr, k=1, return_scores=True)
+        rel = ((got.scores - ref.scores).abs() / ref.scores.abs().clamp_min(1e-6)).max().item()
+        assert rel <= 2e-3, (it, b, n, per_pair, src.dtype, rel)
+        assert torch.equal(got.topk_idx[:, 0], got.scores.argmax(1))
