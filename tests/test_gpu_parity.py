@@ -514,7 +514,7 @@ def test_bitwise_determinism_and_soak(ahv, golden):
     rng = np.random.default_rng(2024)
     ref_v = ahv.HypothesisVerifier(*_weights(golden, dev), math=ahv.MATH_FP32)
     for it in range(24):
-        b, n = int(rng.integers(1, 40)), int(rng.integers(1, 700))
+        b, n = int(rng.integers(1, 33)), int(rng.integers(1, 700))
         per_pair = bool(rng.integers(0, 2))
         src = vs[:b].bfloat16() if rng.integers(0, 2) else vs[:b]
         Rr = ahv.so3.sample_rotations(b * n if per_pair else n, seed=it, device=dev)
