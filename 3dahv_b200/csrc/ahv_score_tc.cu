@@ -136,6 +136,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -200,6 +208,119 @@ template <>
 __device__ __forceinline__ float ld_vol<float>(const float* p) { return __ldg(p); }
 template <>
 __device__ __forceinline__ float ld_vol<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// ---- epilogue role, shared by the SS and TS kernels ---------------------------------------------------
+// 4 warps, warp s = TMEM sub-partition s.  Per hypothesis pair (tile):
+//   phase A: tcgen05.ld D1 -> ReLU (modules/modules.py:68) -> fp16 -> conv2's A operand, either as the
+//            K-major core-matrix tile in shared memory (SS kernel) or straight into TMEM (TS kernel);
+//   phase B (one tile later, after conv2): tcgen05.ld D2 -> undo the pair scale, + bias -> L2 norm with
+//            F.normalize's eps (:122) -> dot with the target features (registers) -> mean over the 64
+//            positions (modules/model.py:193) -> score, and the running arg-max key (:195).
+template <bool kA2InTmem>
+__device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane, uint32_t tmem, uint32_t bar0,
+                                              unsigned char* a2_smem, uint32_t tmem_a2, float* partial,
+                                              const float* __restrict__ tgt_feat, const float* __restrict__ b2,
+                                              const float2* __restrict__ pair_scale, float* __restrict__ scores,
+                                              u64* __restrict__ best_keys, int64_t N) {
+  const int slot = lane >> 4;            // which hypothesis of the tile
+  const int pos = 16 * s + (lane & 15);  // position p*8+q of the folded plane
+  const uint32_t row = 32 * s + lane;    // TMEM lane == row of the conv2 A operand
+  float b2r[kO], tg[kO];
+#pragma unroll
+  for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
+  TileIter it(work);
+  int cur_b = -1;
+  float inv_s = 1.0f;
+  uint32_t g = 0;
+  int prev_b = 0, prev_cnt = 0;
+  int64_t prev_n0 = 0;
+  float prev_inv = 1.0f;
+  // arg-max fused into the epilogue (torch.max, modules/model.py:195): the two score-writing lanes keep a
+  // running best key for the pair they are in and publish it with one atomicMax per (CTA, pair) - keys
+  // order by score, ties by lowest index
+  int key_b = -1;
+  u64 key_best = 0;
+  auto phase_b = [&](uint32_t gg, int pb, int64_t pn0, int pcnt, float pinv) {
+    const uint32_t gb = gg & 1, u = gg >> 1;
+    mbar_wait(bar0 + (kD2Full + gb) * 8, u & 1);
+    tc_fence_after();
+    uint32_t r[32];
+    tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + 64 + gb * 32, r);
+    tmem_ld_wait();
+    float ss = 0.0f, dt = 0.0f;
+#pragma unroll
+    for (int o = 0; o < kO; ++o) {
+      const float v = fmaf(__uint_as_float(r[o]), pinv, b2r[o]);  // undo the pair scale, add bias
+      ss = fmaf(v, v, ss);
+      dt = fmaf(v, tg[o], dt);
+    }
+    float cosv = dt / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (modules/modules.py:122)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) cosv += __shfl_xor_sync(0xffffffffu, cosv, o);  // 16 positions of this slot
+    if ((lane & 15) == 0) partial[(gb * 2 + slot) * 4 + s] = cosv;
+    tc_fence_before();
+    named_bar_sync(2, 128);
+    if (s == 0 && lane < pcnt) {
+      const float* pp = partial + (gb * 2 + lane) * 4;
+      const float tot = ((pp[0] + pp[1]) + pp[2]) + pp[3];  // fixed order: deterministic
+      const float sc = tot * (1.0f / 64.0f);                // .mean(dim=-1)
+      if (scores) scores[(size_t)pb * N + pn0 + lane] = sc;
+      if (best_keys) {
+        const u64 key = make_key(sc, (uint32_t)(pn0 + lane));
+        if (pb != key_b) {
+          if (key_b >= 0) atomicMax(best_keys + key_b, key_best);
+          key_b = pb;
+          key_best = key;
+        } else if (key > key_best) {
+          key_best = key;
+        }
+      }
+    }
+  };
+  while (it.advance()) {
+    const uint32_t gb = g & 1, u = g >> 1;
+    // ---- phase A ----
+    mbar_wait(bar0 + (kD1Full + gb) * 8, u & 1);
+    tc_fence_after();
+    uint32_t r[32];
+    tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + gb * 32, r);
+    tmem_ld_wait();
+    uint32_t wq[16];  // ReLU -> fp16: the 32 channels of this thread's row
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * e]), 0.0f), fmaxf(__uint_as_float(r[2 * e + 1]), 0.0f));
+      wq[e] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    if constexpr (kA2InTmem) {
+      tmem_st16(tmem + ((uint32_t)(32 * s) << 16) + tmem_a2 + gb * 16, wq);  // 16 TMEM columns of conv2's A operand
+      tmem_st_wait();
+    } else {
+      unsigned char* a2 = a2_smem + gb * kA2Bytes + row * 16;  // [kc][rowgroup][8][8] fp16 core matrices
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc)
+        *reinterpret_cast<uint4*>(a2 + kc * 2048) = make_uint4(wq[4 * kc], wq[4 * kc + 1], wq[4 * kc + 2], wq[4 * kc + 3]);
+      fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(bar0 + (kA2Full + gb) * 8);
+      mbar_arrive(bar0 + (kD1Empty + gb) * 8);
+    }
+    // ---- phase B of the previous tile ----
+    if (g > 0) phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+    if (it.b != cur_b) {  // target features / scale of the tile just handed to conv2
+      cur_b = it.b;
+      inv_s = pair_scale[cur_b].y;
+#pragma unroll
+      for (int o = 0; o < kO; ++o) tg[o] = __ldg(tgt_feat + ((size_t)cur_b * kO + o) * kP + pos);
+    }
+    prev_b = it.b; prev_n0 = it.n0; prev_cnt = it.cnt; prev_inv = inv_s;
+    ++g;
+  }
+  phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+  if (best_keys && key_b >= 0) atomicMax(best_keys + key_b, key_best);
+}
 
 // ------------------------------------------------------------------------------
 template <typename T, bool K16>
@@ -509,102 +630,8 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     __syncwarp();
   } else {
     // =========================== EPILOGUE ===========================
-    const int s = warp - kEpiWarp0;       // TMEM sub-partition = warp % 4
-    const int slot = lane >> 4;           // which hypothesis of the tile
-    const int pos = 16 * s + (lane & 15); // position p*8+q of the folded plane
-    const uint32_t row = 32 * s + lane;   // TMEM lane == row of the conv2 A operand
-    float b2r[kO], tg[kO];
-#pragma unroll
-    for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
-    TileIter it(work);
-    int cur_b = -1;
-    float inv_s = 1.0f;
-    uint32_t g = 0;
-    int prev_b = 0, prev_cnt = 0;
-    int64_t prev_n0 = 0;
-    float prev_inv = 1.0f;
-    // arg-max fused into the epilogue (torch.max, modules/model.py:195): the two score-writing
-    // lanes keep a running best key for the pair they are in and publish it with one
-    // atomicMax per (CTA, pair) - keys order by score, ties by lowest index
-    int key_b = -1;
-    u64 key_best = 0;
-    auto phase_b = [&](uint32_t gg, int pb, int64_t pn0, int pcnt, float pinv) {
-      const uint32_t gb = gg & 1, u = gg >> 1;
-      mbar_wait(bar0 + (kD2Full + gb) * 8, u & 1);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + 64 + gb * 32, r);
-      tmem_ld_wait();
-      float ss = 0.0f, dt = 0.0f;
-#pragma unroll
-      for (int o = 0; o < kO; ++o) {
-        const float v = fmaf(__uint_as_float(r[o]), pinv, b2r[o]);  // undo the pair scale, add bias
-        ss = fmaf(v, v, ss);
-        dt = fmaf(v, tg[o], dt);
-      }
-      float cosv = dt / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (modules/modules.py:122)
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) cosv += __shfl_xor_sync(0xffffffffu, cosv, o);  // 16 positions of this slot
-      if ((lane & 15) == 0) partial[(gb * 2 + slot) * 4 + s] = cosv;
-      tc_fence_before();
-      named_bar_sync(2, 128);
-      if (s == 0 && lane < pcnt) {
-        const float* pp = partial + (gb * 2 + lane) * 4;
-        const float tot = ((pp[0] + pp[1]) + pp[2]) + pp[3];
-        const float sc = tot * (1.0f / 64.0f);  // .mean(dim=-1)
-        if (scores) scores[(size_t)pb * N + pn0 + lane] = sc;
-        if (best_keys) {
-          const u64 key = make_key(sc, (uint32_t)(pn0 + lane));
-          if (pb != key_b) {
-            if (key_b >= 0) atomicMax(best_keys + key_b, key_best);
-            key_b = pb;
-            key_best = key;
-          } else if (key > key_best) {
-            key_best = key;
-          }
-        }
-      }
-    };
-    while (it.advance()) {
-      const uint32_t gb = g & 1, u = g >> 1;
-      // ---- phase A: D1 -> ReLU -> fp16 -> A2 ----
-      mbar_wait(bar0 + (kD1Full + gb) * 8, u & 1);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + gb * 32, r);
-      tmem_ld_wait();
-      unsigned char* a2 = smem + kOffA2 + gb * kA2Bytes + row * 16;
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc) {
-        uint32_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[kc * 8 + 2 * e]), 0.0f),
-                                               fmaxf(__uint_as_float(r[kc * 8 + 2 * e + 1]), 0.0f));
-          w[e] = *reinterpret_cast<const uint32_t*>(&hh);
-        }
-        *reinterpret_cast<uint4*>(a2 + kc * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar0 + (kA2Full + gb) * 8);
-        mbar_arrive(bar0 + (kD1Empty + gb) * 8);
-      }
-      // ---- phase B of the previous tile ----
-      if (g > 0) phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
-      if (it.b != cur_b) {  // target features / scale of the tile just handed to conv2
-        cur_b = it.b;
-        inv_s = pair_scale[cur_b].y;
-#pragma unroll
-        for (int o = 0; o < kO; ++o) tg[o] = __ldg(tgt_feat + ((size_t)cur_b * kO + o) * kP + pos);
-      }
-      prev_b = it.b; prev_n0 = it.n0; prev_cnt = it.cnt; prev_inv = inv_s;
-      ++g;
-    }
-    phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
-    if (best_keys && key_b >= 0) atomicMax(best_keys + key_b, key_best);
+    epilogue_role<false>(work, warp - kEpiWarp0, lane, tmem, bar0, smem + kOffA2, 0, partial, tgt_feat, b2, pair_scale,
+                         scores, best_keys, N);
   }
 
   // ---- teardown ----
@@ -653,14 +680,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <typename T, bool K16>
 __global__ void __launch_bounds__(kThreadsTC, 1)
@@ -1000,92 +1019,9 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     }
     __syncwarp();
   } else {
-    // =========================== EPILOGUE (identical to the SS kernel) ===========================
-    const int s = warp - kEpiWarp0;
-    const int slot = lane >> 4;
-    const int pos = 16 * s + (lane & 15);
-    float b2r[kO], tg[kO];
-#pragma unroll
-    for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
-    TileIter it(work);
-    int cur_b = -1;
-    float inv_s = 1.0f;
-    uint32_t g = 0;
-    int prev_b = 0, prev_cnt = 0;
-    int64_t prev_n0 = 0;
-    float prev_inv = 1.0f;
-    int key_b = -1;
-    u64 key_best = 0;
-    auto phase_b = [&](uint32_t gg, int pb, int64_t pn0, int pcnt, float pinv) {
-      const uint32_t gb = gg & 1, u = gg >> 1;
-      mbar_wait(bar0 + (kD2Full + gb) * 8, u & 1);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + 64 + gb * 32, r);
-      tmem_ld_wait();
-      float ss = 0.0f, dt = 0.0f;
-#pragma unroll
-      for (int o = 0; o < kO; ++o) {
-        const float v = fmaf(__uint_as_float(r[o]), pinv, b2r[o]);
-        ss = fmaf(v, v, ss);
-        dt = fmaf(v, tg[o], dt);
-      }
-      float cosv = dt / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) cosv += __shfl_xor_sync(0xffffffffu, cosv, o);
-      if ((lane & 15) == 0) partial[(gb * 2 + slot) * 4 + s] = cosv;
-      tc_fence_before();
-      named_bar_sync(2, 128);
-      if (s == 0 && lane < pcnt) {
-        const float* pp = partial + (gb * 2 + lane) * 4;
-        const float tot = ((pp[0] + pp[1]) + pp[2]) + pp[3];
-        const float sc = tot * (1.0f / 64.0f);
-        if (scores) scores[(size_t)pb * N + pn0 + lane] = sc;
-        if (best_keys) {
-          const u64 key = make_key(sc, (uint32_t)(pn0 + lane));
-          if (pb != key_b) {
-            if (key_b >= 0) atomicMax(best_keys + key_b, key_best);
-            key_b = pb;
-            key_best = key;
-          } else if (key > key_best) {
-            key_best = key;
-          }
-        }
-      }
-    };
-    while (it.advance()) {
-      const uint32_t gb = g & 1, u = g >> 1;
-      mbar_wait(bar0 + (kD1Full + gb) * 8, u & 1);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(32 * s) << 16) + gb * 32, r);
-      tmem_ld_wait();
-      uint32_t wq[16];  // ReLU -> fp16, 32 channels of this thread's row = 16 TMEM columns of conv2's A operand
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * e]), 0.0f), fmaxf(__uint_as_float(r[2 * e + 1]), 0.0f));
-        wq[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      }
-      tmem_st16(tmem + ((uint32_t)(32 * s) << 16) + M::tmem_a2 + gb * 16, wq);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar0 + (kA2Full + gb) * 8);
-        mbar_arrive(bar0 + (kD1Empty + gb) * 8);
-      }
-      if (g > 0) phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
-      if (it.b != cur_b) {
-        cur_b = it.b;
-        inv_s = pair_scale[cur_b].y;
-#pragma unroll
-        for (int o = 0; o < kO; ++o) tg[o] = __ldg(tgt_feat + ((size_t)cur_b * kO + o) * kP + pos);
-      }
-      prev_b = it.b; prev_n0 = it.n0; prev_cnt = it.cnt; prev_inv = inv_s;
-      ++g;
-    }
-    phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
-    if (best_keys && key_b >= 0) atomicMax(best_keys + key_b, key_best);
+    // =========================== EPILOGUE ===========================
+    epilogue_role<true>(work, warp - kEpiWarp0, lane, tmem, bar0, nullptr, M::tmem_a2, partial, tgt_feat, b2, pair_scale,
+                        scores, best_keys, N);
   }
 
   tc_fence_before();
