@@ -115,14 +115,25 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// The MMA warp runs converged (all 32 lanes execute the issue loop with warp-uniform values) and one
+// elected lane issues each tcgen05.mma / commit.  Issuing under `if (lane == 0)` instead makes ptxas
+// wrap every MMA in an ELECT / R2UR.BROADCAST waterfall loop (~16 instructions per MMA), which
+// overloads the scheduler the MMA warp shares with two gather warps.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (elect_one())
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (elect_one())
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -334,7 +345,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   using M = Map<K16>;
   constexpr int kOffVol = M::off_vol, kOffW1 = M::off_w1, kOffW2 = M::off_w2, kOffA = M::off_a, kOffA2 = M::off_a2,
                 kOffBar = M::off_bar, kOffMisc = M::off_misc, kStageBytes = M::stage_bytes;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   Work work;
   {
     const int64_t total = (int64_t)B * N;
@@ -585,8 +596,8 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       }
     }
   } else if (warp == kMmaWarp) {
-    // =========================== MMA ISSUER ===========================
-    if (lane == 0) {
+    // =========================== MMA ISSUER (converged warp) ===========================
+    {
       constexpr uint32_t idesc1 = instr_desc(64, 32), idesc2 = instr_desc(128, 32);
       const uint32_t w1s = s_base + kOffW1, w2s = s_base + kOffW2;
       TileIter it(work);
@@ -670,10 +681,11 @@ struct MapTS {
 };
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (elect_one())
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
@@ -690,7 +702,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
                    u64* __restrict__ best_keys, int B, int64_t N) {
   extern __shared__ __align__(128) unsigned char smem[];
   using M = MapTS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
   Work work;
   {
     const int64_t total = (int64_t)B * N;
@@ -973,8 +985,8 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       ++g;
     }
   } else if (warp == kMmaWarp) {
-    // =========================== MMA ISSUER ===========================
-    if (lane == 0) {
+    // =========================== MMA ISSUER (converged warp) ===========================
+    {
       constexpr uint32_t idesc1 = instr_desc(64, 32), idesc2 = instr_desc(128, 32);
       const uint32_t w1s = s_base + M::off_w1, w2s = s_base + M::off_w2;
       TileIter it(work);
