@@ -171,45 +171,51 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// 1.0f the compiler cannot fold.  The rotation prefetch is loop-carried in registers; multiplying the
+// values loaded BEFORE the loop by this makes every loop-entry value ALU-defined, so the first use at
+// the loop top carries no scoreboard wait - otherwise that wait (on the scoreboard the just-issued
+// prefetch of the NEXT tile also uses) stalls the warp for a full L2 round trip per tile.
+__device__ __forceinline__ float opaque_one(int flag01) { return __uint_as_float(0x3f800000u + ((uint32_t)flag01 >> 8)); }
+
 struct Work {  // contiguous range of (pair, hypothesis) items of this CTA
   int64_t lo, hi, N;
 };
 
-// tile = two consecutive hypotheses of one pair; returns false when exhausted
+// tile = two consecutive hypotheses of one pair; advance() returns false when exhausted.  All per-tile
+// state is 32-bit (N <= 2^31-1 and the CTA's share of B*N < 2^32 are checked on the host): the iterator
+// runs once per tile in every role.
 struct TileIter {
-  int64_t next, hi, N, seg_end;
+  uint32_t n, N, left;  // next hypothesis within the pair, hypotheses per pair, items left for this CTA
   int b;
-  int64_t n0;  // first hypothesis of the tile
-  int cnt;     // 1 or 2 valid hypotheses
-  __device__ __forceinline__ TileIter(const Work& w) : next(w.lo), hi(w.hi), N(w.N), n0(0), cnt(0) {
+  uint32_t n0;  // first hypothesis of the tile
+  int cnt;      // 1 or 2 valid hypotheses
+  __device__ __forceinline__ TileIter(const Work& w) : N((uint32_t)w.N), left((uint32_t)(w.hi - w.lo)), n0(0), cnt(0) {
     b = (int)(w.lo / w.N);
-    seg_end = (int64_t)(b + 1) * w.N;
+    n = (uint32_t)(w.lo - (int64_t)b * w.N);
   }
   __device__ __forceinline__ bool advance() {
-    if (next >= hi) return false;
-    if (next >= seg_end) { ++b; seg_end += N; }
-    n0 = next - (seg_end - N);
-    const int64_t end = seg_end < hi ? seg_end : hi;
-    cnt = (end - next >= 2) ? 2 : 1;
-    next += cnt;
+    if (left == 0) return false;
+    if (n == N) { ++b; n = 0; }
+    n0 = n;
+    const uint32_t room = min(N - n, left);
+    cnt = room >= 2 ? 2 : 1;
+    n += cnt;
+    left -= cnt;
     return true;
   }
   // (pair, first hypothesis, count) of the tile the next advance() will produce; at the very end the
   // current tile again (a harmless, valid address for the rotation prefetch)
-  __device__ __forceinline__ void peek_tile(int& pb, int64_t& pn, int& pc) const {
-    if (next >= hi) { pb = b; pn = n0; pc = cnt > 0 ? cnt : 1; return; }
-    int64_t se = seg_end;
-    pb = b;
-    if (next >= se) { ++pb; se += N; }
-    pn = next - (se - N);
-    const int64_t end = se < hi ? se : hi;
-    pc = (end - next >= 2) ? 2 : 1;
+  __device__ __forceinline__ void peek_tile(int& pb, uint32_t& pn, int& pc) const {
+    if (left == 0) { pb = b; pn = n0; pc = cnt > 0 ? cnt : 1; return; }
+    pb = b; pn = n;
+    if (n == N) { ++pb; pn = 0; }
+    pc = min(N - pn, left) >= 2 ? 2 : 1;
   }
   // (pair, hypothesis) of the item following this tile, or the tile's own first item at the very end
-  __device__ __forceinline__ void peek(int& pb, int64_t& pn) const {
-    if (next >= hi) { pb = b; pn = n0; }
-    else if (next >= seg_end) { pb = b + 1; pn = 0; }
-    else { pb = b; pn = next - (seg_end - N); }
+  __device__ __forceinline__ void peek(int& pb, uint32_t& pn) const {
+    if (left == 0) { pb = b; pn = n0; }
+    else if (n == N) { pb = b + 1; pn = 0; }
+    else { pb = b; pn = n; }
   }
 };
 
@@ -244,14 +250,14 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
   float inv_s = 1.0f;
   uint32_t g = 0;
   int prev_b = 0, prev_cnt = 0;
-  int64_t prev_n0 = 0;
+  uint32_t prev_n0 = 0;
   float prev_inv = 1.0f;
   // arg-max fused into the epilogue (torch.max, modules/model.py:195): the two score-writing lanes keep a
   // running best key for the pair they are in and publish it with one atomicMax per (CTA, pair) - keys
   // order by score, ties by lowest index
   int key_b = -1;
   u64 key_best = 0;
-  auto phase_b = [&](uint32_t gg, int pb, int64_t pn0, int pcnt, float pinv) {
+  auto phase_b = [&](uint32_t gg, int pb, uint32_t pn0, int pcnt, float pinv) {
     const uint32_t gb = gg & 1, u = gg >> 1;
     mbar_wait(bar0 + (kD2Full + gb) * 8, u & 1);
     tc_fence_after();
@@ -421,7 +427,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       const int64_t n0 = work.lo - (int64_t)b0 * N;
       const float* Rg = R + (r_per_pair ? ((size_t)b0 * N + n0) : (size_t)n0) * 9;
 #pragma unroll
-      for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
+      for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e) * opaque_one(r_per_pair);
     }
     while (it.advance()) {
       if (it.b != cur_b) {
@@ -466,7 +472,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
 #pragma unroll
         for (int e = 0; e < 9; ++e) Rr[e] = Rn[e];
         {  // prefetch the next hypothesis' rotation (hides the L2 round trip behind this gather)
-          int nb; int64_t nn;
+          int nb; uint32_t nn;
           if (sl == 0) { nb = it.b; nn = it.n0 + (it.cnt > 1 ? 1 : 0); }
           else it.peek(nb, nn);
           const float* Rg = R + (r_per_pair ? ((size_t)nb * N + nn) : (size_t)nn) * 9;
@@ -769,15 +775,17 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     int cur_b = -1;
     uint32_t g = 0;
     float Rn[9];
-    auto fetch_R = [&](int fb, int64_t fn) {
+    auto fetch_R = [&](int fb, uint32_t fn) {
       const float* Rg = R + (r_per_pair ? ((size_t)fb * N + fn) : (size_t)fn) * 9;
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rn[e] = __ldg(Rg + e);
     };
     {
-      int fb; int64_t fn; int fc;
+      int fb; uint32_t fn; int fc;
       it.peek_tile(fb, fn, fc);
       fetch_R(fb, fn + (slot < fc ? slot : 0));
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Rn[e] *= opaque_one(r_per_pair);
     }
     while (it.advance()) {
       if (it.b != cur_b) {
@@ -821,7 +829,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rr[e] = Rn[e];
       {  // prefetch this lane's rotation of the next tile
-        int nb; int64_t nn; int nc;
+        int nb; uint32_t nn; int nc;
         it.peek_tile(nb, nn, nc);
         fetch_R(nb, nn + (slot < nc ? slot : 0));
       }
@@ -1186,6 +1194,7 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
   const int64_t tiles = ((int64_t)B * N + 1) / 2;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  if (((int64_t)B * N) / grid >= 0xffffffffLL) return AHV_EINVAL;  // per-CTA tile iterator is 32-bit
   {
     static const bool use_ts = [] { const char* e = getenv("AHV_TC_VARIANT"); return !(e && e[0] == 's'); }();
     if (use_ts) {
