@@ -762,12 +762,14 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     uint32_t koff[4], syz[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int ck = (rot + t) & 3;
+      // chunk visited at step t: a rotation for fp32, an XOR swizzle for 16-bit lines (chunk = tap*2 + chalf, so
+      // the tap of step t is (t>>1)^(rot>>1): steps 0,1 share one x tap, steps 2,3 the other - compile-time)
+      const int ck = K16 ? (rot ^ t) : ((rot + t) & 3);
       koff[t] = ck * 16;
       if constexpr (!K16)  // fp32: chunk ck = channels 4ck..4ck+3 (8 B of fp16)
         syz[t] = slot * M::yz_bytes + (ck >> 1) * M::yz_ch + (ck & 1) * 8 + d * M::yz_d + h_ * M::yz_h;
-      else                 // 16-bit: accumulator t&1 holds channel half (rot+t)&1 (16 B of fp16); t < 2 used
-        syz[t] = slot * M::yz_bytes + ((rot + t) & 1) * M::yz_ch + d * M::yz_d + h_ * M::yz_h;
+      else                 // 16-bit: accumulator t&1 holds channel half (rot^t)&1 (16 B of fp16); t < 2 used
+        syz[t] = slot * M::yz_bytes + ((rot ^ t) & 1) * M::yz_ch + d * M::yz_d + h_ * M::yz_h;
     }
     const unsigned char* volb = smem + M::off_vol;
     const int gtid = threadIdx.x;
@@ -787,6 +789,95 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rn[e] *= opaque_one(r_per_pair);
     }
+    // ---- 16-bit path: coordinates/weights of a voxel pair (w0, w0+1), computed one step AHEAD of its loads
+    // (software pipeline across voxel pairs and across tiles) so that the serial coordinate chains of one
+    // pair overlap the shared-memory traffic of the previous one ----
+    struct VoxPair16 {
+      const unsigned char* pa[2];
+      const unsigned char* pb[2];
+      __half2 wg[2][2][4];  // [voxel][x tap of steps {0,1} / {2,3}][y-z corner]
+    };
+    auto coords16 = [&](const float (&Rq)[9], int w0, VoxPair16& o) {
+      // grid = R @ (x, y, z): y and z are fixed per lane, x walks with w
+      const float pgx = fmaf(Rq[2], bz, Rq[1] * by), pgy = fmaf(Rq[5], bz, Rq[4] * by), pgz = fmaf(Rq[8], bz, Rq[7] * by);
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const float bx = sbase[w0 + v];
+        float ix = unnorm(fmaf(Rq[0], bx, pgx)), iy = unnorm(fmaf(Rq[3], bx, pgy)), iz = unnorm(fmaf(Rq[6], bx, pgz));
+        ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
+        const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
+        const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
+        const int pline = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * 9 + ((int)x0 + 1);
+        const int swapy = (pline ^ pf) & 1;  // first y tap = the one whose line has bank parity pf (9 is odd)
+        o.pa[v] = volb + (pline + swapy * 9) * 64;
+        o.pb[v] = volb + (pline + (1 - swapy) * 9) * 64;
+        const float wya = swapy ? fy : 1.0f - fy, wyb = swapy ? 1.0f - fy : fy;
+        const __half2 wy2[2] = {__float2half2_rn(wya), __float2half2_rn(wyb)};
+        const __half2 wz2[2] = {__float2half2_rn(1.0f - fz), __float2half2_rn(fz)};
+        // x tap read at steps {0,1} is (rot>>1), at steps {2,3} the other one
+        const __half2 wxf = __float2half2_rn((rot & 2) ? fx : 1.0f - fx), wxs = __float2half2_rn((rot & 2) ? 1.0f - fx : fx);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const __half2 w4 = __hmul2(wy2[c >> 1], wz2[c & 1]);
+          o.wg[v][0][c] = __hmul2(wxf, w4);
+          o.wg[v][1][c] = __hmul2(wxs, w4);
+        }
+      }
+    };
+    // trilinear taps of the pair (16 LDS.128 per voxel, packed HFMA2), then the operand stores
+    auto sample16 = [&](const VoxPair16& q, int w0, unsigned char* st, uint32_t ax) {
+      constexpr int kDz = kHalo * 9 * 64;
+      __half2 acc[2][2][4];
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) acc[v][0][e2] = acc[v][1][e2] = __float2half2_rn(0.0f);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        uint4 buf[2][4];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          buf[v][0] = *reinterpret_cast<const uint4*>(q.pa[v] + koff[t]);
+          buf[v][1] = *reinterpret_cast<const uint4*>(q.pa[v] + koff[t] + kDz);
+          buf[v][2] = *reinterpret_cast<const uint4*>(q.pb[v] + koff[t]);
+          buf[v][3] = *reinterpret_cast<const uint4*>(q.pb[v] + koff[t] + kDz);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const __half2 wg = q.wg[v][t >> 1][c];
+            const uint4 q4 = buf[v][c];
+            const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2)
+              acc[v][t & 1][k2] = __hfma2(wg, *reinterpret_cast<const __half2*>(&wd[k2]), acc[v][t & 1][k2]);
+          }
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int w = w0 + v;
+        uint32_t a0[4], a1[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          a0[k2] = *reinterpret_cast<const uint32_t*>(&acc[v][0][k2]);
+          a1[k2] = *reinterpret_cast<const uint32_t*>(&acc[v][1][k2]);
+        }
+        *reinterpret_cast<uint4*>(st + syz[0] + w * 16) = make_uint4(a0[0], a0[1], a0[2], a0[3]);
+        *reinterpret_cast<uint4*>(st + syz[1] + w * 16) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
+        // view x: acc[.][0] holds channel half (rot&1); put the halves in channel order and store to TMEM
+        const bool sw = rot & 1;
+        uint32_t regs[8];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          regs[k2] = sw ? a1[k2] : a0[k2];
+          regs[4 + k2] = sw ? a0[k2] : a1[k2];
+        }
+        tmem_st8(ax + w * 8, regs);
+      }
+    };
+    VoxPair16 vp_a, vp_b;
+    if constexpr (K16) coords16(Rn, whalf * 4, vp_a);  // first pair of the first tile
     while (it.advance()) {
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);
@@ -837,9 +928,9 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       if (use > 0) mbar_wait(bar0 + (kEmpty + stage) * 8, (use - 1) & 1);
       unsigned char* st = smem + M::off_a + stage * M::tile_bytes;
       const uint32_t ax = tmem + ((uint32_t)(32 * sub) << 16) + M::tmem_ax + stage * 64;
-      // grid = R @ (x, y, z): y and z are fixed per lane, x walks with w
-      const float pgx = fmaf(Rr[2], bz, Rr[1] * by), pgy = fmaf(Rr[5], bz, Rr[4] * by), pgz = fmaf(Rr[8], bz, Rr[7] * by);
       if constexpr (!K16) {
+        // grid = R @ (x, y, z): y and z are fixed per lane, x walks with w
+        const float pgx = fmaf(Rr[2], bz, Rr[1] * by), pgy = fmaf(Rr[5], bz, Rr[4] * by), pgz = fmaf(Rr[8], bz, Rr[7] * by);
 #pragma unroll 1
         for (int wi = 0; wi < 4; ++wi) {
           const int w = whalf * 4 + wi;
@@ -910,80 +1001,11 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
           tmem_st8(ax + w * 8, regs);
         }
       } else {
-        // 16-bit staged volume (x-pair lines, packed HFMA2).  This path is bound by per-warp dependency
-        // latency, not by bandwidth, so each lane interleaves TWO voxels (w, w+1): twice the independent
-        // instruction streams per warp.
-        constexpr int kDz = kHalo * 9 * 64;
-#pragma unroll 1
-        for (int wp = 0; wp < 2; ++wp) {
-          const unsigned char *pa[2], *pb[2];
-          __half2 w4[2][4], wxt[2][4], acc[2][2][4];
-#pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const float bx = sbase[whalf * 4 + wp * 2 + v];
-            float ix = unnorm(fmaf(Rr[0], bx, pgx)), iy = unnorm(fmaf(Rr[3], bx, pgy)), iz = unnorm(fmaf(Rr[6], bx, pgz));
-            ix = fminf(fmaxf(ix, -1.0f), 8.0f); iy = fminf(fmaxf(iy, -1.0f), 8.0f); iz = fminf(fmaxf(iz, -1.0f), 8.0f);
-            const float x0 = fminf(floorf(ix), 7.0f), y0 = fminf(floorf(iy), 7.0f), z0 = fminf(floorf(iz), 7.0f);
-            const float fx = ix - x0, fy = iy - y0, fz = iz - z0;
-            const int pline = (((int)z0 + 1) * kHalo + ((int)y0 + 1)) * 9 + ((int)x0 + 1);
-            const int swapy = (pline ^ pf) & 1;  // first y tap = the one whose line has bank parity pf (9 is odd)
-            pa[v] = volb + (pline + swapy * 9) * 64;
-            pb[v] = volb + (pline + (1 - swapy) * 9) * 64;
-            const float wya = swapy ? fy : 1.0f - fy, wyb = swapy ? 1.0f - fy : fy;
-            const __half2 wy2[2] = {__float2half2_rn(wya), __float2half2_rn(wyb)};
-            const __half2 wz2[2] = {__float2half2_rn(1.0f - fz), __float2half2_rn(fz)};
-            const __half2 wx2[2] = {__float2half2_rn(1.0f - fx), __float2half2_rn(fx)};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) w4[v][c] = __hmul2(wy2[c >> 1], wz2[c & 1]);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) wxt[v][t] = (((rot + t) & 3) >> 1) ? wx2[1] : wx2[0];  // tap of chunk (rot+t)&3
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) acc[v][0][e2] = acc[v][1][e2] = __float2half2_rn(0.0f);
-          }
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            uint4 buf[2][4];
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              buf[v][0] = *reinterpret_cast<const uint4*>(pa[v] + koff[t]);
-              buf[v][1] = *reinterpret_cast<const uint4*>(pa[v] + koff[t] + kDz);
-              buf[v][2] = *reinterpret_cast<const uint4*>(pb[v] + koff[t]);
-              buf[v][3] = *reinterpret_cast<const uint4*>(pb[v] + koff[t] + kDz);
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-              for (int v = 0; v < 2; ++v) {
-                const __half2 wg = __hmul2(wxt[v][t], w4[v][c]);
-                const uint4 q4 = buf[v][c];
-                const uint32_t wd[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2)
-                  acc[v][t & 1][k2] = __hfma2(wg, *reinterpret_cast<const __half2*>(&wd[k2]), acc[v][t & 1][k2]);
-              }
-          }
-#pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const int w = whalf * 4 + wp * 2 + v;
-            uint32_t a0[4], a1[4];
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              a0[k2] = *reinterpret_cast<const uint32_t*>(&acc[v][0][k2]);
-              a1[k2] = *reinterpret_cast<const uint32_t*>(&acc[v][1][k2]);
-            }
-            *reinterpret_cast<uint4*>(st + syz[0] + w * 16) = make_uint4(a0[0], a0[1], a0[2], a0[3]);
-            *reinterpret_cast<uint4*>(st + syz[1] + w * 16) = make_uint4(a1[0], a1[1], a1[2], a1[3]);
-            // view x: acc[.][0] holds channel half (rot&1); put the halves in channel order and store to TMEM
-            const bool sw = rot & 1;
-            uint32_t regs[8];
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              regs[k2] = sw ? a1[k2] : a0[k2];
-              regs[4 + k2] = sw ? a0[k2] : a1[k2];
-            }
-            tmem_st8(ax + w * 8, regs);
-          }
-        }
+        // 16-bit staged volume (x-pair lines, packed HFMA2): pair 0 was prepared during the previous tile
+        sample16(vp_a, whalf * 4, st, ax);
+        coords16(Rr, whalf * 4 + 2, vp_b);   // overlaps the loads of pair 0
+        sample16(vp_b, whalf * 4 + 2, st, ax);
+        coords16(Rn, whalf * 4, vp_a);       // next tile's pair 0 (Rn = its prefetched rotation) overlaps pair 1
       }
       tmem_st_wait();
       fence_proxy_async();  // YZ stores -> async proxy
