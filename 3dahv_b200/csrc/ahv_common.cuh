@@ -92,6 +92,8 @@ int launch_rotate_volume_bwd(const float* grad_out, int per_rot, const float* R,
                              float* grad_vol, int64_t n, cudaStream_t s);
 int launch_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                         float* feat, int64_t m, cudaStream_t s);
+int launch_tgt_feat(const float* vol_tgt, const float* W1, const float* W2, const float* b2,
+                    unsigned long long* clear_keys, float* feat, int B, cudaStream_t s);
 int launch_score_fp32(const void* vol_src, int vol_dtype, const float* tgt_feat, const float* R,
                       int r_per_pair, const float* W1, const float* W2, const float* b2,
                       const float* base, float* scores, int B, int64_t N, cudaStream_t s);

@@ -295,6 +295,10 @@ int launch_score_fp32(const void* vol_src, int vol_dtype, const float* tgt_feat,
 int launch_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                         float* feat, int64_t m, cudaStream_t s) {
   if (m == 0) return AHV_OK;
+  // the per-pair sizes of the verification step take the same kernel as the fused step's prologue, so
+  // ahv_score (caller-computed target features) and ahv_verify agree bit for bit; the persistent
+  // weight-staging kernel below serves bulk calls (refcompat: thousands of materialised volumes)
+  if (m <= 4096) return launch_tgt_feat(vol, W1, W2, b2, nullptr, feat, (int)m, s);
   const int sms = sm_count();
   if (sms <= 0) return AHV_ECUDA;
   const unsigned grid = (unsigned)(m < sms ? m : sms);

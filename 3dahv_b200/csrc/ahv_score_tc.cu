@@ -226,6 +226,97 @@ __device__ __forceinline__ float ld_vol<float>(const float* p) { return __ldg(p)
 template <>
 __device__ __forceinline__ float ld_vol<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
+// ---- one-time per CTA: W1/W2 (fp32, global) -> fp16 UMMA B-operand layouts in shared memory ------------
+// conv1: 24 slices j = (view, kk), each [chalf][ngroup][n%8][c%8]; conv2: [kc][ngroup][8][8] behind them.
+// Also leaves the largest L1 norm of a W1 row in *l1max_bits (bounds |conv1 output| / max|V|; a positive
+// float's bit pattern orders like the float).  Every CTA does this itself (48 KB of L2 reads) so that the
+// scoring kernel depends on no preparation kernel.
+__device__ __forceinline__ void pack_weights(unsigned char* wsm, uint32_t* l1max_bits, const float* __restrict__ W1,
+                                             const float* __restrict__ W2, int warp, int lane) {
+  __half* w1h = reinterpret_cast<__half*>(wsm);
+  for (int n = warp; n < kO; n += kThreadsTC / 32) {
+    float l1 = 0.0f;
+    for (int k = lane; k < kK; k += 32) {
+      const float w = __ldg(W1 + n * kK + k);
+      l1 += fabsf(w);
+      const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7, j = view * 8 + kk;
+      w1h[j * 512 + (c >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (c & 7)] = __float2half_rn(w);
+    }
+    l1 = warp_sum(l1);
+    if (lane == 0) atomicMax(l1max_bits, __float_as_uint(l1));
+  }
+  for (int i = threadIdx.x; i < kO * kO; i += kThreadsTC) {
+    const int n = i / kO, k = i % kO;
+    w1h[kW1Bytes / 2 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2half_rn(__ldg(W2 + i));
+  }
+}
+
+// ---- per pair: stage the source volume, pre-scaled by the pair's power-of-two scale -------------------
+// Called by the 256 gather threads between two named barriers.  The volume is read once into registers, its
+// max |V| reduced over the 8 warps, the scale s = 2^e chosen so that max|V|*s <= 2^12 and
+// max|V|*s*L1max <= 2^14 (fp16 max 65504; exact, undone after conv2), then the scaled values are written in
+// the gather's layout: fp32 lines [halo voxel][16 ch], or for 16-bit "x-pair lines" (every voxel is tap 0 of
+// pair xh and tap 1 of pair xh-1).  Returns 1/s.
+template <typename T, bool K16>
+__device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* __restrict__ vg, float l1max,
+                                                   float* red, int gtid) {
+  float val[32];
+  float mx = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    // fp32: task = gtid + 256*(i>>2) -> (voxel, 4-channel group jj), channel jj*4 + (i&3)
+    // 16-bit: task = gtid + 256*(i>>3) -> (voxel, channel half), channel chalf*8 + (i&7)
+    const int task = gtid + 256 * (K16 ? (i >> 3) : (i >> 2));
+    const int v = task & 511, grp = task >> 9;
+    const int ch = K16 ? grp * 8 + (i & 7) : grp * 4 + (i & 3);
+    val[i] = ld_vol<T>(vg + ch * kVox + v);
+    mx = fmaxf(mx, fabsf(val[i]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((gtid & 31) == 0) red[gtid >> 5] = mx;
+  named_bar_sync(1, kGatherWarps * 32);
+  float m = red[0];
+#pragma unroll
+  for (int w = 1; w < kGatherWarps; ++w) m = fmaxf(m, red[w]);
+  float sc = 1.0f;
+  if (m > 0.0f && isfinite(m)) {
+    const float bound = fminf(4096.0f, 16384.0f / fmaxf(l1max, 1e-20f));
+    int e = ilogbf(bound / m);  // floor(log2)
+    e = max(-100, min(100, e));
+    sc = scalbnf(1.0f, e);
+  }
+  if constexpr (!K16) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int task = gtid + 256 * it;
+      const int v = task & 511, jj = task >> 9;
+      const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
+      const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
+      *reinterpret_cast<float4*>(vsm + (line * kC + jj * 4) * 4) =
+          make_float4(val[4 * it] * sc, val[4 * it + 1] * sc, val[4 * it + 2] * sc, val[4 * it + 3] * sc);
+    }
+  } else {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int task = gtid + 256 * it;
+      const int v = task & 511, chalf = task >> 9;
+      const int zh = (v >> 6) + 1, yh = ((v >> 3) & 7) + 1, xh = (v & 7) + 1;
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {  // bf16 inputs (8-bit mantissa) x power-of-two scale -> fp16 exactly; fp32 inputs are rounded
+        const __half2 two = __floats2half2_rn(val[8 * it + 2 * e] * sc, val[8 * it + 2 * e + 1] * sc);
+        pk[e] = *reinterpret_cast<const uint32_t*>(&two);
+      }
+      const uint4 q4 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      unsigned char* row = vsm + ((zh * kHalo + yh) * 9) * 64;
+      *reinterpret_cast<uint4*>(row + xh * 64 + chalf * 16) = q4;              // tap 0 of pair xh (xh <= 8)
+      *reinterpret_cast<uint4*>(row + (xh - 1) * 64 + 32 + chalf * 16) = q4;   // tap 1 of pair xh-1
+    }
+  }
+  return 1.0f / sc;
+}
+
 // ---- epilogue role, shared by the SS and TS kernels ---------------------------------------------------
 // 4 warps, warp s = TMEM sub-partition s.  Per hypothesis pair (tile):
 //   phase A: tcgen05.ld D1 -> ReLU (modules/modules.py:68) -> fp16 -> conv2's A operand, either as the
@@ -237,7 +328,7 @@ template <bool kA2InTmem>
 __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane, uint32_t tmem, uint32_t bar0,
                                               unsigned char* a2_smem, uint32_t tmem_a2, float* partial,
                                               const float* __restrict__ tgt_feat, const float* __restrict__ b2,
-                                              const float2* __restrict__ pair_scale, float* __restrict__ scores,
+                                              const float* inv_ring, float* __restrict__ scores,
                                               u64* __restrict__ best_keys, int64_t N) {
   const int slot = lane >> 4;            // which hypothesis of the tile
   const int pos = 16 * s + (lane & 15);  // position p*8+q of the folded plane
@@ -245,6 +336,9 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
   float b2r[kO], tg[kO];
 #pragma unroll
   for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
+  // the target features and the cleared arg-max keys come from the prologue grid; every other role of this
+  // kernel is independent of it (no-op when the kernel was not launched programmatically dependent)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   TileIter it(work);
   int cur_b = -1;
   float inv_s = 1.0f;
@@ -328,7 +422,7 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
     if (g > 0) phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
     if (it.b != cur_b) {  // target features / scale of the tile just handed to conv2
       cur_b = it.b;
-      inv_s = pair_scale[cur_b].y;
+      inv_s = inv_ring[cur_b & 7];  // written by the gather role when it staged this pair
 #pragma unroll
       for (int o = 0; o < kO; ++o) tg[o] = __ldg(tgt_feat + ((size_t)cur_b * kO + o) * kP + pos);
     }
@@ -344,8 +438,8 @@ template <typename T, bool K16>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_feat,
                 const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
-                const float* __restrict__ base, const uint4* __restrict__ w_packed,
-                const float2* __restrict__ pair_scale, float* __restrict__ scores,
+                const float* __restrict__ base, const float* __restrict__ W1,
+                const float* __restrict__ W2, float* __restrict__ scores,
                 u64* __restrict__ best_keys, int B, int64_t N) {
   extern __shared__ __align__(128) unsigned char smem[];
   using M = Map<K16>;
@@ -367,13 +461,17 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc);
   float* partial = reinterpret_cast<float*>(smem + kOffMisc + 16);  // [2 tilebuf][2 slot][4 warps]
   float* sbase = reinterpret_cast<float*>(smem + kOffMisc + 96);    // 8 base coordinates
+  uint32_t* l1max_bits = reinterpret_cast<uint32_t*>(smem + kOffMisc + 128);  // max L1 norm of a W1 row (float bits)
+  float* red = reinterpret_cast<float*>(smem + kOffMisc + 144);        // 8 per-warp maxima (volume staging)
+  float* inv_ring = reinterpret_cast<float*>(smem + kOffMisc + 176);   // 1/scale of pair b at [b & 7] (gather -> epilogue)
 
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < kVolSmemBytes / 16; i += kThreadsTC)
     reinterpret_cast<uint4*>(vol)[i] = make_uint4(0, 0, 0, 0);  // halo stays zero for the whole kernel
-  for (int i = threadIdx.x; i < (kW1Bytes + kW2Bytes) / 16; i += kThreadsTC)
-    reinterpret_cast<uint4*>(smem + kOffW1)[i] = w_packed[i];
   if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
+  if (threadIdx.x == 8) *l1max_bits = 0u;
+  __syncthreads();
+  pack_weights(smem + kOffW1, l1max_bits, W1, W2, warp, lane);
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
@@ -433,37 +531,8 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);  // everyone is done reading the previous volume
         const T* vg = vol_src + (size_t)it.b * kC * kVox;
-        const float sc = pair_scale[it.b].x;
-        if constexpr (!K16) {
-          for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
-            const int v = task & 511, jj = task >> 9;
-            const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
-            const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
-            float4 o;
-            o.x = ld_vol<T>(vg + (jj * 4 + 0) * kVox + v) * sc;
-            o.y = ld_vol<T>(vg + (jj * 4 + 1) * kVox + v) * sc;
-            o.z = ld_vol<T>(vg + (jj * 4 + 2) * kVox + v) * sc;
-            o.w = ld_vol<T>(vg + (jj * 4 + 3) * kVox + v) * sc;
-            *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
-          }
-        } else {
-          // every voxel goes into two pair lines: as tap 0 of pair x0h = xh and as tap 1 of pair xh-1
-          for (int task = gtid; task < 2 * kVox; task += kGatherWarps * 32) {
-            const int v = task & 511, chalf = task >> 9;
-            const int zh = (v >> 6) + 1, yh = ((v >> 3) & 7) + 1, xh = (v & 7) + 1;
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {  // bf16 inputs (8-bit mantissa) x power-of-two scale -> fp16 exactly; fp32 inputs are rounded
-              const __half2 two = __floats2half2_rn(ld_vol<T>(vg + (chalf * 8 + 2 * e) * kVox + v) * sc,
-                                                    ld_vol<T>(vg + (chalf * 8 + 2 * e + 1) * kVox + v) * sc);
-              pk[e] = *reinterpret_cast<const uint32_t*>(&two);
-            }
-            const uint4 q4 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            unsigned char* row = smem + kOffVol + ((zh * kHalo + yh) * 9) * 64;
-            *reinterpret_cast<uint4*>(row + xh * 64 + chalf * 16) = q4;              // tap 0 of pair xh (xh <= 8)
-            *reinterpret_cast<uint4*>(row + (xh - 1) * 64 + 32 + chalf * 16) = q4;   // tap 1 of pair xh-1
-          }
-        }
+        const float inv = stage_pair_volume<T, K16>(smem + kOffVol, vg, __uint_as_float(*l1max_bits), red, gtid);
+        if (gtid == 0) inv_ring[it.b & 7] = inv;
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
       }
@@ -647,7 +716,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     __syncwarp();
   } else {
     // =========================== EPILOGUE ===========================
-    epilogue_role<false>(work, warp - kEpiWarp0, lane, tmem, bar0, smem + kOffA2, 0, partial, tgt_feat, b2, pair_scale,
+    epilogue_role<false>(work, warp - kEpiWarp0, lane, tmem, bar0, smem + kOffA2, 0, partial, tgt_feat, b2, inv_ring,
                          scores, best_keys, N);
   }
 
@@ -703,8 +772,8 @@ template <typename T, bool K16>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_feat,
                    const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
-                   const float* __restrict__ base, const uint4* __restrict__ w_packed,
-                   const float2* __restrict__ pair_scale, float* __restrict__ scores,
+                   const float* __restrict__ base, const float* __restrict__ W1,
+                   const float* __restrict__ W2, float* __restrict__ scores,
                    u64* __restrict__ best_keys, int B, int64_t N) {
   extern __shared__ __align__(128) unsigned char smem[];
   using M = MapTS;
@@ -724,12 +793,16 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + M::off_misc);
   float* partial = reinterpret_cast<float*>(smem + M::off_misc + 16);  // [2 tilebuf][2 slot][4 warps]
   float* sbase = reinterpret_cast<float*>(smem + M::off_misc + 96);    // 8 base coordinates
+  uint32_t* l1max_bits = reinterpret_cast<uint32_t*>(smem + M::off_misc + 128);  // max L1 norm of a W1 row (float bits)
+  float* red = reinterpret_cast<float*>(smem + M::off_misc + 144);        // 8 per-warp maxima (volume staging)
+  float* inv_ring = reinterpret_cast<float*>(smem + M::off_misc + 176);   // 1/scale of pair b at [b & 7] (gather -> epilogue)
 
   for (int i = threadIdx.x; i < kVolSmemBytes / 16; i += kThreadsTC)
     reinterpret_cast<uint4*>(vol)[i] = make_uint4(0, 0, 0, 0);  // halo stays zero for the whole kernel
-  for (int i = threadIdx.x; i < (kW1Bytes + kW2Bytes) / 16; i += kThreadsTC)
-    reinterpret_cast<uint4*>(smem + M::off_w1)[i] = w_packed[i];
   if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
+  if (threadIdx.x == 8) *l1max_bits = 0u;
+  __syncthreads();
+  pack_weights(smem + M::off_w1, l1max_bits, W1, W2, warp, lane);
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
@@ -882,37 +955,8 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);
         const T* vg = vol_src + (size_t)it.b * kC * kVox;
-        const float sc = pair_scale[it.b].x;
-        if constexpr (!K16) {
-          for (int task = gtid; task < 4 * kVox; task += kGatherWarps * 32) {
-            const int v = task & 511, jj = task >> 9;
-            const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
-            const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
-            float4 o;
-            o.x = ld_vol<T>(vg + (jj * 4 + 0) * kVox + v) * sc;
-            o.y = ld_vol<T>(vg + (jj * 4 + 1) * kVox + v) * sc;
-            o.z = ld_vol<T>(vg + (jj * 4 + 2) * kVox + v) * sc;
-            o.w = ld_vol<T>(vg + (jj * 4 + 3) * kVox + v) * sc;
-            *reinterpret_cast<float4*>(vol + line * kC + jj * 4) = o;
-          }
-        } else {
-          // x-pair lines (see the SS kernel): every voxel is tap 0 of pair xh and tap 1 of pair xh-1
-          for (int task = gtid; task < 2 * kVox; task += kGatherWarps * 32) {
-            const int v = task & 511, chalf = task >> 9;
-            const int zh = (v >> 6) + 1, yh = ((v >> 3) & 7) + 1, xh = (v & 7) + 1;
-            uint32_t pk8[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __half2 two = __floats2half2_rn(ld_vol<T>(vg + (chalf * 8 + 2 * e) * kVox + v) * sc,
-                                                    ld_vol<T>(vg + (chalf * 8 + 2 * e + 1) * kVox + v) * sc);
-              pk8[e] = *reinterpret_cast<const uint32_t*>(&two);
-            }
-            const uint4 q4 = make_uint4(pk8[0], pk8[1], pk8[2], pk8[3]);
-            unsigned char* rowp = smem + M::off_vol + ((zh * kHalo + yh) * 9) * 64;
-            *reinterpret_cast<uint4*>(rowp + xh * 64 + chalf * 16) = q4;
-            *reinterpret_cast<uint4*>(rowp + (xh - 1) * 64 + 32 + chalf * 16) = q4;
-          }
-        }
+        const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, vg, __uint_as_float(*l1max_bits), red, gtid);
+        if (gtid == 0) inv_ring[it.b & 7] = inv;
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
       }
@@ -1062,7 +1106,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     __syncwarp();
   } else {
     // =========================== EPILOGUE ===========================
-    epilogue_role<true>(work, warp - kEpiWarp0, lane, tmem, bar0, nullptr, M::tmem_a2, partial, tgt_feat, b2, pair_scale,
+    epilogue_role<true>(work, warp - kEpiWarp0, lane, tmem, bar0, nullptr, M::tmem_a2, partial, tgt_feat, b2, inv_ring,
                         scores, best_keys, N);
   }
 
@@ -1074,87 +1118,75 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
   }
 }
 
-// ---- prologue: one launch, three independent jobs running concurrently -------------------
-//   block 0        : pack W1/W2 to fp16 in the UMMA B-operand layouts; clear the arg-max keys
-//   blocks 1..B    : per-pair power-of-two scale
-//   blocks B+1..2B : target features forward_3d2d(vol_tgt[b]) (modules/model.py:191), fp32 FFMA
-// w_packed: conv1 B operand, 24 slices j=(view,kk): [chalf][ngroup][n%8][c%8] fp16, then conv2's.
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
-tc_prologue_kernel(const T* __restrict__ vol_src, const float* __restrict__ vol_tgt,
-                   const float* __restrict__ W1, const float* __restrict__ W2,
-                   const float* __restrict__ b2, __half* __restrict__ w_packed,
-                   float2* __restrict__ pair_scale, u64* __restrict__ best_keys,
-                   float* __restrict__ tgt_feat, int B) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red[8];
-  __shared__ float l1max_s;
-  const int t = threadIdx.x;
-  if (blockIdx.x == 0) {
-    for (int i = t; i < kO * kK; i += kThreads) {
-      const int n = i / kK, k = i % kK;
-      const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7;
-      const int j = view * 8 + kk;
-      w_packed[j * 512 + (c >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (c & 7)] = __float2half_rn(W1[i]);
-    }
-    for (int i = t; i < kO * kO; i += kThreads) {
-      const int n = i / kO, k = i % kO;
-      w_packed[kW1Bytes / 2 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2half_rn(W2[i]);
-    }
-    if (best_keys)
-      for (int i = t; i < B; i += kThreads) best_keys[i] = 0ull;
-    return;
-  }
-  if ((int)blockIdx.x > B) {  // target features
-    Fp32Smem& sm = *reinterpret_cast<Fp32Smem*>(smem_raw);
-    const int b = blockIdx.x - 1 - B;
-    stage_weights(sm, W1, W2, nullptr);
-    float b2r[8];
+// ---- prologue: target features forward_3d2d(vol_tgt[b]) (modules/model.py:191) in fp32, + arg-max key clear ----
+// grid (16, B), 128 threads: CTA (j, b) computes the 4 positions (p = j>>1, q = 4*(j&1) .. +3) of pair b for
+// all 32 channels.  6.7 KB of static shared memory and <= 96 registers per thread, so these CTAs co-reside
+// with the scoring kernel's CTAs (201 KB, 416 x 128 registers): the scoring kernel is launched
+// programmatically dependent and only its epilogue warps wait for this grid.
+//   A[q][k]   tri-plane operand of the 4 positions (modules/modules.py:115-118):
+//             k = c*8+kk       -> V[c, p, q, kk]   (view x)
+//             k = 128+c*8+kk   -> V[c, p, kk, q]   (view y)
+//             k = 256+c*8+kk   -> V[c, kk, p, q]   (view z)
+//   conv1: warp w owns output rows o = w, w+4, ..., w+28; lanes stride k (coalesced W1 row reads, the next
+//          row's 12 values in flight while this row is reduced); ReLU -> h1[q][o].
+//   conv2 + bias + L2 normalise: warp = position, lane = output channel.
+constexpr int kTgtThreads = 128, kTgtCtasPerPair = 16;
+__global__ void __launch_bounds__(kTgtThreads, 4)
+tc_tgt_feat_kernel(const float* __restrict__ vol_tgt, const float* __restrict__ W1, const float* __restrict__ W2,
+                   const float* __restrict__ b2, u64* __restrict__ best_keys, float* __restrict__ tgt_feat, int B) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the scoring kernel start its setup now
+  __shared__ float A[4][kK];
+  __shared__ float h1[4][kO + 1];
+  const int p = blockIdx.x >> 1, q0 = (blockIdx.x & 1) * 4, b = blockIdx.y;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  if (best_keys && blockIdx.x == 0 && t == 0) best_keys[b] = 0ull;
+  const float* V = vol_tgt + (size_t)b * kC * kVox;
+  float wr[2][12];
 #pragma unroll
-    for (int oo = 0; oo < 8; ++oo) b2r[oo] = b2[(t & 3) * 8 + oo];
-    forward_3d2d_block<float>(sm, vol_tgt + (size_t)b * kC * kVox, b2r, tgt_feat + (size_t)b * kO * kP);
-    return;
+  for (int j = 0; j < 12; ++j) wr[0][j] = __ldg(W1 + warp * kK + lane + 32 * j);
+#pragma unroll
+  for (int i = 0; i < 4 * kK / kTgtThreads; ++i) {
+    const int e = t + kTgtThreads * i;
+    const int ql = e / kK, k = e - ql * kK, q = q0 + ql;
+    const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7;
+    const int d = view == 2 ? kk : p, h = view == 0 ? q : (view == 1 ? kk : p), w = view == 0 ? kk : q;
+    A[ql][k] = __ldg(V + c * kVox + d * 64 + h * 8 + w);
   }
-  const int b = blockIdx.x - 1;
-  // largest L1 norm of a W1 row bounds |conv1 output| / max|V|
-  float l1 = 0.0f;
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < 8; r += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {  // two rows per trip so the double buffer is statically indexed
+      const int o = warp + 4 * (r + u);
+      if (r + u + 1 < 8) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) wr[u ^ 1][j] = __ldg(W1 + (o + 4) * kK + lane + 32 * j);
+      }
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int j = 0; j < 12; ++j)
+#pragma unroll
+        for (int ql = 0; ql < 4; ++ql) acc[ql] = fmaf(wr[u][j], A[ql][lane + 32 * j], acc[ql]);
+#pragma unroll
+      for (int ql = 0; ql < 4; ++ql) {
+        const float v = warp_sum(acc[ql]);
+        if (lane == ql) h1[ql][o] = fmaxf(v, 0.0f);  // ReLU (modules/modules.py:68)
+      }
+    }
+  }
+  __syncthreads();
   {
-    const int o = t >> 3, part = t & 7;  // 8 threads per output row
-    for (int k = part; k < kK; k += 8) l1 += fabsf(W1[o * kK + k]);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 4);
+    const int ql = warp, o2 = lane;  // 4 warps = 4 positions, lanes = output channels
+    float v = __ldg(b2 + o2);
 #pragma unroll
-    for (int o2 = 8; o2 < 32; o2 <<= 1) l1 = fmaxf(l1, __shfl_xor_sync(0xffffffffu, l1, o2));
-    if ((t & 31) == 0) red[t >> 5] = l1;
-    __syncthreads();
-    if (t == 0) {
-      float m = red[0];
-      for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-      l1max_s = m;
+    for (int o = 0; o < kO; o += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(W2 + o2 * kO + o));
+      v = fmaf(w4.x, h1[ql][o], v); v = fmaf(w4.y, h1[ql][o + 1], v);
+      v = fmaf(w4.z, h1[ql][o + 2], v); v = fmaf(w4.w, h1[ql][o + 3], v);
     }
-    __syncthreads();
-  }
-  float mx = 0.0f;
-  const T* v = vol_src + (size_t)b * kC * kVox;
-  for (int i = t; i < kC * kVox; i += kThreads) mx = fmaxf(mx, fabsf(ld_vol<T>(v + i)));
-#pragma unroll
-  for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-  __syncthreads();
-  if ((t & 31) == 0) red[t >> 5] = mx;
-  __syncthreads();
-  if (t == 0) {
-    float m = red[0];
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-    // power-of-two scale: max|V|*s <= 2^12 and max|V|*s*L1max <= 2^14 (fp16 max 65504)
-    float s = 1.0f;
-    if (m > 0.0f && isfinite(m)) {
-      const float bound = fminf(4096.0f, 16384.0f / fmaxf(l1max_s, 1e-20f));
-      int e = ilogbf(bound / m);  // floor(log2)
-      e = max(-100, min(100, e));
-      s = scalbnf(1.0f, e);
-    }
-    pair_scale[b] = make_float2(s, 1.0f / s);
+    const float ss = warp_sum(v * v);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps (modules/modules.py:122)
+    tgt_feat[((size_t)b * kO + o2) * kP + p * 8 + q0 + ql] = v * inv;
   }
 }
 
@@ -1198,6 +1230,26 @@ __host__ inline Scratch carve(void* ws, int B) {
   return sc;
 }
 
+template <typename KernelT, typename... Args>
+static int launch_pdl(KernelT kernel, unsigned grid, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsTC);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  AHV_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, args...));
+  return AHV_OK;
+}
+
+// Launches: [target features + key clear] -> scoring.  The scoring kernel packs the weights and derives
+// the per-pair scales itself; when the prologue runs, the scoring kernel is launched programmatically
+// dependent on it (its setup, weight packing, volume staging and first gathers overlap the prologue; only
+// the epilogue warps wait for the target features).
 template <typename T, bool K16>
 int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_in, const float* R,
                  int r_per_pair, const float* W1, const float* W2, const float* b2, const float* base,
@@ -1205,39 +1257,47 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   int dev = 0, sms = 0;
   AHV_CUDA_OK(cudaGetDevice(&dev));
   AHV_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int pro_blocks = 1 + B + (vol_tgt ? B : 0);
-  const size_t pro_smem = vol_tgt ? sizeof(Fp32Smem) : 0;
-  AHV_CUDA_OK(cudaFuncSetAttribute(tc_prologue_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(Fp32Smem)));
-  tc_prologue_kernel<T><<<pro_blocks, kThreads, pro_smem, s>>>(vol_src, vol_tgt, W1, W2, b2, sc.w_packed,
-                                                              sc.pair_scale, want_argmax ? sc.best_keys : nullptr,
-                                                              sc.tgt_feat, B);
-  AHV_CUDA_OK(cudaGetLastError());
+  const bool prologue = vol_tgt != nullptr;
+  if (prologue) {
+    const int st = launch_tgt_feat(vol_tgt, W1, W2, b2, want_argmax ? sc.best_keys : nullptr, sc.tgt_feat, B, s);
+    if (st != AHV_OK) return st;
+  } else if (want_argmax) {
+    AHV_CUDA_OK(cudaMemsetAsync(sc.best_keys, 0, (size_t)B * sizeof(u64), s));
+  }
   // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
   const int64_t tiles = ((int64_t)B * N + 1) / 2;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   if (((int64_t)B * N) / grid >= 0xffffffffLL) return AHV_EINVAL;  // per-CTA tile iterator is 32-bit
-  {
-    static const bool use_ts = [] { const char* e = getenv("AHV_TC_VARIANT"); return !(e && e[0] == 's'); }();
-    if (use_ts) {
-      AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
-      score_tc_ts_kernel<T, K16><<<grid, kThreadsTC, MapTS::smem_bytes, s>>>(
-          vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair, b2, base, (const uint4*)sc.w_packed, sc.pair_scale,
-          scores, want_argmax ? sc.best_keys : nullptr, B, N);
-      AHV_CUDA_OK(cudaGetLastError());
-      return AHV_OK;
-    }
+  const float* tgt = prologue ? sc.tgt_feat : tgt_feat_in;
+  u64* keys = want_argmax ? sc.best_keys : nullptr;
+  static const bool use_ts = [] { const char* e = getenv("AHV_TC_VARIANT"); return !(e && e[0] == 's'); }();
+  static const bool use_pdl = [] { const char* e = getenv("AHV_PDL"); return !(e && e[0] == '0'); }();
+  if (use_ts) {
+    AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
+    return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue && use_pdl, vol_src, tgt, R, r_per_pair,
+                      b2, base, W1, W2, scores, keys, B, N);
   }
   constexpr int kSmemBytes = Map<K16>::smem_bytes;
   AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  score_tc_kernel<T, K16><<<grid, kThreadsTC, kSmemBytes, s>>>(vol_src, vol_tgt ? sc.tgt_feat : tgt_feat_in, R, r_per_pair,
-                                                         b2, base, (const uint4*)sc.w_packed, sc.pair_scale, scores,
-                                                         want_argmax ? sc.best_keys : nullptr, B, N);
-  AHV_CUDA_OK(cudaGetLastError());
-  return AHV_OK;
+  return launch_pdl(score_tc_kernel<T, K16>, grid, kSmemBytes, s, prologue && use_pdl, vol_src, tgt, R, r_per_pair, b2, base,
+                    W1, W2, scores, keys, B, N);
 }
 
 }  // namespace tc
+
+// forward_3d2d for B plain volumes (+ optional clear of B arg-max keys): the fused step's prologue, also
+// behind ahv_forward_3d2d for per-pair sizes
+int launch_tgt_feat(const float* vol_tgt, const float* W1, const float* W2, const float* b2,
+                    unsigned long long* clear_keys, float* feat, int B, cudaStream_t s) {
+  for (int b0 = 0; b0 < B; b0 += 65535) {  // gridDim.y limit
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    tc::tc_tgt_feat_kernel<<<dim3(tc::kTgtCtasPerPair, nb), tc::kTgtThreads, 0, s>>>(vol_tgt + (size_t)b0 * kC * kVox, W1, W2, b2,
+                                                      clear_keys ? clear_keys + b0 : nullptr,
+                                                      feat + (size_t)b0 * kO * kP, nb);
+    AHV_CUDA_OK(cudaGetLastError());
+  }
+  return AHV_OK;
+}
 
 size_t score_tc_workspace_bytes(int B, int64_t N) {
   (void)N;
