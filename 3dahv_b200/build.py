@@ -40,6 +40,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
+    flags = NVCC_FLAGS + (["-DAHV_TIMELINE"] if os.environ.get("AHV_TIMELINE") else [])  # diagnostics build
     objs = []
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
@@ -47,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

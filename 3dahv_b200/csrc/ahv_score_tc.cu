@@ -41,6 +41,20 @@ namespace ahv {
 
 namespace tc {
 
+// Optional in-kernel timeline (build with -DAHV_TIMELINE, read with ahv_diag_timeline): globaltimer stamps
+// of the TS kernel's setup / first-tile milestones per CTA, used to attribute the fixed cost of a launch.
+#ifdef AHV_TIMELINE
+__device__ unsigned long long g_timeline[160][16];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define AHV_TL(i) g_timeline[blockIdx.x][i] = gtimer()
+#else
+#define AHV_TL(i) ((void)0)
+#endif
+
 constexpr int kGatherWarps = 8;
 constexpr int kEpiWarp0 = 8;
 constexpr int kMmaWarp = 12;
@@ -177,6 +191,16 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
 // prefetch of the NEXT tile also uses) stalls the warp for a full L2 round trip per tile.
 __device__ __forceinline__ float opaque_one(int flag01) { return __uint_as_float(0x3f800000u + ((uint32_t)flag01 >> 8)); }
 
+// Fused selection epilogue (modules/model.py:195-196): the last CTA to finish decodes the arg-max keys
+// into (score, global index, sampled_R[pred_index]) per pair.  val == nullptr disables it.
+struct Finalize {
+  float* val;
+  int64_t* idx;
+  float* R_best;
+  int64_t idx_offset;
+  unsigned* counter;  // zero at kernel start (cleared with the keys), reset by the last CTA
+};
+
 struct Work {  // contiguous range of (pair, hypothesis) items of this CTA
   int64_t lo, hi, N;
 };
@@ -228,27 +252,47 @@ __device__ __forceinline__ float ld_vol<__nv_bfloat16>(const __nv_bfloat16* p) {
 
 // ---- one-time per CTA: W1/W2 (fp32, global) -> fp16 UMMA B-operand layouts in shared memory ------------
 // conv1: 24 slices j = (view, kk), each [chalf][ngroup][n%8][c%8]; conv2: [kc][ngroup][8][8] behind them.
-// Also leaves the largest L1 norm of a W1 row in *l1max_bits (bounds |conv1 output| / max|V|; a positive
-// float's bit pattern orders like the float).  Every CTA does this itself (48 KB of L2 reads) so that the
-// scoring kernel depends on no preparation kernel.
-__device__ __forceinline__ void pack_weights(unsigned char* wsm, uint32_t* l1max_bits, const float* __restrict__ W1,
-                                             const float* __restrict__ W2, int warp, int lane) {
+// Every CTA does this itself (52 KB of L2 reads) so that the scoring kernel depends on no preparation
+// kernel.  It runs on the 5 non-gather warps (MMA + epilogue, tid = 0..159) while the gather warps already
+// stage the first volume and resample the first tile; the MMA warp is released by named barrier 3.
+constexpr int kPackThreads = kThreadsTC - kGatherWarps * 32;  // 160
+__device__ __forceinline__ void pack_weights(unsigned char* wsm, const float* __restrict__ W1,
+                                             const float* __restrict__ W2, int tid) {
   __half* w1h = reinterpret_cast<__half*>(wsm);
-  for (int n = warp; n < kO; n += kThreadsTC / 32) {
-    float l1 = 0.0f;
-    for (int k = lane; k < kK; k += 32) {
-      const float w = __ldg(W1 + n * kK + k);
-      l1 += fabsf(w);
-      const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7, j = view * 8 + kk;
-      w1h[j * 512 + (c >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (c & 7)] = __float2half_rn(w);
-    }
-    l1 = warp_sum(l1);
-    if (lane == 0) atomicMax(l1max_bits, __float_as_uint(l1));
+  constexpr int kV4 = kO * kK / 4;  // float4 = 4 consecutive kk of one (row, view, channel)
+#pragma unroll 10
+  for (int i = tid; i < kV4; i += kPackThreads) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(W1) + i);
+    const int n = i / (kK / 4), k = (i - n * (kK / 4)) * 4;
+    const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7;
+    __half* dst = w1h + (view * 8 + kk) * 512 + (c >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (c & 7);
+    dst[0] = __float2half_rn(w4.x); dst[512] = __float2half_rn(w4.y);
+    dst[1024] = __float2half_rn(w4.z); dst[1536] = __float2half_rn(w4.w);
   }
-  for (int i = threadIdx.x; i < kO * kO; i += kThreadsTC) {
+  for (int i = tid; i < kO * kO; i += kPackThreads) {
     const int n = i / kO, k = i % kO;
     w1h[kW1Bytes / 2 + (k >> 3) * 256 + (n >> 3) * 64 + (n & 7) * 8 + (k & 7)] = __float2half_rn(__ldg(W2 + i));
   }
+}
+
+// Largest L1 norm of a W1 row (bounds |conv1 output| / max|V| for the pair scale), by the 8 gather warps:
+// warp w sums rows 4w..4w+3 (48 coalesced loads per lane in flight, fixed summation order -> the same value
+// in every CTA) and folds them into *l1max_bits (a non-negative float's bit pattern orders like the float).
+__device__ __forceinline__ void w1_l1max(uint32_t* l1max_bits, const float* __restrict__ W1, int warp, int lane) {
+  float wv[4][12];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int j = 0; j < 12; ++j) wv[r][j] = __ldg(W1 + (4 * warp + r) * kK + lane + 32 * j);
+  float m = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float l1 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) l1 += fabsf(wv[r][j]);
+    m = fmaxf(m, warp_sum(l1));
+  }
+  if (lane == 0) atomicMax(l1max_bits, __float_as_uint(m));
 }
 
 // ---- per pair: stage the source volume, pre-scaled by the pair's power-of-two scale -------------------
@@ -258,10 +302,9 @@ __device__ __forceinline__ void pack_weights(unsigned char* wsm, uint32_t* l1max
 // the gather's layout: fp32 lines [halo voxel][16 ch], or for 16-bit "x-pair lines" (every voxel is tap 0 of
 // pair xh and tap 1 of pair xh-1).  Returns 1/s.
 template <typename T, bool K16>
-__device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* __restrict__ vg, float l1max,
-                                                   float* red, int gtid) {
+__device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* __restrict__ vg, uint32_t* l1max_bits,
+                                                   const float* __restrict__ W1, bool first, float* red, int gtid) {
   float val[32];
-  float mx = 0.0f;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     // fp32: task = gtid + 256*(i>>2) -> (voxel, 4-channel group jj), channel jj*4 + (i&3)
@@ -270,12 +313,17 @@ __device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* 
     const int v = task & 511, grp = task >> 9;
     const int ch = K16 ? grp * 8 + (i & 7) : grp * 4 + (i & 3);
     val[i] = ld_vol<T>(vg + ch * kVox + v);
-    mx = fmaxf(mx, fabsf(val[i]));
   }
+  // first pair of the CTA: the W1 row norms ride the same memory round trip as the volume
+  if (first) w1_l1max(l1max_bits, W1, gtid >> 5, gtid & 31);
+  float mx = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fabsf(val[i]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((gtid & 31) == 0) red[gtid >> 5] = mx;
   named_bar_sync(1, kGatherWarps * 32);
+  const float l1max = __uint_as_float(*l1max_bits);
   float m = red[0];
 #pragma unroll
   for (int w = 1; w < kGatherWarps; ++w) m = fmaxf(m, red[w]);
@@ -329,7 +377,8 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
                                               unsigned char* a2_smem, uint32_t tmem_a2, float* partial,
                                               const float* __restrict__ tgt_feat, const float* __restrict__ b2,
                                               const float* inv_ring, float* __restrict__ scores,
-                                              u64* __restrict__ best_keys, int64_t N) {
+                                              u64* __restrict__ best_keys, int64_t N, int B,
+                                              const float* __restrict__ R, int r_per_pair, const Finalize& fin) {
   const int slot = lane >> 4;            // which hypothesis of the tile
   const int pos = 16 * s + (lane & 15);  // position p*8+q of the folded plane
   const uint32_t row = 32 * s + lane;    // TMEM lane == row of the conv2 A operand
@@ -339,6 +388,7 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
   // the target features and the cleared arg-max keys come from the prologue grid; every other role of this
   // kernel is independent of it (no-op when the kernel was not launched programmatically dependent)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (s == 0 && lane == 0) AHV_TL(7);
   TileIter it(work);
   int cur_b = -1;
   float inv_s = 1.0f;
@@ -418,6 +468,7 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
       mbar_arrive(bar0 + (kA2Full + gb) * 8);
       mbar_arrive(bar0 + (kD1Empty + gb) * 8);
     }
+    if (s == 0 && lane == 0 && g == 0) AHV_TL(8);
     // ---- phase B of the previous tile ----
     if (g > 0) phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
     if (it.b != cur_b) {  // target features / scale of the tile just handed to conv2
@@ -430,7 +481,32 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
     ++g;
   }
   phase_b(g - 1, prev_b, prev_n0, prev_cnt, prev_inv);
+  if (s == 0 && lane == 0) AHV_TL(9);
   if (best_keys && key_b >= 0) atomicMax(best_keys + key_b, key_best);
+  if (best_keys && fin.val && s == 0) {
+    __syncwarp();
+    unsigned last = 0;
+    if (lane == 0) {
+      __threadfence();  // this CTA's keys before its ticket
+      last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {  // every other CTA has published its keys
+      __threadfence();
+      for (int b = lane; b < B; b += 32) {
+        const u64 key = __ldcg(best_keys + b);
+        const uint32_t n = key_index(key);
+        fin.val[b] = key_score(key);
+        fin.idx[b] = (int64_t)n + fin.idx_offset;
+        if (fin.R_best) {
+          const float* src = R + ((r_per_pair ? (size_t)b * N : 0) + (size_t)n) * 9;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) fin.R_best[b * 9 + e] = __ldg(src + e);
+        }
+      }
+      if (lane == 0) *fin.counter = 0u;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------
@@ -440,7 +516,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
                 const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
                 const float* __restrict__ base, const float* __restrict__ W1,
                 const float* __restrict__ W2, float* __restrict__ scores,
-                u64* __restrict__ best_keys, int B, int64_t N) {
+                u64* __restrict__ best_keys, int B, int64_t N, Finalize fin) {
   extern __shared__ __align__(128) unsigned char smem[];
   using M = Map<K16>;
   constexpr int kOffVol = M::off_vol, kOffW1 = M::off_w1, kOffW2 = M::off_w2, kOffA = M::off_a, kOffA2 = M::off_a2,
@@ -470,8 +546,6 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     reinterpret_cast<uint4*>(vol)[i] = make_uint4(0, 0, 0, 0);  // halo stays zero for the whole kernel
   if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
   if (threadIdx.x == 8) *l1max_bits = 0u;
-  __syncthreads();
-  pack_weights(smem + kOffW1, l1max_bits, W1, W2, warp, lane);
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
@@ -486,11 +560,15 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), 128);
   }
-  fence_proxy_async();  // weights were written through the generic proxy, UMMA reads through the async proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (warp >= kGatherWarps) {  // MMA + epilogue warps: weights -> fp16 operand layouts, then release the MMA warp
+    pack_weights(smem + kOffW1, W1, W2, threadIdx.x - kGatherWarps * 32);
+    fence_proxy_async();  // written through the generic proxy, UMMA reads through the async proxy
+    named_bar_sync(3, kPackThreads);
+  }
 
   if (warp < kGatherWarps) {
     // =========================== GATHER ===========================
@@ -531,7 +609,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);  // everyone is done reading the previous volume
         const T* vg = vol_src + (size_t)it.b * kC * kVox;
-        const float inv = stage_pair_volume<T, K16>(smem + kOffVol, vg, __uint_as_float(*l1max_bits), red, gtid);
+        const float inv = stage_pair_volume<T, K16>(smem + kOffVol, vg, l1max_bits, W1, cur_b < 0, red, gtid);
         if (gtid == 0) inv_ring[it.b & 7] = inv;
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
@@ -717,7 +795,7 @@ score_tc_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_fea
   } else {
     // =========================== EPILOGUE ===========================
     epilogue_role<false>(work, warp - kEpiWarp0, lane, tmem, bar0, smem + kOffA2, 0, partial, tgt_feat, b2, inv_ring,
-                         scores, best_keys, N);
+                         scores, best_keys, N, B, R, r_per_pair, fin);
   }
 
   // ---- teardown ----
@@ -774,7 +852,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
                    const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
                    const float* __restrict__ base, const float* __restrict__ W1,
                    const float* __restrict__ W2, float* __restrict__ scores,
-                   u64* __restrict__ best_keys, int B, int64_t N) {
+                   u64* __restrict__ best_keys, int B, int64_t N, Finalize fin) {
   extern __shared__ __align__(128) unsigned char smem[];
   using M = MapTS;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
@@ -786,6 +864,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     work.N = N;
   }
   if (work.lo >= work.hi) return;
+  if (threadIdx.x == 0) AHV_TL(0);
 
   float* vol = reinterpret_cast<float*>(smem + M::off_vol);
   const uint32_t s_base = smem_u32(smem);
@@ -801,8 +880,6 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     reinterpret_cast<uint4*>(vol)[i] = make_uint4(0, 0, 0, 0);  // halo stays zero for the whole kernel
   if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
   if (threadIdx.x == 8) *l1max_bits = 0u;
-  __syncthreads();
-  pack_weights(smem + M::off_w1, l1max_bits, W1, W2, warp, lane);
   if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
@@ -817,11 +894,17 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), M::tmem_cols);
   }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) AHV_TL(1);
+  if (warp >= kGatherWarps) {  // MMA + epilogue warps: weights -> fp16 operand layouts, then release the MMA warp
+    pack_weights(smem + M::off_w1, W1, W2, threadIdx.x - kGatherWarps * 32);
+    fence_proxy_async();  // written through the generic proxy, UMMA reads through the async proxy
+    named_bar_sync(3, kPackThreads);
+    if (threadIdx.x == 256) AHV_TL(5);
+  }
 
   if (warp < kGatherWarps) {
     // =========================== GATHER ===========================
@@ -859,6 +942,14 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       int fb; uint32_t fn; int fc;
       it.peek_tile(fb, fn, fc);
       fetch_R(fb, fn + (slot < fc ? slot : 0));
+      // first pair of this CTA: its volume (and the W1 row norms) ride the same memory round trip as the
+      // first rotations
+      cur_b = fb;
+      const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, vol_src + (size_t)fb * kC * kVox, l1max_bits, W1,
+                                                  true, red, gtid);
+      if (gtid == 0) inv_ring[fb & 7] = inv;
+      named_bar_sync(1, kGatherWarps * 32);
+      if (threadIdx.x == 0) AHV_TL(3);
 #pragma unroll
       for (int e = 0; e < 9; ++e) Rn[e] *= opaque_one(r_per_pair);
     }
@@ -955,7 +1046,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);
         const T* vg = vol_src + (size_t)it.b * kC * kVox;
-        const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, vg, __uint_as_float(*l1max_bits), red, gtid);
+        const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, vg, l1max_bits, W1, false, red, gtid);
         if (gtid == 0) inv_ring[it.b & 7] = inv;
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
@@ -1056,6 +1147,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       tc_fence_before();    // TMEM stores -> tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar0 + (kFull + stage) * 8);
+      if (threadIdx.x == 0 && g == 0) AHV_TL(4);
       ++g;
     }
   } else if (warp == kMmaWarp) {
@@ -1098,6 +1190,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
         }
         umma_commit(bar0 + (kEmpty + stage) * 8);
         umma_commit(bar0 + (kD1Full + gb) * 8);
+        if (lane == 0 && g == 0) AHV_TL(6);
         if (g > 0) conv2(g - 1);
         ++g;
       }
@@ -1107,15 +1200,17 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
   } else {
     // =========================== EPILOGUE ===========================
     epilogue_role<true>(work, warp - kEpiWarp0, lane, tmem, bar0, nullptr, M::tmem_a2, partial, tgt_feat, b2, inv_ring,
-                        scores, best_keys, N);
+                        scores, best_keys, N, B, R, r_per_pair, fin);
   }
 
+  if (threadIdx.x == 0) AHV_TL(10);
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, M::tmem_cols);
   }
+  if (threadIdx.x == 0) AHV_TL(11);
 }
 
 // ---- prologue: target features forward_3d2d(vol_tgt[b]) (modules/model.py:191) in fp32, + arg-max key clear ----
@@ -1133,13 +1228,15 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
 constexpr int kTgtThreads = 128, kTgtCtasPerPair = 16;
 __global__ void __launch_bounds__(kTgtThreads, 4)
 tc_tgt_feat_kernel(const float* __restrict__ vol_tgt, const float* __restrict__ W1, const float* __restrict__ W2,
-                   const float* __restrict__ b2, u64* __restrict__ best_keys, float* __restrict__ tgt_feat, int B) {
+                   const float* __restrict__ b2, u64* __restrict__ best_keys, unsigned* __restrict__ done_counter,
+                   float* __restrict__ tgt_feat, int B) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the scoring kernel start its setup now
   __shared__ float A[4][kK];
   __shared__ float h1[4][kO + 1];
   const int p = blockIdx.x >> 1, q0 = (blockIdx.x & 1) * 4, b = blockIdx.y;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   if (best_keys && blockIdx.x == 0 && t == 0) best_keys[b] = 0ull;
+  if (done_counter && blockIdx.x == 0 && b == 0 && t == 32) *done_counter = 0u;
   const float* V = vol_tgt + (size_t)b * kC * kVox;
   float wr[2][12];
 #pragma unroll
@@ -1190,28 +1287,11 @@ tc_tgt_feat_kernel(const float* __restrict__ vol_tgt, const float* __restrict__ 
   }
 }
 
-// decode the arg-max keys: (score, global index, sampled_R[pred_index]) per pair (modules/model.py:195-196)
-__global__ void __launch_bounds__(128)
-tc_finalize_kernel(const u64* __restrict__ best_keys, const float* __restrict__ R, int r_per_pair,
-                   int64_t idx_offset, int B, int64_t N, float* __restrict__ val,
-                   int64_t* __restrict__ idx, float* __restrict__ R_best) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const u64 key = best_keys[b];
-  const uint32_t n = key_index(key);
-  val[b] = key_score(key);
-  idx[b] = (int64_t)n + idx_offset;
-  if (R_best) {
-    const float* src = R + ((r_per_pair ? (size_t)b * N : 0) + (size_t)n) * 9;
-#pragma unroll
-    for (int e = 0; e < 9; ++e) R_best[b * 9 + e] = src[e];
-  }
-}
-
 struct Scratch {  // carve-up of the tensor-core path's workspace
   __half* w_packed;
   float2* pair_scale;
   u64* best_keys;
+  unsigned* counter;
   float* tgt_feat;
 };
 __host__ inline size_t scratch_bytes(int B) {
@@ -1227,6 +1307,7 @@ __host__ inline Scratch carve(void* ws, int B) {
   sc.pair_scale = reinterpret_cast<float2*>(p);
   p += (size_t)B * sizeof(float2);
   sc.best_keys = reinterpret_cast<u64*>(p);
+  sc.counter = reinterpret_cast<unsigned*>(sc.best_keys + B);  // inside the 256-byte tail of scratch_bytes
   return sc;
 }
 
@@ -1253,7 +1334,7 @@ static int launch_pdl(KernelT kernel, unsigned grid, size_t smem, cudaStream_t s
 template <typename T, bool K16>
 int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_in, const float* R,
                  int r_per_pair, const float* W1, const float* W2, const float* b2, const float* base,
-                 float* scores, bool want_argmax, int B, int64_t N, const Scratch& sc, cudaStream_t s) {
+                 float* scores, bool want_argmax, int B, int64_t N, const Scratch& sc, Finalize fin, cudaStream_t s) {
   int dev = 0, sms = 0;
   AHV_CUDA_OK(cudaGetDevice(&dev));
   AHV_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1262,8 +1343,9 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
     const int st = launch_tgt_feat(vol_tgt, W1, W2, b2, want_argmax ? sc.best_keys : nullptr, sc.tgt_feat, B, s);
     if (st != AHV_OK) return st;
   } else if (want_argmax) {
-    AHV_CUDA_OK(cudaMemsetAsync(sc.best_keys, 0, (size_t)B * sizeof(u64), s));
+    AHV_CUDA_OK(cudaMemsetAsync(sc.best_keys, 0, (size_t)B * sizeof(u64) + sizeof(unsigned), s));
   }
+  fin.counter = sc.counter;
   // a tile is two hypotheses: do not spread tiny problems over more CTAs than tiles
   const int64_t tiles = ((int64_t)B * N + 1) / 2;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
@@ -1275,12 +1357,12 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   if (use_ts) {
     AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
     return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue && use_pdl, vol_src, tgt, R, r_per_pair,
-                      b2, base, W1, W2, scores, keys, B, N);
+                      b2, base, W1, W2, scores, keys, B, N, fin);
   }
   constexpr int kSmemBytes = Map<K16>::smem_bytes;
   AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   return launch_pdl(score_tc_kernel<T, K16>, grid, kSmemBytes, s, prologue && use_pdl, vol_src, tgt, R, r_per_pair, b2, base,
-                    W1, W2, scores, keys, B, N);
+                    W1, W2, scores, keys, B, N, fin);
 }
 
 }  // namespace tc
@@ -1289,11 +1371,16 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
 // behind ahv_forward_3d2d for per-pair sizes
 int launch_tgt_feat(const float* vol_tgt, const float* W1, const float* W2, const float* b2,
                     unsigned long long* clear_keys, float* feat, int B, cudaStream_t s) {
+  // same shared-memory carve-out as the scoring kernel: an SM cannot change its L1/shared split while a CTA
+  // is resident, so with the default (small) carve-out the dependent scoring CTAs could not join these SMs
+  AHV_CUDA_OK(cudaFuncSetAttribute(tc::tc_tgt_feat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
   for (int b0 = 0; b0 < B; b0 += 65535) {  // gridDim.y limit
     const int nb = B - b0 < 65535 ? B - b0 : 65535;
-    tc::tc_tgt_feat_kernel<<<dim3(tc::kTgtCtasPerPair, nb), tc::kTgtThreads, 0, s>>>(vol_tgt + (size_t)b0 * kC * kVox, W1, W2, b2,
-                                                      clear_keys ? clear_keys + b0 : nullptr,
-                                                      feat + (size_t)b0 * kO * kP, nb);
+    tc::tc_tgt_feat_kernel<<<dim3(tc::kTgtCtasPerPair, nb), tc::kTgtThreads, 0, s>>>(
+        vol_tgt + (size_t)b0 * kC * kVox, W1, W2, b2, clear_keys ? clear_keys + b0 : nullptr,
+        clear_keys && b0 == 0 ? reinterpret_cast<unsigned*>(clear_keys + B) : nullptr,  // Scratch::counter
+        feat + (size_t)b0 * kO * kP, nb);
     AHV_CUDA_OK(cudaGetLastError());
   }
   return AHV_OK;
@@ -1311,15 +1398,15 @@ float* scratch_tgt_feat(void* ws, int B) { return tc::carve(ws, B).tgt_feat; }
 static int dispatch(const void* vol_src, int vol_dtype, bool f16_gather, const float* vol_tgt,
                     const float* tgt_feat, const float* R, int r_per_pair, const float* W1, const float* W2,
                     const float* b2, const float* base, float* scores, bool want_argmax, int B, int64_t N,
-                    const tc::Scratch& sc, cudaStream_t s) {
+                    const tc::Scratch& sc, const tc::Finalize& fin, cudaStream_t s) {
   if (vol_dtype == AHV_VOL_BF16)
     return tc::launch_typed<__nv_bfloat16, true>((const __nv_bfloat16*)vol_src, vol_tgt, tgt_feat, R, r_per_pair, W1,
-                                                 W2, b2, base, scores, want_argmax, B, N, sc, s);
+                                                 W2, b2, base, scores, want_argmax, B, N, sc, fin, s);
   if (f16_gather)
     return tc::launch_typed<float, true>((const float*)vol_src, vol_tgt, tgt_feat, R, r_per_pair, W1, W2, b2, base,
-                                         scores, want_argmax, B, N, sc, s);
+                                         scores, want_argmax, B, N, sc, fin, s);
   return tc::launch_typed<float, false>((const float*)vol_src, vol_tgt, tgt_feat, R, r_per_pair, W1, W2, b2, base,
-                                        scores, want_argmax, B, N, sc, s);
+                                        scores, want_argmax, B, N, sc, fin, s);
 }
 
 // scores only (target features supplied by the caller)
@@ -1330,11 +1417,11 @@ int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, c
   if ((int64_t)B * N == 0) return AHV_OK;
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   return dispatch(vol_src, vol_dtype, f16_gather, nullptr, tgt_feat, R, r_per_pair, W1, W2, b2, base, scores, false,
-                  B, N, tc::carve(ws, B), s);
+                  B, N, tc::carve(ws, B), tc::Finalize{nullptr, nullptr, nullptr, 0, nullptr}, s);
 }
 
-// the whole verification step with arg-max selection in three launches:
-// prologue (weights, scales, target features) -> fused scoring + arg-max -> finalize
+// the whole verification step with arg-max selection in two launches: prologue (target features, key
+// clear) -> fused scoring + arg-max, whose last CTA also decodes the winners (no finalize launch)
 int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R,
                             int r_per_pair, const float* W1, const float* W2, const float* b2,
                             const float* base, float* scores, float* best_val, int64_t* best_idx,
@@ -1343,13 +1430,14 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
   if ((int64_t)B * N == 0) return AHV_OK;
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   const tc::Scratch sc = tc::carve(ws, B);
-  int st = dispatch(vol_src, vol_dtype, f16_gather, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2, base, scores, true,
-                    B, N, sc, s);
-  if (st != AHV_OK) return st;
-  tc::tc_finalize_kernel<<<(B + 127) / 128, 128, 0, s>>>(sc.best_keys, R, r_per_pair, idx_offset, B, N, best_val,
-                                                         best_idx, R_best);
-  AHV_CUDA_OK(cudaGetLastError());
-  return AHV_OK;
+  return dispatch(vol_src, vol_dtype, f16_gather, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2, base, scores, true,
+                  B, N, sc, tc::Finalize{best_val, best_idx, R_best, idx_offset, nullptr}, s);
 }
 
 }  // namespace ahv
+
+#ifdef AHV_TIMELINE
+extern "C" AHV_API int ahv_diag_timeline(unsigned long long* host_out /*[160][16]*/) {
+  return cudaMemcpyFromSymbol(host_out, ahv::tc::g_timeline, sizeof(unsigned long long) * 160 * 16) == cudaSuccess ? AHV_OK : AHV_ECUDA;
+}
+#endif

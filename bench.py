@@ -210,12 +210,12 @@ def run_ours(args):
     launches = {"n": 0}
 
     def step():
-        if world == 1:   # ahv_verify: prologue + fused score/arg-max + finalize = 3 launches
+        if world == 1:   # ahv_verify: target-feature prologue + fused score/arg-max/selection = 2 launches
             r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=0, gather=True)
-            launches["n"] += 3
+            launches["n"] += 2
             return r.topk_val, r.topk_idx, r.R_best
         r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=shard_lo, gather=False)
-        launches["n"] += 3
+        launches["n"] += 2
         vals, idxs = ahv.dist.all_gather_topk(r.topk_val, r.topk_idx)
         val, idx = ahv.ops.topk_merge(vals, idxs)
         own = (idx >= shard_lo) & (idx < shard_lo + N)
