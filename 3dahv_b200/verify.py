@@ -79,7 +79,7 @@ class HypothesisVerifier:
         k = min(k, N)
         vs = vol_src if vol_src.dtype == torch.bfloat16 else vol_src.float()
         ws = self._workspace(B, N, k, dev)
-        if tgt_feat is None:   # one C call for the whole step (3 launches when k == 1)
+        if tgt_feat is None:   # one C call for the whole step (2 launches when k == 1)
             scores, val, idx, R_best = ops.verify(vs, vol_tgt.float(), R, W1, W2, b2, k=k, idx_offset=idx_offset,
                                                   math=self.math, return_scores=return_scores, gather=gather,
                                                   workspace=ws)

@@ -122,8 +122,9 @@ AHV_API int ahv_score(const void* vol_src, int vol_dtype, const float* tgt_feat,
 /* The whole verification step of modules/model.py:186-196 / test_co3d.py:137-146 in one call:
  * target features of vol_tgt [B,16,8,8,8] (fp32), fused scoring of every (pair, hypothesis),
  * selection and sampled_R[pred_index].  With AHV_MATH_TC and k==1 (the reference's torch.max) this
- * is three launches — prologue (weight packing, per-pair scale, target features, concurrently),
- * the fused scoring kernel with the arg-max folded into its epilogue, and a finalize kernel.
+ * is two launches — the target-feature prologue, and the fused scoring kernel (launched programmatically
+ * dependent on it; packs the weights and derives the per-pair scales itself) with the arg-max folded
+ * into its epilogue and the winners decoded by its last CTA.
  * scores [B,N] or NULL; topk_val/topk_idx [B,k]; R_best [B,k,3,3] or NULL. */
 AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
                        const float* W1, const float* W2, const float* b2, const float* base, float* scores,

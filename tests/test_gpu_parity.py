@@ -297,7 +297,7 @@ def test_refcompat_idiom(ahv, golden):
 
 @pytest.mark.parametrize("B,N", [(1, 1), (1, 3000), (3, 37), (32, 999)])
 def test_fused_verify_argmax_equals_generic_path(ahv, golden, B, N):
-    """ahv_verify with k=1 (arg-max folded into the scoring epilogue, 3 launches) must agree bit for
+    """ahv_verify with k=1 (arg-max and winner decode folded into the scoring kernel, 2 launches) must agree bit for
     bit with scores + separate top-k, including ties and the odd-tail tile."""
     dev = _dev()
     w = golden["weights"]
@@ -406,6 +406,44 @@ print("SS-OK", err, errb)
     env = dict(os.environ, AHV_TC_VARIANT="ss")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and "SS-OK" in out.stdout, out.stderr[-1500:]
+
+
+def test_pdl_off_is_bit_identical(ahv, golden, tmp_path):
+    """The scoring kernel is launched programmatically dependent on the target-feature prologue (only its
+    epilogue warps wait for that grid).  AHV_PDL=0 serialises the two launches; a fresh process with it
+    must reproduce this process's scores and winners bit for bit."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dev = _dev()
+    g = golden["shared_n3000_b3"]
+    T = lambda a: torch.from_numpy(a).to(dev)
+    v = ahv.HypothesisVerifier(*_weights(golden, dev))
+    here = v.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=1, return_scores=True)
+    out_path = str(tmp_path / "pdl0.npz")
+    code = r'''
+import importlib, os, sys, numpy as np, torch
+sys.path.insert(0, ROOT)
+ahv = importlib.import_module("3dahv_b200")
+dev = torch.device("cuda", 0)
+g = dict(np.load(os.path.join(ROOT, "tests/golden/shared_n3000_b3.npz"))); w = dict(np.load(os.path.join(ROOT, "tests/golden/weights.npz")))
+T = lambda a: torch.from_numpy(a).to(dev)
+v = ahv.HypothesisVerifier(T(w["W1"]), T(w["W2"]), T(w["b2"]))
+r = v.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=1, return_scores=True)
+r2 = v.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=1, return_scores=False)
+assert torch.equal(r.topk_idx, r2.topk_idx) and torch.equal(r.R_best, r2.R_best)
+np.savez(OUT, scores=r.scores.cpu().numpy(), idx=r.topk_idx.cpu().numpy(), val=r.topk_val.cpu().numpy())
+print("PDL0-OK")
+'''.replace("ROOT", repr(root)).replace("OUT", repr(out_path))
+    env = dict(os.environ, AHV_PDL="0")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and "PDL0-OK" in out.stdout, out.stderr[-1500:]
+    other = np.load(out_path)
+    assert np.array_equal(other["scores"], here.scores.cpu().numpy())
+    assert np.array_equal(other["idx"], here.topk_idx.cpu().numpy())
+    assert np.array_equal(other["val"], here.topk_val.cpu().numpy())
 
 
 def test_non_finite_inputs_do_not_hang_or_fault(ahv, golden):
