@@ -1172,15 +1172,17 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
         const uint32_t stage = g % kStages, use = g / kStages;
         mbar_wait(bar0 + (kFull + stage) * 8, use & 1);
         tc_fence_after();
+        // view x from TMEM, both hypotheses of the tile in one M=128 MMA per K slice (w=kk, c): A and D of a
+        // TS-form MMA share the lane, so row i of the M=128 tile is TMEM lane i - exactly the rows the
+        // two interleaved M=64 tiles below accumulate into.  Halves view x's W1 (B operand) reads.
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_f16_ts(tmem + gb * 32, tmem + M::tmem_ax + stage * 64 + kk * 8, smem_desc(w1s + kk * 1024, 512, 128), idesc2, kk);
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
           const uint32_t lane_off = (uint32_t)(16 * sl) << 16;
           const uint32_t d1 = tmem + lane_off + gb * 32;
-          const uint32_t axs = tmem + lane_off + M::tmem_ax + stage * 64;
           const uint32_t a = s_base + M::off_a + stage * M::tile_bytes + sl * M::yz_bytes;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // view x from TMEM: rows (d,h), K slice = (w=kk, c)
-            umma_f16_ts(d1, axs + kk * 8, smem_desc(w1s + kk * 1024, 512, 128), idesc1, kk);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view y: rows (d,w), K slice = (h=kk, c)
             umma_f16(d1, smem_desc(a + kk * M::yz_h, M::yz_ch, M::yz_d), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
