@@ -74,6 +74,20 @@ AHV_API int ahv_rotate_volume_backward(const float* grad_out, int vol_per_rotati
   return launch_rotate_volume_bwd(grad_out, vol_per_rotation != 0, R, base, grad_vol, n, (cudaStream_t)stream);
 }
 
+AHV_API int ahv_score_backward(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair,
+                               const float* W1, const float* W2, const float* b2, const float* base,
+                               const float* grad_scores, float* grad_vol, float* grad_tgt, float* grad_W1,
+                               float* grad_W2, float* grad_b2, int B, int64_t N, void* stream) {
+  if (B < 0 || N < 0 || N > 0x7fffffffLL) return AHV_EINVAL;
+  if ((int64_t)B * N > 0 && (!vol_src || !tgt_feat || !R || !W1 || !W2 || !b2 || !base || !grad_scores || !grad_vol ||
+                             !grad_tgt || !grad_W1 || !grad_W2 || !grad_b2))
+    return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_score_bwd(vol_src, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, grad_scores, grad_vol, grad_tgt,
+                          grad_W1, grad_W2, grad_b2, B, N, (cudaStream_t)stream);
+}
+
 AHV_API int ahv_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                      float* feat, int64_t m, void* stream) {
   if (m < 0 || (m > 0 && (!vol || !W1 || !W2 || !b2 || !feat))) return AHV_EINVAL;

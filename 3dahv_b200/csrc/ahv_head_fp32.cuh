@@ -71,6 +71,52 @@ __device__ __forceinline__ void load_plain_volume(Fp32Smem& sm, const T* __restr
   }
 }
 
+// ---- phase G: trilinear gather of one hypothesis into rotA / rotT ---------
+// 4 lanes per output voxel (4 channels each), 8 voxels per warp step.
+// kRecord: lane j==0 of every voxel also stores the voxel's tap (corner line, fractions) to taps[v] - the
+// backward kernel's adjoint gather re-uses them so that its weights are the forward's bit for bit.
+template <bool kRecord>
+__device__ __forceinline__ void gather_hypothesis(Fp32Smem& sm, const float* R, float4* taps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 3, q = lane >> 2;
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int s = it * 8 + warp;  // (d,h) slab
+    const int d = s >> 3, h = s & 7, w = q;
+    Tap t = make_tap(R, sm.base[w], sm.base[h], sm.base[d]);
+    if (kRecord && j == 0) taps[d * 64 + h * 8 + w] = make_float4(__int_as_float(t.line), t.fx, t.fy, t.fz);
+    // Two voxels share a 128-bit shared-memory phase (8 lanes).  Their x-taps
+    // sit in adjacent 64 B lines of opposite bank halves; issuing them in
+    // parity order makes every phase conflict-free.
+    const int swap = (t.line ^ q) & 1;
+    const float wx_first = swap ? t.fx : 1.0f - t.fx;
+    const float wx_second = swap ? 1.0f - t.fx : t.fx;
+    const float* p0 = sm.vol + (t.line + swap) * kC + j * 4;
+    const float* p1 = sm.vol + (t.line + 1 - swap) * kC + j * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float wyz = (dy ? t.fy : 1.0f - t.fy) * (dz ? t.fz : 1.0f - t.fz);
+        const int off = (dz * kHalo * kHalo + dy * kHalo) * kC;
+        const float4 a = *reinterpret_cast<const float4*>(p0 + off);
+        const float4 b = *reinterpret_cast<const float4*>(p1 + off);
+        const float wa = wyz * wx_first, wb = wyz * wx_second;
+        acc.x = fmaf(wa, a.x, acc.x); acc.y = fmaf(wa, a.y, acc.y);
+        acc.z = fmaf(wa, a.z, acc.z); acc.w = fmaf(wa, a.w, acc.w);
+        acc.x = fmaf(wb, b.x, acc.x); acc.y = fmaf(wb, b.y, acc.y);
+        acc.z = fmaf(wb, b.z, acc.z); acc.w = fmaf(wb, b.w, acc.w);
+      }
+    const int oa = d * kRotD + h * 8 + w, ot = d * kRotD + w * 8 + h;
+    const int c0 = j * 4;
+    sm.rotA[(c0 + 0) * kRotC + oa] = acc.x; sm.rotT[(c0 + 0) * kRotC + ot] = acc.x;
+    sm.rotA[(c0 + 1) * kRotC + oa] = acc.y; sm.rotT[(c0 + 1) * kRotC + ot] = acc.y;
+    sm.rotA[(c0 + 2) * kRotC + oa] = acc.z; sm.rotT[(c0 + 2) * kRotC + ot] = acc.z;
+    sm.rotA[(c0 + 3) * kRotC + oa] = acc.w; sm.rotT[(c0 + 3) * kRotC + ot] = acc.w;
+  }
+}
+
 // ---- phase C1: tri-plane conv 384->32 + ReLU -> h1s ------------------------
 // h1[o,p,q] = sum_{c,k} W1[o,c*8+k] V[c,p,q,k] + W1[o,128+c*8+k] V[c,p,k,q]
 //                     + W1[o,256+c*8+k] V[c,k,p,q]      (modules/modules.py:115-118)

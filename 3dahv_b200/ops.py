@@ -109,6 +109,31 @@ def rotate_volume_backward(grad_out: torch.Tensor, R: torch.Tensor, per_rotation
     return out
 
 
+def score_backward(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor,
+                   b2: torch.Tensor, grad_scores: torch.Tensor):
+    """Fused gradient of the verification scores (modules/model.py:53-56 under autograd): returns
+    (grad_vol_src [B,16,8,8,8], grad_tgt_feat [B,32,64], grad_W1 [32,384], grad_W2 [32,32], grad_b2 [32])."""
+    vs, tg, R, gs = _dev(vol_src, "vol_src"), _dev(tgt_feat, "tgt_feat"), _dev(R, "R"), _dev(grad_scores, "grad_scores")
+    W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
+    B = vs.shape[0]
+    per_pair = R.dim() == 4
+    N = R.shape[1] if per_pair else R.shape[0]
+    if tuple(vs.shape) != (B, 16, 8, 8, 8) or tuple(tg.shape) != (B, 32, 64) or tuple(gs.shape) != (B, N):
+        raise ValueError("vol_src [B,16,8,8,8], tgt_feat [B,32,64], grad_scores [B,N] expected")
+    if per_pair and R.shape[0] != B:
+        raise ValueError("per-pair rotations must be [B,N,3,3]")
+    dev = vs.device
+    z = lambda *shape: torch.zeros(*shape, device=dev, dtype=torch.float32)
+    g_vol, g_tgt, g_w1, g_w2, g_b2 = z(B, 16, 8, 8, 8), z(B, 32, 64), z(32, 384), z(32, 32), z(32)
+    base = base_coords(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ahv_score_backward(vs.data_ptr(), tg.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(),
+                                                 W2.data_ptr(), b2.data_ptr(), base.data_ptr(), gs.data_ptr(),
+                                                 g_vol.data_ptr(), g_tgt.data_ptr(), g_w1.data_ptr(), g_w2.data_ptr(),
+                                                 g_b2.data_ptr(), B, N, _stream(vs)), "ahv_score_backward")
+    return g_vol, g_tgt, g_w1, g_w2, g_b2
+
+
 def forward_3d2d(vol: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
     """Feature_Aligner.forward_3d2d (modules/modules.py:112-124): [m,16,8,8,8] -> [m,32,64]."""
     v = _dev(vol, "vol")

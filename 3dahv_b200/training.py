@@ -4,12 +4,14 @@ The reference trains with `infoNCE_loss` (modules/model.py:43-63): per-pair rota
 `[B,N,3,3]`, `rotate_volume` -> `forward_3d2d` -> similarity -> softmax over hypotheses with
 temperature 0.1, all under PyTorch autograd (≈420 KB of saved activations per hypothesis).
 
-Here the forward scores come from the fused CUDA kernel (nothing saved), and the backward pass
-recomputes chunk by chunk with bounded memory: the trilinear resampling and its adjoint are the
-library's own kernels (`ahv_rotate_volume`, `ahv_rotate_volume_backward`), the small verification
-head (two 1x1 convolutions, ReLU, L2 normalise) is differentiated by PyTorch on the recomputed
-chunk.  Gradients flow to the source volumes, the target volumes (through their features), W1, W2
-and b2 — i.e. to everything upstream of the hot path (`forward_2d3d`, the backbone).
+Here the forward scores come from the fused CUDA kernel (nothing saved), and the backward pass is ONE
+fused kernel as well (`ahv_score_backward`, csrc/ahv_score_bwd.cu): per (pair, hypothesis) it recomputes
+the forward in shared memory and pushes the upstream gradient back to the source volume (adjoint of the
+trilinear resampling as a gather), the target features, W1, W2 and b2.  Only the B target volumes go
+through PyTorch autograd (`head_torch`, negligible).  Gradients therefore flow to everything upstream of
+the hot path (`forward_2d3d`, the backbone).  `fused_backward=False` selects the earlier chunked
+recomputation (library `ahv_rotate_volume` / `ahv_rotate_volume_backward` + PyTorch head), kept as an
+independent cross-check.
 """
 from __future__ import annotations
 
@@ -60,20 +62,31 @@ class _VerifyScores(torch.autograd.Function):
     """scores[b,n] of modules/model.py:53-56; forward fused, backward chunked recomputation."""
 
     @staticmethod
-    def forward(ctx, vol_src, vol_tgt, R, W1, W2, b2, math, chunk):
+    def forward(ctx, vol_src, vol_tgt, R, W1, W2, b2, math, chunk, fused_backward):
         tgt = ops.forward_3d2d(vol_tgt.detach().float(), W1.detach(), W2.detach(), b2.detach())
         scores, _, _ = ops.score(vol_src.detach().float(), tgt, R, W1.detach(), W2.detach(), b2.detach(), k=0, math=math,
                                  return_scores=True)
-        ctx.save_for_backward(vol_src, vol_tgt, R, W1, W2, b2)
+        ctx.save_for_backward(vol_src, vol_tgt, R, W1, W2, b2, tgt)
         ctx.chunk = chunk
+        ctx.fused_backward = fused_backward
         return scores
 
     @staticmethod
     def backward(ctx, grad_scores):
-        vol_src, vol_tgt, R, W1, W2, b2 = ctx.saved_tensors
+        vol_src, vol_tgt, R, W1, W2, b2, tgt_saved = ctx.saved_tensors
         B = vol_src.shape[0]
         per_pair = R.dim() == 4
         N = R.shape[1] if per_pair else R.shape[0]
+        if ctx.fused_backward:
+            g_vs, g_tgt, g_w1, g_w2, g_b = ops.score_backward(vol_src.detach().float(), tgt_saved, R, W1.detach().float(),
+                                                              W2.detach().float(), b2.detach().float(),
+                                                              grad_scores.contiguous().float())
+            with torch.enable_grad():   # target side: B volumes through the differentiable head
+                vt = vol_tgt.detach().float().requires_grad_(True)
+                w1, w2, bb = (t.detach().float().requires_grad_(True) for t in (W1, W2, b2))
+                gt = torch.autograd.grad(head_torch(vt, w1, w2, bb), [vt, w1, w2, bb], grad_outputs=g_tgt)
+            return (g_vs, gt[0], None, (g_w1 + gt[1].reshape(32, 384)).reshape(W1.shape),
+                    (g_w2 + gt[2].reshape(32, 32)).reshape(W2.shape), g_b + gt[3], None, None, None)
         with torch.enable_grad():
             vs = vol_src.detach().float().requires_grad_(True)
             vt = vol_tgt.detach().float().requires_grad_(True)
@@ -97,12 +110,13 @@ class _VerifyScores(torch.autograd.Function):
             gt = torch.autograd.grad(tgt, [vt, w1, w2, bb], grad_outputs=g_tgt, allow_unused=True)
             g_vt = gt[0]
             g_w1, g_w2, g_b = g_w1 + gt[1], g_w2 + gt[2], g_b + gt[3]
-        return g_vs, g_vt, None, g_w1.reshape(W1.shape), g_w2.reshape(W2.shape), g_b, None, None
+        return g_vs, g_vt, None, g_w1.reshape(W1.shape), g_w2.reshape(W2.shape), g_b, None, None, None
 
 
-def verification_scores(vol_src, vol_tgt, R, W1, W2, b2, math: int = MATH_TC, chunk: int = 1024) -> torch.Tensor:
+def verification_scores(vol_src, vol_tgt, R, W1, W2, b2, math: int = MATH_TC, chunk: int = 1024,
+                        fused_backward: bool = True) -> torch.Tensor:
     """Differentiable pred_sim [B,N] (modules/model.py:53-56 / :193).  R [N,3,3] or [B,N,3,3]."""
-    return _VerifyScores.apply(vol_src, vol_tgt, R.contiguous(), W1, W2, b2, math, chunk)
+    return _VerifyScores.apply(vol_src, vol_tgt, R.contiguous(), W1, W2, b2, math, chunk, fused_backward)
 
 
 def infonce_loss(scores: torch.Tensor, sampled_R: torch.Tensor, gt_delta_R: torch.Tensor, acc_thr_deg: float,

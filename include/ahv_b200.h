@@ -92,6 +92,17 @@ AHV_API int ahv_rotate_volume(const float* vol, int vol_per_rotation, const floa
 AHV_API int ahv_rotate_volume_backward(const float* grad_out, int vol_per_rotation, const float* R,
                                        const float* base, float* grad_vol, int64_t n, void* stream);
 
+/* Gradient of the verification scores (training variant: the autograd path of modules/model.py:53-56 inside
+ * infoNCE_loss, :43-63) in one fused kernel: for every (pair b, hypothesis n) the forward is recomputed in
+ * shared memory and grad_scores[b,n] is pushed back to the source volume, the target features, W1, W2 and
+ * b2 (fp32).  vol_src [B,16,8,8,8], tgt_feat [B,32,64] = forward_3d2d(vol_tgt), R [N,3,3] or [B,N,3,3],
+ * grad_scores [B,N].  Gradients are ADDED into grad_vol [B,16,8,8,8], grad_tgt [B,32,64], grad_W1 [32,384],
+ * grad_W2 [32,32], grad_b2 [32] (caller zeroes them).  Nothing is materialised per hypothesis. */
+AHV_API int ahv_score_backward(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair,
+                               const float* W1, const float* W2, const float* b2, const float* base,
+                               const float* grad_scores, float* grad_vol, float* grad_tgt, float* grad_W1,
+                               float* grad_W2, float* grad_b2, int B, int64_t N, void* stream);
+
 /* Feature_Aligner.forward_3d2d (modules/modules.py:112-124): tri-plane fold,
  * conv1x1 384->32, ReLU, conv1x1 32->32 + bias, L2 normalise over channels.
  * vol [m,16,8,8,8] -> feat [m,32,64].  W1 [32,384], W2 [32,32], b2 [32]

@@ -23,8 +23,9 @@ def _cpu_reference(oracle, vs, vt, R, W1, W2, b2, grad_scores):
     return s.detach(), [t.grad for t in (vs, vt, W1, W2, b2)]
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("per_pair", [False, True])
-def test_score_gradients_match_autograd_of_the_oracle(ahv, golden, oracle, per_pair):
+def test_score_gradients_match_autograd_of_the_oracle(ahv, golden, oracle, per_pair, fused):
     dev = torch.device("cuda", 0)
     g, w = golden["shared_n3000_b3"], golden["weights"]
     T = torch.from_numpy
@@ -37,7 +38,7 @@ def test_score_gradients_match_autograd_of_the_oracle(ahv, golden, oracle, per_p
 
     leaves = [t.to(dev).requires_grad_(True) for t in (vs, vt, W1, W2, b2)]
     s = ahv.training.verification_scores(leaves[0], leaves[1], R.to(dev), leaves[2], leaves[3], leaves[4],
-                                         math=ahv.MATH_FP32, chunk=16)
+                                         math=ahv.MATH_FP32, chunk=16, fused_backward=fused)
     assert torch.allclose(s.detach().cpu().double(), ref_s, rtol=2e-5, atol=0)
     (s * gs.to(dev)).sum().backward()
     for name, leaf, ref in zip(("vol_src", "vol_tgt", "W1", "W2", "b2"), leaves, ref_g):
@@ -90,3 +91,33 @@ def test_infonce_loss_and_training_step_direction(ahv, golden):
             p -= 0.05 * p.grad / p.grad.norm().clamp_min(1e-12)
     new_loss, _ = loss_fn()
     assert new_loss.mean().item() < loss.mean().item()
+
+
+def test_fused_backward_edge_cases(ahv, golden, oracle):
+    """ahv_score_backward on the cases the scoring tests stress: a CTA range that crosses pair boundaries
+    (many pairs x few hypotheses), identity / axis-flip rotations (taps exactly on voxels, whole faces out
+    of bounds), a zero source volume (constant features), and a non-orthonormal matrix (full-scan adjoint)."""
+    dev = torch.device("cuda", 0)
+    w = golden["weights"]
+    T = torch.from_numpy
+    gen = torch.Generator().manual_seed(11)
+    B, N = 7, 5
+    vs = torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2
+    vt = torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2
+    vs[2] = 0.0
+    R = ahv.so3.sample_rotations(B * N, seed=5, device=dev).cpu().reshape(B, N, 3, 3).clone()
+    R[0, 0] = torch.eye(3)
+    R[0, 1] = torch.diag(torch.tensor([-1.0, -1.0, 1.0]))
+    R[1, 0] = torch.tensor([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    R[3, 2] = R[3, 2] * 0.8 + 0.05          # not a rotation: scaled and sheared
+    W1, W2, b2 = T(w["W1"]), T(w["W2"]), T(w["b2"])
+    gs = torch.randn(B, N, generator=gen)
+    ref_s, ref_g = _cpu_reference(oracle, vs, vt, R, W1, W2, b2, gs)
+    leaves = [t.to(dev).requires_grad_(True) for t in (vs, vt, W1, W2, b2)]
+    s = ahv.training.verification_scores(leaves[0], leaves[1], R.to(dev), leaves[2], leaves[3], leaves[4], math=ahv.MATH_FP32)
+    assert torch.allclose(s.detach().cpu().double(), ref_s, rtol=5e-5, atol=1e-6)
+    (s * gs.to(dev)).sum().backward()
+    for name, leaf, ref in zip(("vol_src", "vol_tgt", "W1", "W2", "b2"), leaves, ref_g):
+        got = leaf.grad.detach().cpu().double()
+        scale = ref.abs().max().item()
+        assert torch.allclose(got, ref, rtol=0, atol=2e-4 * scale), (name, (got - ref).abs().max().item(), scale)
