@@ -19,9 +19,10 @@
 // pair); they leave the CTA through global atomics (caller zero-initialises the outputs).
 //
 // The adjoint of the resampling is a GATHER, not a scatter (shared-memory atomics would cost ~130k cycles
-// per hypothesis): every thread owns two input voxels, inverts the rotation to find the <= 64 output
-// voxels whose 2x2x2 tap cube can contain them, and re-uses the taps the forward gather recorded, so the
-// weights are the forward's bit for bit.  A matrix that is not a rotation falls back to scanning all 512.
+// per hypothesis): every thread owns two input voxels, pulls them back through R^T, walks the 4 x 4 (d, h)
+// columns around that point, intersects on each column the three |i_a - v_a| < 1 intervals in w, and for
+// the few candidates left re-uses the taps the forward gather recorded, so the weights are the forward's
+// bit for bit.  A matrix that is not a rotation falls back to scanning all 512 output voxels.
 #include "ahv_head_fp32.cuh"
 
 namespace ahv {
@@ -284,7 +285,12 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
           const float ox = unnorm(Rr[0] * gx + Rr[3] * gy + Rr[6] * gz);
           const float oy = unnorm(Rr[1] * gx + Rr[4] * gy + Rr[7] * gz);
           const float oz = unnorm(Rr[2] * gx + Rr[5] * gy + Rr[8] * gz);
-          const int w0 = (int)floorf(ox) - 1, h0 = (int)floorf(oy) - 1, d0 = (int)floorf(oz) - 1;
+          (void)ox;
+          const int h0 = (int)floorf(oy) - 1, d0 = (int)floorf(oz) - 1;
+          // In index space the sample point of output voxel o' is i = R (o' - 3.5) + 3.5, and o' touches this
+          // voxel iff |i_a - v_a| < 1 on all three axes.  Along a (d, h) column that is three intervals in w:
+          // intersect them (with a margin; tap_weight() makes the exact decision) instead of testing 4 values.
+          const float vx = (float)x, vy = (float)y, vz = (float)z;
 #pragma unroll 1
           for (int dd = 0; dd < 4; ++dd) {
             const int d = d0 + dd;
@@ -293,11 +299,23 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
             for (int hh = 0; hh < 4; ++hh) {
               const int h = h0 + hh;
               if ((unsigned)h > 7u) continue;
+              const float uh = (float)h - 3.5f, ud = (float)d - 3.5f;
+              float ulo = -3.5f, uhi = 3.5f;  // u = w - 3.5
 #pragma unroll
-              for (int ww = 0; ww < 4; ++ww) {
-                const int w = w0 + ww;
-                if ((unsigned)w <= 7u) visit(d * 64 + h * 8 + w);
+              for (int a = 0; a < 3; ++a) {
+                const float ca = fmaf(Rr[3 * a + 1], uh, fmaf(Rr[3 * a + 2], ud, 3.5f - (a == 0 ? vx : (a == 1 ? vy : vz))));
+                const float r = Rr[3 * a];
+                if (fabsf(r) > 1e-6f) {
+                  const float ir = 1.0f / r;
+                  const float e0 = (-1.0f - ca) * ir, e1 = (1.0f - ca) * ir;
+                  ulo = fmaxf(ulo, fminf(e0, e1));
+                  uhi = fminf(uhi, fmaxf(e0, e1));
+                } else if (fabsf(ca) >= 1.001f) {
+                  uhi = -10.0f;  // the whole column misses on this axis
+                }
               }
+              const int wlo = max(0, (int)ceilf(ulo + 3.5f - 1e-3f)), whi = min(7, (int)floorf(uhi + 3.5f + 1e-3f));
+              for (int w = wlo; w <= whi; ++w) visit(d * 64 + h * 8 + w);
             }
           }
         } else {
