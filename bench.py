@@ -161,7 +161,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"CO3D config 2 shape (B={PAIRS} pairs x {HYPS} hypotheses, fp32), CPU sample {sp}x{sh} per step"},
+            # same workload as the product arm; each timed step scores a bounded sample of it on the host cores
+            "config": {"workload": (f"CO3D config 2 (BASELINE.json configs[1]): B={PAIRS} pairs x N={HYPS} hypotheses per GPU, "
+                                    f"fp32 volumes, shared rotation set, top-1; N>1 = weak scaling over hypothesis shards "
+                                    f"+ NCCL all-gather of top-k"), "pairs": PAIRS, "hypotheses_per_gpu": HYPS,
+                       "math": "reference ATen calls on the host CPU", "sample_per_step": f"{sp} pairs x {sh} hypotheses"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
