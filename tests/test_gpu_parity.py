@@ -562,3 +562,49 @@ def test_bitwise_determinism_and_soak(ahv, golden):
         rel = ((got.scores - ref.scores).abs() / ref.scores.abs().clamp_min(1e-6)).max().item()
         assert rel <= 2e-3, (it, b, n, per_pair, src.dtype, rel)
         assert torch.equal(got.topk_idx[:, 0], got.scores.argmax(1))
+
+
+def test_concurrent_streams_and_threads(ahv, golden):
+    """the library is re-entrant and stream-ordered.  Four Python threads, each on its own CUDA
+    stream with its own inputs, run fused verification steps concurrently (programmatically dependent
+    launches, last-CTA winner decode and per-call workspaces all interleave on the device); every result must
+    equal the serial one bit for bit."""
+    import threading
+
+    dev = _dev()
+    w = _weights(golden, dev)
+    gen = torch.Generator().manual_seed(77)
+    jobs = []
+    for i, (B, N) in enumerate([(1, 3000), (5, 777), (32, 500), (2, 4001)]):
+        vs = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+        vt = (torch.randn(B, 16, 8, 8, 8, generator=gen) * 1.1 - 0.2).to(dev)
+        R = ahv.so3.sample_rotations(N, seed=100 + i, device=dev)
+        jobs.append((vs, vt, R))
+    serial = [ahv.HypothesisVerifier(*w).score(vs, vt, R, k=1, return_scores=True) for vs, vt, R in jobs]
+    torch.cuda.synchronize()
+    results, errors = [None] * len(jobs), []
+
+    def worker(i):
+        try:
+            st = torch.cuda.Stream(device=dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            v = ahv.HypothesisVerifier(*w)
+            with torch.cuda.stream(st):
+                for _ in range(10):
+                    r = v.score(*jobs[i], k=1, return_scores=True)
+                    r2 = v.score(*jobs[i], k=1, return_scores=False)
+            st.synchronize()
+            results[i] = (r, r2)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (r, r2), ref in zip(results, serial):
+        assert torch.equal(r.scores, ref.scores)
+        assert torch.equal(r.topk_idx, ref.topk_idx) and torch.equal(r.topk_val, ref.topk_val)
+        assert torch.equal(r2.topk_idx, ref.topk_idx) and torch.equal(r2.R_best, ref.R_best)
