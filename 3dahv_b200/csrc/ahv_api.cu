@@ -1,5 +1,7 @@
 // extern "C" surface of lib3dahv_b200 (see include/ahv_b200.h for the contract
 // and the reference interface each entry replaces).
+#include <cstring>
+
 #include "ahv_common.cuh"
 
 using namespace ahv;
@@ -208,6 +210,62 @@ AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt,
   if (R_best)
     st = launch_gather_rotations(R, r_per_pair != 0, topk_idx, idx_offset, B, N, k, R_best, s);
   return st;
+}
+
+// ---- hypothesis set sharded over the GPUs of one node: winners exchanged through peer memory -------------
+AHV_API size_t ahv_peer_bytes(int B) { return B < 0 ? 0 : peer_exchange_bytes(B); }
+
+AHV_API int ahv_peer_alloc(size_t bytes, void** ptr) {
+  if (!ptr || bytes == 0) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  if (cudaMalloc(ptr, bytes) != cudaSuccess) return AHV_ECUDA;
+  if (cudaMemset(*ptr, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return AHV_ECUDA;
+  return AHV_OK;
+}
+
+AHV_API int ahv_peer_free(void* ptr) { return (!ptr || cudaFree(ptr) == cudaSuccess) ? AHV_OK : AHV_ECUDA; }
+
+AHV_API int ahv_peer_export(void* ptr, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr || !handle64) return AHV_EINVAL;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, ptr) != cudaSuccess) return AHV_ECUDA;
+  memcpy(handle64, &h, 64);
+  return AHV_OK;
+}
+
+AHV_API int ahv_peer_open(const unsigned char* handle64, void** ptr) {
+  if (!handle64 || !ptr) return AHV_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  if (cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return AHV_ECUDA;
+  return AHV_OK;
+}
+
+AHV_API int ahv_peer_close(void* ptr) { return (!ptr || cudaIpcCloseMemHandle(ptr) == cudaSuccess) ? AHV_OK : AHV_ECUDA; }
+
+AHV_API int ahv_verify_sharded(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
+                               const float* W1, const float* W2, const float* b2, const float* base, float* best_val,
+                               int64_t* best_idx, float* R_best, int64_t idx_offset, int B, int64_t N, int math_mode,
+                               void* workspace, size_t workspace_bytes, int rank, int world, void* const* peers,
+                               void* stream) {
+  if (B < 1 || N < 1 || N > 0x7fffffffLL || world < 1 || world > 8 || rank < 0 || rank >= world) return AHV_EINVAL;
+  if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
+  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_TC_F16GATHER) return AHV_ENOTSUP;  // the fused exchange lives in the tensor-core kernel
+  if (!vol_src || !vol_tgt || !R || !W1 || !W2 || !b2 || !base || !best_val || !best_idx || (world > 1 && !peers))
+    return AHV_EINVAL;
+  if (!aligned16(vol_src) || !aligned16(vol_tgt) || !aligned16(R) || !aligned16(W1) || !aligned16(W2) ||
+      !aligned16(workspace))
+    return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  if (!workspace || workspace_bytes < ahv_workspace_bytes(B, N, 1)) return AHV_EWORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const size_t off_tc = align_up((size_t)B * (size_t)N * sizeof(float), 256) + align_up(topk_workspace_bytes(B, N, 1), 256);
+  return launch_verify_tc_argmax(vol_src, vol_dtype, vol_tgt, R, r_per_pair != 0, W1, W2, b2, base, nullptr, best_val,
+                                 best_idx, R_best, idx_offset, B, N, ws + off_tc, workspace_bytes - off_tc,
+                                 (cudaStream_t)stream, math_mode == AHV_MATH_TC_F16GATHER, rank, world, peers);
 }
 
 AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_host, const float* R_host,

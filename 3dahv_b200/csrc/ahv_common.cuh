@@ -111,7 +111,8 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
                             int r_per_pair, const float* W1, const float* W2, const float* b2,
                             const float* base, float* scores, float* best_val, int64_t* best_idx,
                             float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
-                            cudaStream_t s, bool f16_gather);
+                            cudaStream_t s, bool f16_gather, int rank = 0, int world = 1, void* const* peers = nullptr);
+size_t peer_exchange_bytes(int B);  // exchange buffer of the sharded step (ahv_peer_alloc)
 int launch_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* val,
                 int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t topk_workspace_bytes(int B, int64_t N, int k);

@@ -259,13 +259,25 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
                             int r_per_pair, const float* W1, const float* W2, const float* b2,
                             const float* base, float* scores, float* best_val, int64_t* best_idx,
                             float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
-                            cudaStream_t s, bool f16_gather) {
-  if ((int64_t)B * N == 0) return AHV_OK;
+                            cudaStream_t s, bool f16_gather, int rank, int world, void* const* peers) {
+  if ((int64_t)B * N == 0) return world > 1 ? AHV_EINVAL : AHV_OK;  // a sharded step needs every rank in the exchange
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   const tc::Scratch sc = tc::carve(ws, B);
+  tc::Finalize fin{best_val, best_idx, R_best, idx_offset, nullptr};
+  if (world > 1) {
+    if (world > tc::kMaxPeers || rank < 0 || rank >= world || !peers) return AHV_EINVAL;
+    fin.rank = rank;
+    fin.world = world;
+    for (int r = 0; r < world; ++r) {
+      if (!peers[r]) return AHV_EINVAL;
+      fin.peers[r] = static_cast<unsigned char*>(peers[r]);
+    }
+  }
   return dispatch(vol_src, vol_dtype, f16_gather, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2, base, scores, true,
-                  B, N, sc, tc::Finalize{best_val, best_idx, R_best, idx_offset, nullptr}, s);
+                  B, N, sc, fin, s);
 }
+
+size_t peer_exchange_bytes(int B) { return tc::peer_entry_off(2, 0, B, 0); }
 
 }  // namespace ahv
 

@@ -27,6 +27,7 @@ constexpr int kEpiWarp0 = 8;
 constexpr int kMmaWarp = 12;
 constexpr int kThreadsTC = 13 * 32;
 constexpr int kStages = 3;
+constexpr int kMaxPeers = 8;  // GPUs of one NVSwitch node
 
 // ---- shared memory map (bytes) ----
 constexpr int kW1Bytes = 24 * 1024;  // 24 MMA slices x [2 chalf][4 ngroup][8][8] fp16
@@ -49,7 +50,99 @@ struct Finalize {
   float* R_best;
   int64_t idx_offset;
   unsigned* counter;  // zero at kernel start (cleared with the keys), reset by the last CTA
+  // hypothesis set sharded over `world` GPUs: the winners are exchanged through peer memory
+  // by this kernel itself (no NCCL call, no merge kernel); peers[r] = rank r's exchange buffer, mapped here
+  int rank, world;
+  unsigned char* peers[kMaxPeers];
 };
+
+// ---- peer exchange buffer (one per rank, cudaMalloc'ed by ahv_peer_alloc, IPC-mapped into every peer) ----
+//   [0,256)    header: uint32 seq (number of exchanges this rank has completed), uint32 err
+//   [256,512)  flags[2 parity][8 ranks] uint32: flags[par][r] == s  <=>  rank r's entries of exchange s are here
+//   [512,...)  entries[2 parity][8 ranks][B] x 64 B: {int64 global index, float score, float R[9], pad}
+// Exchange s uses parity s & 1.  A rank can only finish exchange s+1 after every peer has sent s+1, i.e. after
+// every peer is done reading exchange s, so two parities suffice; sequence numbers make the flags
+// self-cleaning (CUDA-graph replay needs no host-side reset).
+constexpr int kPeerFlagsOff = 256, kPeerEntriesOff = 512, kPeerEntryBytes = 64;
+__host__ __device__ inline size_t peer_entry_off(int par, int r, int B, int b) {
+  return (size_t)kPeerEntriesOff + (((size_t)par * kMaxPeers + r) * B + b) * kPeerEntryBytes;
+}
+__device__ __forceinline__ uint32_t ordered_bits(float score) {  // same order as make_key()
+  uint32_t u = __float_as_uint(score + 0.0f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Last CTA of rank `rank`: publish this shard's winners to every peer, wait for theirs, merge
+// (higher score wins, ties -> lowest global index, like torch.max on the unsharded set; every rank computes
+// the same result).  One warp.
+__device__ __forceinline__ void peer_exchange_and_merge(const Finalize& fin, const u64* best_keys, const float* R,
+                                                        int r_per_pair, int64_t N, int B, int lane) {
+  unsigned char* mine = fin.peers[fin.rank];
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(mine);
+  const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(hdr) + 1u;
+  const int par = (int)(seq & 1u);
+  for (int b = lane; b < B; b += 32) {
+    const u64 key = __ldcg(best_keys + b);
+    const uint32_t n = key_index(key);
+    const int64_t gidx = (int64_t)n + fin.idx_offset;
+    const float* src = R + ((r_per_pair ? (size_t)b * N : 0) + (size_t)n) * 9;
+    float r9[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) r9[e] = __ldg(src + e);
+    const uint4 q0 = make_uint4((uint32_t)gidx, (uint32_t)((u64)gidx >> 32), __float_as_uint(key_score(key)), __float_as_uint(r9[0]));
+    const uint4 q1 = make_uint4(__float_as_uint(r9[1]), __float_as_uint(r9[2]), __float_as_uint(r9[3]), __float_as_uint(r9[4]));
+    const uint4 q2 = make_uint4(__float_as_uint(r9[5]), __float_as_uint(r9[6]), __float_as_uint(r9[7]), __float_as_uint(r9[8]));
+    for (int p = 0; p < fin.world; ++p) {  // NVLink peer stores (p == rank: local)
+      uint4* dst = reinterpret_cast<uint4*>(fin.peers[p] + peer_entry_off(par, fin.rank, B, b));
+      dst[0] = q0; dst[1] = q1; dst[2] = q2;
+    }
+  }
+  __threadfence_system();  // entries before the flag, system scope
+  __syncwarp();
+  if (lane < fin.world) {
+    volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(fin.peers[lane] + kPeerFlagsOff) + par * kMaxPeers + fin.rank;
+    *flag = seq;
+  }
+  bool ok = true;
+  if (lane < fin.world) {
+    const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(mine + kPeerFlagsOff) + par * kMaxPeers + lane;
+    const long long t0 = clock64();
+    while (*flag != seq) {
+      if (clock64() - t0 > 4000000000LL) { ok = false; break; }  // ~2 s: a peer died; fail instead of hanging the GPU
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system();
+  for (int b = lane; b < B; b += 32) {
+    float bv = 0.0f;
+    uint32_t bo = 0;
+    int64_t bi = -1;
+    uint4 bq0 = make_uint4(0, 0, 0, 0), bq1 = bq0, bq2 = bq0;
+    for (int r = 0; r < fin.world; ++r) {
+      const uint4* e = reinterpret_cast<const uint4*>(mine + peer_entry_off(par, r, B, b));
+      const uint4 q0 = __ldcv(e);
+      const int64_t gi = (int64_t)(((u64)q0.y << 32) | q0.x);
+      const float v = __uint_as_float(q0.z);
+      const uint32_t o = ordered_bits(v);
+      if (bi < 0 || o > bo || (o == bo && gi < bi)) {
+        bo = o; bv = v; bi = gi; bq0 = q0; bq1 = __ldcv(e + 1); bq2 = __ldcv(e + 2);
+      }
+    }
+    fin.val[b] = ok ? bv : __int_as_float(0x7fc00000);
+    fin.idx[b] = ok ? bi : -1;
+    if (fin.R_best) {
+      float* o9 = fin.R_best + b * 9;
+      o9[0] = __uint_as_float(bq0.w);
+      o9[1] = __uint_as_float(bq1.x); o9[2] = __uint_as_float(bq1.y); o9[3] = __uint_as_float(bq1.z); o9[4] = __uint_as_float(bq1.w);
+      o9[5] = __uint_as_float(bq2.x); o9[6] = __uint_as_float(bq2.y); o9[7] = __uint_as_float(bq2.z); o9[8] = __uint_as_float(bq2.w);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    hdr[0] = seq;
+    if (!ok) hdr[1] = 1u;
+  }
+}
 
 struct Work {  // contiguous range of (pair, hypothesis) items of this CTA
   int64_t lo, hi, N;
@@ -341,7 +434,11 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
       last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {  // every other CTA has published its keys
+    if (last && fin.world > 1) {
+      __threadfence();
+      peer_exchange_and_merge(fin, best_keys, R, r_per_pair, N, B, lane);
+      if (lane == 0) *fin.counter = 0u;
+    } else if (last) {  // every other CTA has published its keys
       __threadfence();
       for (int b = lane; b < B; b += 32) {
         const u64 key = __ldcg(best_keys + b);

@@ -44,14 +44,68 @@ def pad_topk(val: torch.Tensor, idx: torch.Tensor, k: int):
     return torch.cat([val, pv], 1), torch.cat([idx, pi], 1)
 
 
+class PeerExchange:
+    """Exchange buffers for the fused sharded step (`ahv_verify_sharded`): every rank allocates one buffer
+    (`ahv_peer_alloc`), sends its CUDA IPC handle to the peers (one all-gather of 64 bytes at set-up) and maps
+    theirs, after which the scoring kernels talk to each other through NVLink peer memory and a verification
+    step involves no NCCL call at all.  One instance per (process group, max pairs B)."""
+
+    def __init__(self, max_pairs: int, device, group=None):
+        import ctypes
+
+        from . import _lib
+
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("the peer exchange covers the GPUs of one node (<= 8)")
+        self.max_pairs = max_pairs
+        self.device = torch.device(device)
+        lib = _lib.lib()
+        self._lib = lib
+        own = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ahv_peer_alloc(lib.ahv_peer_bytes(max_pairs), ctypes.byref(own)), "ahv_peer_alloc")
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(lib.ahv_peer_export(own, handle), "ahv_peer_export")
+            mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.device)
+            every = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(every, mine, group=group)
+            self.own = own.value
+            self.ptrs, self._opened = [], []
+            for r, h in enumerate(every):
+                if r == self.rank:
+                    self.ptrs.append(self.own)
+                    continue
+                p = ctypes.c_void_p()
+                _lib.check(lib.ahv_peer_open(bytes(h.cpu().numpy().tobytes()), ctypes.byref(p)), "ahv_peer_open")
+                self.ptrs.append(p.value)
+                self._opened.append(p.value)
+        dist.barrier(group=group)
+
+    def close(self):
+        """Collective: every rank unmaps the peers' buffers before anyone frees its own."""
+        if getattr(self, "own", None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self._lib.ahv_peer_close(p)
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            self._lib.ahv_peer_free(self.own)
+        self.own, self.ptrs, self._opened = None, [], []
+
+
 class ShardedVerifier:
     """Wraps a HypothesisVerifier; `score` takes the FULL rotation set on every
     rank (36 B per hypothesis, replicated like the 40 KB/pair volumes) and
     scores only this rank's slice."""
 
-    def __init__(self, verifier, group=None, merge=None, score_fn=None):
+    def __init__(self, verifier, group=None, merge=None, score_fn=None, peer: "PeerExchange | None" = None):
         self.verifier = verifier
         self.group = group
+        self.peer = peer   # fused NVLink exchange for k == 1 (else: NCCL all-gather + merge kernel)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._merge = merge or ops.topk_merge
@@ -70,6 +124,17 @@ class ShardedVerifier:
         k = min(k, N)
         lo, hi = shard_bounds(N, self.rank, self.world)
         B = vol_src.shape[0]
+        last_lo, _ = shard_bounds(N, self.world - 1, self.world)
+        if (self.peer is not None and k == 1 and self.world > 1 and last_lo < N and B <= self.peer.max_pairs
+                and self._score_fn == self._score_local and self.verifier.math != ops.MATH_FP32):
+            # every rank has a non-empty slice: one fused call, the kernels exchange and merge the winners themselves
+            v = self.verifier
+            W1, W2, b2 = v._weights_on(vol_src.device)
+            Rs = (R[:, lo:hi] if per_pair else R[lo:hi]).contiguous()
+            vs = vol_src if vol_src.dtype == torch.bfloat16 else vol_src.float()
+            val, idx, Rb = ops.verify_sharded(vs, vol_tgt.float(), Rs, W1, W2, b2, lo, self.rank, self.world, self.peer.ptrs,
+                                              math=v.math, workspace=v._workspace(B, hi - lo, 1, vol_src.device))
+            return val[:, None], idx[:, None], Rb[:, None]
         if hi > lo:
             Rs = (R[:, lo:hi] if per_pair else R[lo:hi]).contiguous()
             val, idx = self._score_fn(vol_src, vol_tgt, Rs, min(k, hi - lo), lo)

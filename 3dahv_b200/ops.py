@@ -239,6 +239,37 @@ def verify(vol_src, vol_tgt, R, W1, W2, b2, k: int = 1, idx_offset: int = 0, mat
     return scores, val, idx, Rb
 
 
+def verify_sharded(vol_src, vol_tgt, R, W1, W2, b2, idx_offset: int, rank: int, world: int, peer_ptrs, math: int = MATH_TC,
+                   workspace: torch.Tensor | None = None):
+    """ahv_verify_sharded: k == 1 on this rank's slice `R` of the rotation set; the scoring kernel exchanges the
+    winners with the peers' kernels through NVLink peer memory and merges.  Returns (best_val [B], best_idx [B]
+    global, R_best [B,3,3]) over the whole set, identical on every rank."""
+    import ctypes
+
+    vs = _dev(vol_src, "vol_src", vol_src.dtype if vol_src.dtype == torch.bfloat16 else torch.float32)
+    vt, R = _dev(vol_tgt, "vol_tgt"), _dev(R, "R")
+    W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
+    B = vs.shape[0]
+    per_pair = R.dim() == 4
+    N = R.shape[1] if per_pair else R.shape[0]
+    dev = vs.device
+    val = torch.empty(B, device=dev, dtype=torch.float32)
+    idx = torch.empty(B, device=dev, dtype=torch.int64)
+    Rb = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
+    need = workspace_bytes(B, N, 1)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    base = base_coords(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ahv_verify_sharded(
+            vs.data_ptr(), VOL_BF16 if vs.dtype == torch.bfloat16 else VOL_F32, vt.data_ptr(), R.data_ptr(), int(per_pair),
+            W1.data_ptr(), W2.data_ptr(), b2.data_ptr(), base.data_ptr(), val.data_ptr(), idx.data_ptr(), Rb.data_ptr(),
+            idx_offset, B, N, math, workspace.data_ptr(), workspace.numel() * workspace.element_size(), rank, world, arr,
+            _stream(vs)), "ahv_verify_sharded")
+    return val, idx, Rb
+
+
 def topk(scores: torch.Tensor, k: int, idx_offset: int = 0):
     """torch.max / top-k with the reference's tie rule (lowest index wins)."""
     s = _dev(scores, "scores")

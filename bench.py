@@ -164,7 +164,7 @@ def run_reference(args):
             # same workload as the product arm; each timed step scores a bounded sample of it on the host cores
             "config": {"workload": (f"CO3D config 2 (BASELINE.json configs[1]): B={PAIRS} pairs x N={HYPS} hypotheses per GPU, "
                                     f"fp32 volumes, shared rotation set, top-1; N>1 = weak scaling over hypothesis shards "
-                                    f"+ NCCL all-gather of top-k"), "pairs": PAIRS, "hypotheses_per_gpu": HYPS,
+                                    f"+ in-kernel NVLink exchange of the winners"), "pairs": PAIRS, "hypotheses_per_gpu": HYPS,
                        "math": "reference ATen calls on the host CPU", "sample_per_step": f"{sp} pairs x {sh} hypotheses"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,12 +212,20 @@ def run_ours(args):
     R = ahv.ops.rotations_from_normals(normals_h.to(dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB L2
     launches = {"n": 0}
+    peer = None
+    if world > 1 and k == 1 and args.collective == "peer" and math != ahv.MATH_FP32:
+        peer = ahv.dist.PeerExchange(B, dev)
 
     def step():
         if world == 1:   # ahv_verify: target-feature prologue + fused score/arg-max/selection = 2 launches
             r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=0, gather=True)
             launches["n"] += 2
             return r.topk_val, r.topk_idx, r.R_best
+        if peer is not None:   # fused: the scoring kernels exchange and merge their winners over NVLink peer memory
+            val, idx, Rb = ahv.ops.verify_sharded(vs, vt, R, verifier.W1, verifier.W2, verifier.b2, shard_lo, rank, world,
+                                                  peer.ptrs, math=math, workspace=verifier._workspace(B, N, 1, dev))
+            launches["n"] += 2
+            return val, idx, Rb
         r = verifier.score(vs, vt, R, k=k, return_scores=False, idx_offset=shard_lo, gather=False)
         launches["n"] += 2
         vals, idxs = ahv.dist.all_gather_topk(r.topk_val, r.topk_idx)
@@ -344,10 +352,12 @@ def run_ours(args):
                             "operands (10-bit mantissa, TF32-equivalent) with fp32 accumulation on tcgen05; scores within "
                             "1.3e-4 relative of the reference's fp32 CPU path (gate 1e-3)",
             "config": {"workload": (f"Objaverse config 3 (BASELINE.json configs[2]): B={B} pairs, bf16 volumes, one set of "
-                                    f"{args.hyps} hypotheses sharded over {world} GPU(s), NCCL all-gather of top-{k}") if strong else
+                                    f"{args.hyps} hypotheses sharded over {world} GPU(s), winners exchanged {'by the scoring kernels over NVLink peer memory' if peer is not None else 'with an NCCL all-gather'}") if strong else
                                    (f"CO3D config 2 (BASELINE.json configs[1]): B={B} pairs x N={N} hypotheses per GPU, "
                                     f"fp32 volumes, shared rotation set, top-{k}; N>1 = weak scaling over hypothesis shards "
-                                    f"+ NCCL all-gather of top-k"), "pairs": B, "hypotheses_per_gpu": N, "math": args.math,
+                                    f"+ in-kernel NVLink exchange of the winners"), "pairs": B, "hypotheses_per_gpu": N, "math": args.math,
+                       "collective": ("none (1 GPU)" if world == 1 else "peer memory, fused into the scoring kernel" if peer is not None
+                                      else "NCCL all-gather + merge kernel"),
                        "l2": "flushed between timed steps (256 MiB memset, untimed)"},
             "voxel_samples_per_s": value * 512,
             "clocks": clocks,
@@ -385,6 +395,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--collective", choices=["peer", "nccl"], default="peer",
+                    help="N>1: winners exchanged by the scoring kernels through NVLink peer memory (default) or "
+                         "NCCL all-gather + merge kernel")
     ap.add_argument("--math", choices=["tc", "fp32"], default=os.environ.get("AHV_BENCH_MATH", "tc"))
     ap.add_argument("--pairs", type=int, default=PAIRS)
     ap.add_argument("--hyps", type=int, default=HYPS)

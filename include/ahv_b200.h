@@ -156,6 +156,28 @@ AHV_API int ahv_topk_merge(const float* vals, const int64_t* idx, int parts, int
 AHV_API int ahv_gather_rotations(const float* R, int r_per_pair, const int64_t* idx, int64_t idx_offset,
                          int B, int64_t N, int k, float* R_out, void* stream);
 
+/* Hypothesis set sharded over the GPUs of one NVSwitch node (the reference is single GPU).
+ * ahv_verify_sharded is ahv_verify with k == 1 on THIS rank's slice of the rotation set (global index =
+ * local + idx_offset) whose scoring kernel also performs the exchange: its last CTA writes this shard's
+ * winners (score, global index, rotation) into every peer's exchange buffer over NVLink, waits for the
+ * peers' flags and merges (higher score, ties -> lowest global index), so best_val/best_idx/R_best are the
+ * result over the WHOLE set, identical on every rank, with no NCCL call and no merge launch.
+ * peers[r] = rank r's exchange buffer as mapped in this process (peers[rank] = own).  Every rank must make
+ * the same sequence of calls with the same B.  Buffers: ahv_peer_alloc (zeroed cudaMalloc of
+ * ahv_peer_bytes(B)), ahv_peer_export -> 64-byte CUDA IPC handle to send to the peers, ahv_peer_open on
+ * their side; ahv_peer_close / ahv_peer_free to release.  AHV_MATH_TC / AHV_MATH_TC_F16GATHER only. */
+AHV_API size_t ahv_peer_bytes(int B);
+AHV_API int ahv_peer_alloc(size_t bytes, void** ptr);
+AHV_API int ahv_peer_free(void* ptr);
+AHV_API int ahv_peer_export(void* ptr, unsigned char* handle64);
+AHV_API int ahv_peer_open(const unsigned char* handle64, void** ptr);
+AHV_API int ahv_peer_close(void* ptr);
+AHV_API int ahv_verify_sharded(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
+                               const float* W1, const float* W2, const float* b2, const float* base, float* best_val,
+                               int64_t* best_idx, float* R_best, int64_t idx_offset, int B, int64_t N, int math_mode,
+                               void* workspace, size_t workspace_bytes, int rank, int world, void* const* peers,
+                               void* stream);
+
 /* Convenience entry taking HOST buffers (pageable or pinned): copies the
  * inputs to the device, computes the target features, runs ahv_score and
  * copies the selection back; synchronises `stream` before returning.  This is

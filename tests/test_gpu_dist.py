@@ -28,10 +28,23 @@ def _worker(rank, world, port, k, out_q):
     sv = ahv.dist.ShardedVerifier(v)
     val, idx, Rb = sv.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=k)
     single = v.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=k, return_scores=False)
+    # fused exchange: the scoring kernels trade their winners through NVLink peer memory (no NCCL in the step)
+    peer = ahv.dist.PeerExchange(8, dev)
+    fv = ahv.dist.ShardedVerifier(v, peer=peer)
+    fused = []
+    for rep in range(3):                                  # repeated exchanges exercise both parities
+        fval, fidx, fRb = fv.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=1)
+        fused.append((fval.cpu().numpy(), fidx.cpu().numpy(), fRb.cpu().numpy()))
+    Rp = torch.stack([T(g["R"][b * 900:(b + 1) * 900]) for b in range(3)]).contiguous()   # per-pair sets [3,900,3,3]
+    pval, pidx, pRb = fv.score(T(g["vol_src"]), T(g["vol_tgt"]), Rp, k=1)
+    psingle = v.score(T(g["vol_src"]), T(g["vol_tgt"]), Rp, k=1, return_scores=False)
     torch.cuda.synchronize()
     out_q.put((rank, val.cpu().numpy(), idx.cpu().numpy(), Rb.cpu().numpy(), single.topk_val.cpu().numpy(),
-               single.topk_idx.cpu().numpy()))
+               single.topk_idx.cpu().numpy(), fused,
+               (pval.cpu().numpy(), pidx.cpu().numpy(), pRb.cpu().numpy(), psingle.topk_val.cpu().numpy(),
+                psingle.topk_idx.cpu().numpy(), psingle.R_best.cpu().numpy())))
     dist.barrier()
+    peer.close()
     dist.destroy_process_group()
 
 
@@ -47,7 +60,12 @@ def test_sharded_equals_single_gpu_nccl(golden):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, val, idx, Rb, sval, sidx in res:
+    for rank, val, idx, Rb, sval, sidx, fused, pp in res:
         assert np.array_equal(idx, sidx) and np.array_equal(val, sval)
         assert np.array_equal(Rb, golden["shared_n3000_b3"]["R"][idx])
+        for fval, fidx, fRb in fused:                     # fused peer exchange == unsharded top-1, on every rank
+            assert np.array_equal(fidx[:, 0], sidx[:, 0]) and np.array_equal(fval[:, 0], sval[:, 0])
+            assert np.array_equal(fRb[:, 0], golden["shared_n3000_b3"]["R"][sidx[:, 0]])
+        pval, pidx, pRb, sv, si, sR = pp
+        assert np.array_equal(pidx, si) and np.array_equal(pval, sv) and np.array_equal(pRb, sR)
     assert np.array_equal(res[0][2], res[1][2])
