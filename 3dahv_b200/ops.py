@@ -43,7 +43,10 @@ def _dev(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
         raise RuntimeError(f"{name} must be a CUDA tensor: the 3DAHV hot path has no CPU fallback")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:   # the C ABI wants 16-byte aligned buffers; a slice such as R[lo:hi] need not be
+        t = t.clone()
+    return t
 
 
 def rotations_from_normals(normals: torch.Tensor) -> torch.Tensor:

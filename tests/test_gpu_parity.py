@@ -608,3 +608,19 @@ def test_concurrent_streams_and_threads(ahv, golden):
         assert torch.equal(r.scores, ref.scores)
         assert torch.equal(r.topk_idx, ref.topk_idx) and torch.equal(r.topk_val, ref.topk_val)
         assert torch.equal(r2.topk_idx, ref.topk_idx) and torch.equal(r2.R_best, ref.R_best)
+
+
+def test_misaligned_slices_are_accepted(ahv, golden):
+    """A hypothesis shard R[lo:hi] starts at lo*36 bytes, which is 16-byte aligned only for lo % 4 == 0; the
+    binding must hand the C ABI an aligned copy instead of failing with AHV_EINVAL (8-GPU shards of 50 000)."""
+    dev = _dev()
+    g = golden["shared_n3000_b3"]
+    T = lambda a: torch.from_numpy(a).to(dev)
+    v = ahv.HypothesisVerifier(*_weights(golden, dev))
+    R = T(g["R"])
+    full = v.score(T(g["vol_src"]), T(g["vol_tgt"]), R, k=1, return_scores=True)
+    for lo in (1, 2, 3, 6250 % 3000):
+        part = v.score(T(g["vol_src"]), T(g["vol_tgt"]), R[lo:], k=1, return_scores=True, idx_offset=lo)
+        assert torch.equal(part.scores, full.scores[:, lo:])
+        vs_view = T(g["vol_src"])[1:]                      # volumes: 32 KB per pair, always aligned; still a view
+        assert v.score(vs_view, T(g["vol_tgt"])[1:], R[lo:], k=1).topk_idx.shape == (2, 1)
