@@ -11,15 +11,22 @@
 //                        rotated order and the two taps that sit in adjacent lines in bank-parity
 //                        order, which makes every LDS.128 phase conflict-free by construction.
 //                        Results are rounded to fp16 and become the tri-plane A operand of conv1.
-//   warp  12    MMA      one elected thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
-//                        conv1 = 24 x (M=64,N=32,K=16) per hypothesis - slice (view,k) multiplies the
-//                        16 channels at a fixed k, so the rearrange/cat of modules/modules.py:115-118
-//                        is pure descriptor arithmetic - two hypotheses interleaved in the two 16-lane
-//                        halves of each TMEM sub-partition; conv2 = 2 x (M=128,N=32,K=16) per pair.
+//   warp  12    MMA      converged warp, one elect.sync lane issues tcgen05.mma (kind::f16, fp32
+//                        accumulate in TMEM): conv1 = 24 K slices (view,k) of (N=32,K=16) per hypothesis -
+//                        slice (view,k) multiplies the 16 channels at a fixed k, so the rearrange/cat of
+//                        modules/modules.py:115-118 is pure descriptor arithmetic - two hypotheses
+//                        interleaved in the two 16-lane halves of each TMEM sub-partition (M=64 per
+//                        hypothesis for views y/z, one M=128 MMA per slice for view x in the TS kernel);
+//                        conv2 = 2 x (M=128,N=32,K=16) per pair.
 //   warps 8-11  EPILOGUE tcgen05.ld D1 -> ReLU -> fp16 -> conv2 operand; tcgen05.ld D2 -> +bias ->
 //                        L2 norm -> dot with the target features (registers) -> mean over 64
-//                        positions -> score (+ running arg-max key, one atomicMax per CTA and pair).
+//                        positions -> score (+ running arg-max key, one atomicMax per CTA and pair);
+//                        the last CTA to finish decodes the winners and, when the hypothesis set is
+//                        sharded over GPUs, exchanges them with the peers' kernels over NVLink.
 // Pipelines (mbarrier): A-operand stages full/empty (3 deep), TMEM D1 full/empty, A2 full, D2 full.
+// Set-up: every CTA packs W1/W2 to fp16 operand layouts itself (MMA/epilogue warps) and derives each
+// pair's scale while staging its volume (gather warps), so the kernel depends on the target-feature
+// prologue only through its epilogue warps (programmatic dependent launch).
 //
 //   score_tc_ts_kernel  (default)  view x of conv1 and conv2's A operand go register -> TMEM
 //                        (tcgen05.st) and are consumed in the TS form of tcgen05.mma; only the YZ
