@@ -119,23 +119,38 @@ class GraphedVerifier:
     replay."""
 
     def __init__(self, verifier: HypothesisVerifier, B: int, N: int, k: int = 1, per_pair_R: bool = False,
-                 device="cuda", vol_dtype=torch.float32):
+                 device="cuda", vol_dtype=torch.float32, peer=None, idx_offset: int = 0):
+        """`peer` (a `dist.PeerExchange`): N is THIS rank's slice of a hypothesis set sharded over the peer
+        group (global index = local + idx_offset) and the captured step is `ahv_verify_sharded` - the scoring
+        kernels exchange their winners over NVLink themselves, so the multi-GPU step contains no NCCL call and
+        is graph-capturable as it stands.  Every rank must replay in lockstep."""
         self.v = verifier.to(torch.device(device))
         dev = torch.device(device)
         self.vol_src = torch.zeros(B, 16, 8, 8, 8, device=dev, dtype=vol_dtype)
         self.vol_tgt = torch.zeros(B, 16, 8, 8, 8, device=dev)
         self.R = torch.eye(3, device=dev).repeat(*((B, N) if per_pair_R else (N,)), 1, 1).contiguous()
         self.k = min(k, N)
+        if peer is not None and self.k != 1:
+            raise ValueError("the fused peer exchange selects the arg-max (k = 1)")
+
+        def run():
+            if peer is None:
+                return self.v.score(self.vol_src, self.vol_tgt, self.R, k=self.k, return_scores=False, idx_offset=idx_offset)
+            W1, W2, b2 = self.v._weights_on(dev)
+            val, idx, Rb = ops.verify_sharded(self.vol_src, self.vol_tgt, self.R, W1, W2, b2, idx_offset, peer.rank, peer.world,
+                                              peer.ptrs, math=self.v.math, workspace=self.v._workspace(B, N, 1, dev))
+            return VerifyResult(None, val[:, None], idx[:, None], Rb[:, None])
+
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(stream):
             for _ in range(2):                      # warm-up outside capture (module load, attributes)
-                self.out = self.v.score(self.vol_src, self.vol_tgt, self.R, k=self.k, return_scores=False)
+                self.out = run()
         torch.cuda.current_stream(dev).wait_stream(stream)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = self.v.score(self.vol_src, self.vol_tgt, self.R, k=self.k, return_scores=False)
+            self.out = run()
 
     @torch.no_grad()
     def __call__(self, vol_src=None, vol_tgt=None, R=None) -> VerifyResult:

@@ -30,6 +30,20 @@ for name, sv in (("nccl_allgather_merge", ahv.dist.ShardedVerifier(v)), ("fused_
     out[name] = {"p50_us": float(t), "idx": idx[:, 0].tolist()[:4]}
     ref = idx if ref is None else ref
     assert torch.equal(ref, idx)
+lo, hi = ahv.dist.shard_bounds(N, rank, world)
+gv = ahv.GraphedVerifier(v, B, hi - lo, k=1, device=dev, peer=peer, idx_offset=lo)
+gv(vs, vt, R[lo:hi])
+for _ in range(10):
+    gv()
+dist.barrier(); torch.cuda.synchronize()
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+for a, b in ev:
+    a.record(); o = gv(); b.record()
+torch.cuda.synchronize()
+t = torch.tensor([statistics.median(a.elapsed_time(b) for a, b in ev) * 1e3], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+out["fused_peer_exchange_graph_replay"] = {"p50_us": float(t), "idx": o.topk_idx[:, 0].tolist()[:4]}
+assert torch.equal(o.topk_idx, ref)
 single = v.score(vs, vt, R, k=1, return_scores=False)
 assert torch.equal(single.topk_idx, ref)
 if rank == 0:

@@ -35,6 +35,12 @@ def _worker(rank, world, port, k, out_q):
     for rep in range(3):                                  # repeated exchanges exercise both parities
         fval, fidx, fRb = fv.score(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), k=1)
         fused.append((fval.cpu().numpy(), fidx.cpu().numpy(), fRb.cpu().numpy()))
+    # the sharded step is NCCL-free, hence CUDA-graph capturable: replay it and compare again
+    lo, hi = ahv.dist.shard_bounds(3000, rank, world)
+    gv = ahv.GraphedVerifier(v, 3, hi - lo, k=1, device=dev, peer=peer, idx_offset=lo)
+    for rep in range(3):
+        out = gv(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"][lo:hi]))
+        fused.append((out.topk_val.cpu().numpy(), out.topk_idx.cpu().numpy(), out.R_best.cpu().numpy()))
     Rp = torch.stack([T(g["R"][b * 900:(b + 1) * 900]) for b in range(3)]).contiguous()   # per-pair sets [3,900,3,3]
     pval, pidx, pRb = fv.score(T(g["vol_src"]), T(g["vol_tgt"]), Rp, k=1)
     psingle = v.score(T(g["vol_src"]), T(g["vol_tgt"]), Rp, k=1, return_scores=False)
