@@ -266,6 +266,14 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
           dev = fmaxf(dev, fabsf(gij - (i == j ? 1.0f : 0.0f)));
         }
       const bool is_rot = dev < 1e-3f;  // NaN compares false -> full scan
+      // per axis a: the w-coefficient of the sample point and its reciprocal (one division per axis and item)
+      float inv_r[3];
+      bool flat[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        flat[a] = !(fabsf(Rr[3 * a]) > 1e-6f);
+        inv_r[a] = flat[a] ? 0.0f : 1.0f / Rr[3 * a];
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int vi = t + 256 * j;
@@ -304,9 +312,8 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
 #pragma unroll
               for (int a = 0; a < 3; ++a) {
                 const float ca = fmaf(Rr[3 * a + 1], uh, fmaf(Rr[3 * a + 2], ud, 3.5f - (a == 0 ? vx : (a == 1 ? vy : vz))));
-                const float r = Rr[3 * a];
-                if (fabsf(r) > 1e-6f) {
-                  const float ir = 1.0f / r;
+                if (!flat[a]) {
+                  const float ir = inv_r[a];
                   const float e0 = (-1.0f - ca) * ir, e1 = (1.0f - ca) * ir;
                   ulo = fmaxf(ulo, fminf(e0, e1));
                   uhi = fminf(uhi, fmaxf(e0, e1));
