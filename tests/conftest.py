@@ -19,7 +19,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     out = {}
-    for name in ("weights", "shared_n3000_b3", "primitives", "per_pair"):
+    for name in ("weights", "shared_n3000_b3", "primitives", "per_pair", "training_grads"):
         out[name] = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     return out
 

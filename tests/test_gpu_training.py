@@ -121,3 +121,30 @@ def test_fused_backward_edge_cases(ahv, golden, oracle):
         got = leaf.grad.detach().cpu().double()
         scale = ref.abs().max().item()
         assert torch.allclose(got, ref, rtol=0, atol=2e-4 * scale), (name, (got - ref).abs().max().item(), scale)
+
+
+@pytest.mark.parametrize("math_name", ["fp32", "tc"])
+def test_infonce_gradients_match_the_reference_fixture(ahv, golden, math_name):
+    """End to end against the REFERENCE's autograd (tests/golden/training_grads.npz, made by
+    oracle/make_golden_training.py from the reference's rotate_volume / forward_3d2d and the body of
+    infoNCE_loss): similarities, loss and the gradients of loss.mean() with respect to both volumes and the
+    head weights.  The backward kernel is fp32 in both modes; with AHV_MATH_TC only the forward scores (hence
+    the softmax weights that feed the backward) carry the tensor-core path's ~1e-4 error."""
+    dev = torch.device("cuda", 0)
+    g, w, tr = golden["shared_n3000_b3"], golden["weights"], golden["training_grads"]
+    T = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    vs, vt = T(g["vol_src"]).requires_grad_(True), T(g["vol_tgt"]).requires_grad_(True)
+    W1, W2, b2 = (T(w[k]).clone().requires_grad_(True) for k in ("W1", "W2", "b2"))
+    R, gt = T(tr["sampled_R"]), T(tr["gt_R"])
+    math = ahv.MATH_FP32 if math_name == "fp32" else ahv.MATH_TC
+    s = ahv.training.verification_scores(vs, vt, R, W1, W2, b2, math=math)
+    tol_s = 2e-5 if math_name == "fp32" else 1e-3
+    assert np.max(np.abs(s.detach().cpu().numpy() - tr["sim"]) / np.abs(tr["sim"])) <= tol_s
+    loss = ahv.training.infonce_loss(s, R, gt, acc_thr_deg=float(tr["acc_thr"]))
+    assert np.allclose(loss.detach().cpu().numpy(), tr["loss"], rtol=2e-4 if math_name == "fp32" else 5e-3)
+    loss.mean().backward()
+    tol_g = 2e-4 if math_name == "fp32" else 5e-3
+    for name, leaf in (("g_vol_src", vs), ("g_vol_tgt", vt), ("g_W1", W1), ("g_W2", W2), ("g_b2", b2)):
+        ref = tr[name].astype(np.float64)
+        err = np.abs(leaf.grad.detach().cpu().numpy().reshape(ref.shape) - ref).max()
+        assert err <= tol_g * np.abs(ref).max(), (name, err, np.abs(ref).max())

@@ -132,3 +132,34 @@ def test_so3_grid_restatement_properties(oracle):
     assert nn.min() > 4.0 and nn.max() < 10.0
     mean_angle = np.degrees(np.arccos(np.clip((np.trace(R, axis1=1, axis2=2) - 1) / 2, -1, 1))).mean()
     assert abs(mean_angle - 126.5) < 1.0          # Haar: pi/2 + 2/pi
+
+
+def test_training_oracle_matches_reference_autograd(golden, oracle):
+    """tests/golden/training_grads.npz holds loss, similarities and gradients produced by the reference's own
+    `rotate_volume` / `Feature_Aligner.forward_3d2d` under PyTorch autograd with the body of `infoNCE_loss`
+    (modules/model.py:43-63; oracle/make_golden_training.py).  The differentiable restatement the GPU
+    training tests use as their checker must reproduce them."""
+    import torch
+
+    g, w, tr = golden["shared_n3000_b3"], golden["weights"], golden["training_grads"]
+    T = lambda a: torch.from_numpy(np.asarray(a)).double()
+    vs, vt = T(g["vol_src"]).requires_grad_(True), T(g["vol_tgt"]).requires_grad_(True)
+    W1, W2, b2 = (T(w[k]).requires_grad_(True) for k in ("W1", "W2", "b2"))
+    R, gt = T(tr["sampled_R"]), T(tr["gt_R"])
+    tgt = oracle.forward_3d2d_torch(vt, W1, W2, b2)
+    sims = []
+    for b in range(vs.shape[0]):
+        rot = oracle.rotate_volume_torch(vs[b][None].expand(R.shape[1], -1, -1, -1, -1), R[b])
+        sims.append((oracle.forward_3d2d_torch(rot, W1, W2, b2) * tgt[b][None]).sum(dim=1).mean(dim=-1))
+    sim = torch.stack(sims)
+    np.testing.assert_allclose(sim.detach().numpy(), tr["sim"], rtol=1e-9, atol=1e-12)
+    gt_sim = ((R.flatten(2) * gt.reshape(-1, 1, 9)).sum(-1).clamp(-1, 3) - 1) / 2
+    pos = 180.0 * torch.arccos(gt_sim) / np.pi <= float(tr["acc_thr"])
+    assert pos[:, 0].all() and int(pos.sum()) > 3                   # ground truth first, a few more positives
+    e = torch.exp(sim / 0.1)
+    loss = -torch.log((e * pos).sum(-1) / e.sum(-1).clamp(min=1e-8))
+    np.testing.assert_allclose(loss.detach().numpy(), tr["loss"], rtol=1e-9)
+    loss.mean().backward()
+    for name, leaf in (("g_vol_src", vs), ("g_vol_tgt", vt), ("g_W1", W1), ("g_W2", W2), ("g_b2", b2)):
+        ref = tr[name].astype(np.float64)
+        np.testing.assert_allclose(leaf.grad.numpy(), ref, rtol=0, atol=2e-6 * np.abs(ref).max(), err_msg=name)
