@@ -55,18 +55,19 @@ namespace tc {
 
 // ---- prologue: target features forward_3d2d(vol_tgt[b]) (modules/model.py:191) in fp32, + arg-max key clear ----
 // grid (16, B), 128 threads: CTA (j, b) computes the 4 positions (p = j>>1, q = 4*(j&1) .. +3) of pair b for
-// all 32 channels.  6.7 KB of static shared memory and <= 96 registers per thread, so these CTAs co-reside
-// with the scoring kernel's CTAs (201 KB, 416 x 128 registers): the scoring kernel is launched
-// programmatically dependent and only its epilogue warps wait for this grid.
+// all 32 channels.  The scoring kernel is launched programmatically dependent on this grid and only its
+// epilogue warps wait for it.  (In practice the two kernels do not share an SM although 6.7 KB of shared
+// memory would fit beside the scoring CTA, so this kernel is built to be SHORT: all of a warp's W1 rows are
+// fetched in one L2 round trip - the scoring CTAs of the 16 SMs it occupies start that much later.)
 //   A[q][k]   tri-plane operand of the 4 positions (modules/modules.py:115-118):
 //             k = c*8+kk       -> V[c, p, q, kk]   (view x)
 //             k = 128+c*8+kk   -> V[c, p, kk, q]   (view y)
 //             k = 256+c*8+kk   -> V[c, kk, p, q]   (view z)
-//   conv1: warp w owns output rows o = w, w+4, ..., w+28; lanes stride k (coalesced W1 row reads, the next
-//          row's 12 values in flight while this row is reduced); ReLU -> h1[q][o].
+//   conv1: warp w owns output rows o = w, w+4, ..., w+28; lanes stride k (coalesced W1 row reads);
+//          ReLU -> h1[q][o].
 //   conv2 + bias + L2 normalise: warp = position, lane = output channel.
 constexpr int kTgtThreads = 128, kTgtCtasPerPair = 16;
-__global__ void __launch_bounds__(kTgtThreads, 4)
+__global__ void __launch_bounds__(kTgtThreads, 2)
 tc_tgt_feat_kernel(const float* __restrict__ vol_tgt, const float* __restrict__ W1, const float* __restrict__ W2,
                    const float* __restrict__ b2, u64* __restrict__ best_keys, unsigned* __restrict__ done_counter,
                    float* __restrict__ tgt_feat, int B) {
@@ -78,9 +79,15 @@ tc_tgt_feat_kernel(const float* __restrict__ vol_tgt, const float* __restrict__ 
   if (best_keys && blockIdx.x == 0 && t == 0) best_keys[b] = 0ull;
   if (done_counter && blockIdx.x == 0 && b == 0 && t == 32) *done_counter = 0u;
   const float* V = vol_tgt + (size_t)b * kC * kVox;
-  float wr[2][12];
+  float wr[8][12];  // this warp's eight W1 rows: all 96 loads in flight at once (one L2 round trip)
 #pragma unroll
-  for (int j = 0; j < 12; ++j) wr[0][j] = __ldg(W1 + warp * kK + lane + 32 * j);
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int j = 0; j < 12; ++j) wr[r][j] = __ldg(W1 + (warp + 4 * r) * kK + lane + 32 * j);
+  float4 w2r[kO / 4];  // conv2: this thread's W2 row (lane = output channel), fetched in the same round trip
+#pragma unroll
+  for (int o = 0; o < kO / 4; ++o) w2r[o] = __ldg(reinterpret_cast<const float4*>(W2 + lane * kO) + o);
+  const float bias = __ldg(b2 + lane);
 #pragma unroll
   for (int i = 0; i < 4 * kK / kTgtThreads; ++i) {
     const int e = t + kTgtThreads * i;
@@ -90,34 +97,27 @@ tc_tgt_feat_kernel(const float* __restrict__ vol_tgt, const float* __restrict__ 
     A[ql][k] = __ldg(V + c * kVox + d * 64 + h * 8 + w);
   }
   __syncthreads();
-#pragma unroll 1
-  for (int r = 0; r < 8; r += 2) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {  // two rows per trip so the double buffer is statically indexed
-      const int o = warp + 4 * (r + u);
-      if (r + u + 1 < 8) {
+  for (int r = 0; r < 8; ++r) {
+    const int o = warp + 4 * r;
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-        for (int j = 0; j < 12; ++j) wr[u ^ 1][j] = __ldg(W1 + (o + 4) * kK + lane + 32 * j);
-      }
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int j = 0; j < 12; ++j)
 #pragma unroll
-      for (int j = 0; j < 12; ++j)
+      for (int ql = 0; ql < 4; ++ql) acc[ql] = fmaf(wr[r][j], A[ql][lane + 32 * j], acc[ql]);
 #pragma unroll
-        for (int ql = 0; ql < 4; ++ql) acc[ql] = fmaf(wr[u][j], A[ql][lane + 32 * j], acc[ql]);
-#pragma unroll
-      for (int ql = 0; ql < 4; ++ql) {
-        const float v = warp_sum(acc[ql]);
-        if (lane == ql) h1[ql][o] = fmaxf(v, 0.0f);  // ReLU (modules/modules.py:68)
-      }
+    for (int ql = 0; ql < 4; ++ql) {
+      const float v = warp_sum(acc[ql]);
+      if (lane == ql) h1[ql][o] = fmaxf(v, 0.0f);  // ReLU (modules/modules.py:68)
     }
   }
   __syncthreads();
   {
     const int ql = warp, o2 = lane;  // 4 warps = 4 positions, lanes = output channels
-    float v = __ldg(b2 + o2);
+    float v = bias;
 #pragma unroll
     for (int o = 0; o < kO; o += 4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(W2 + o2 * kO + o));
+      const float4 w4 = w2r[o / 4];
       v = fmaf(w4.x, h1[ql][o], v); v = fmaf(w4.y, h1[ql][o + 1], v);
       v = fmaf(w4.z, h1[ql][o + 2], v); v = fmaf(w4.w, h1[ql][o + 3], v);
     }
