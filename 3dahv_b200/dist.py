@@ -63,29 +63,47 @@ class PeerExchange:
         self.device = torch.device(device)
         lib = _lib.lib()
         self._lib = lib
+        self.own, self.ptrs, self._opened = None, [], []
+        # Every step below that can fail is local; the ranks agree on the outcome with one all-reduce at the
+        # end, so a rank that cannot export or map a buffer makes ALL ranks raise instead of leaving the
+        # others blocked in a collective.
+        ok = True
         own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
         with torch.cuda.device(self.device):
-            _lib.check(lib.ahv_peer_alloc(lib.ahv_peer_bytes(max_pairs), ctypes.byref(own)), "ahv_peer_alloc")
-            handle = ctypes.create_string_buffer(64)
-            _lib.check(lib.ahv_peer_export(own, handle), "ahv_peer_export")
+            if lib.ahv_peer_alloc(lib.ahv_peer_bytes(max_pairs), ctypes.byref(own)) != 0:
+                ok = False
+            elif lib.ahv_peer_export(own, handle) != 0:
+                ok = False
+            self.own = own.value
             mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.device)
             every = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(every, mine, group=group)
-            self.own = own.value
-            self.ptrs, self._opened = [], []
-            for r, h in enumerate(every):
-                if r == self.rank:
-                    self.ptrs.append(self.own)
-                    continue
-                p = ctypes.c_void_p()
-                _lib.check(lib.ahv_peer_open(bytes(h.cpu().numpy().tobytes()), ctypes.byref(p)), "ahv_peer_open")
-                self.ptrs.append(p.value)
-                self._opened.append(p.value)
-        dist.barrier(group=group)
+            flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag) == 1:
+                for r, h in enumerate(every):
+                    if r == self.rank:
+                        self.ptrs.append(self.own)
+                        continue
+                    p = ctypes.c_void_p()
+                    if lib.ahv_peer_open(bytes(h.cpu().numpy().tobytes()), ctypes.byref(p)) != 0:
+                        ok = False
+                        break
+                    self.ptrs.append(p.value)
+                    self._opened.append(p.value)
+            else:
+                ok = False
+            flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag) != 1:
+            self.close()
+            raise RuntimeError("peer exchange unavailable: a rank could not allocate, export or map a CUDA IPC buffer "
+                               "(use the NCCL path: ShardedVerifier without `peer`)")
 
     def close(self):
         """Collective: every rank unmaps the peers' buffers before anyone frees its own."""
-        if getattr(self, "own", None) is None:
+        if getattr(self, "own", None) is None and not getattr(self, "_opened", None):
             return
         torch.cuda.synchronize(self.device)
         with torch.cuda.device(self.device):
@@ -93,7 +111,8 @@ class PeerExchange:
                 self._lib.ahv_peer_close(p)
             if dist.is_initialized():
                 dist.barrier(group=self.group)
-            self._lib.ahv_peer_free(self.own)
+            if self.own:
+                self._lib.ahv_peer_free(self.own)
         self.own, self.ptrs, self._opened = None, [], []
 
 

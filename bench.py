@@ -214,7 +214,11 @@ def run_ours(args):
     launches = {"n": 0}
     peer = None
     if world > 1 and k == 1 and args.collective == "peer" and math != ahv.MATH_FP32:
-        peer = ahv.dist.PeerExchange(B, dev)
+        try:
+            peer = ahv.dist.PeerExchange(B, dev)
+        except RuntimeError as e:   # raised on every rank together: fall back to NCCL all-gather + merge
+            if rank == 0:
+                print(f"[bench] {e}", file=sys.stderr)
 
     def step():
         if world == 1:   # ahv_verify: target-feature prologue + fused score/arg-max/selection = 2 launches
