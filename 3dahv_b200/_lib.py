@@ -42,6 +42,7 @@ SIGNATURES = {
     "ahv_peer_export": (_i, [_vp, ctypes.c_char_p]),
     "ahv_peer_open": (_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "ahv_peer_close": (_i, [_vp]),
+    "ahv_peer_status": (_i, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
     "ahv_verify_sharded": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _i, _vp, _sz, _i, _i,
                                 ctypes.POINTER(ctypes.c_void_p), _vp]),
     "ahv_predict_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),

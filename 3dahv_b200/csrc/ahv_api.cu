@@ -243,6 +243,15 @@ AHV_API int ahv_peer_open(const unsigned char* handle64, void** ptr) {
   return AHV_OK;
 }
 
+AHV_API int ahv_peer_status(const void* own, unsigned* exchanges_done, unsigned* timed_out) {
+  if (!own || !exchanges_done || !timed_out) return AHV_EINVAL;
+  unsigned hdr[2];
+  if (cudaMemcpy(hdr, own, sizeof(hdr), cudaMemcpyDeviceToHost) != cudaSuccess) return AHV_ECUDA;  // synchronises
+  *exchanges_done = hdr[0];
+  *timed_out = hdr[1];
+  return AHV_OK;
+}
+
 AHV_API int ahv_peer_close(void* ptr) { return (!ptr || cudaIpcCloseMemHandle(ptr) == cudaSuccess) ? AHV_OK : AHV_ECUDA; }
 
 AHV_API int ahv_verify_sharded(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,

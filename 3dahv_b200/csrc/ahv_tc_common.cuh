@@ -108,7 +108,9 @@ __device__ __forceinline__ void peer_exchange_and_merge(const Finalize& fin, con
     const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(mine + kPeerFlagsOff) + par * kMaxPeers + lane;
     const long long t0 = clock64();
     while (*flag != seq) {
-      if (clock64() - t0 > 4000000000LL) { ok = false; break; }  // ~2 s: a peer died; fail instead of hanging the GPU
+      // ~20 s at 2 GHz: ranks may reach a step seconds apart (host-side skew); only a peer that never arrives
+      // is turned into an error (NaN scores, index -1, header error word) instead of a GPU that hangs forever
+      if (clock64() - t0 > 40000000000LL) { ok = false; break; }
     }
   }
   ok = __all_sync(0xffffffffu, ok);

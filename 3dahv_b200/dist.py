@@ -101,6 +101,20 @@ class PeerExchange:
             raise RuntimeError("peer exchange unavailable: a rank could not allocate, export or map a CUDA IPC buffer "
                                "(use the NCCL path: ShardedVerifier without `peer`)")
 
+    def check(self) -> int:
+        """Synchronises the device and raises if an exchange on this rank timed out waiting for a peer (that
+        step returned NaN scores and index -1).  Returns the number of exchanges completed."""
+        import ctypes
+
+        from . import _lib
+
+        seq, err = ctypes.c_uint32(), ctypes.c_uint32()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.ahv_peer_status(self.own, ctypes.byref(seq), ctypes.byref(err)), "ahv_peer_status")
+        if err.value != 0:
+            raise RuntimeError("a sharded verification step timed out waiting for a peer rank")
+        return int(seq.value)
+
     def close(self):
         """Collective: every rank unmaps the peers' buffers before anyone frees its own."""
         if getattr(self, "own", None) is None and not getattr(self, "_opened", None):

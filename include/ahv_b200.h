@@ -165,13 +165,17 @@ AHV_API int ahv_gather_rotations(const float* R, int r_per_pair, const int64_t* 
  * peers[r] = rank r's exchange buffer as mapped in this process (peers[rank] = own).  Every rank must make
  * the same sequence of calls with the same B.  Buffers: ahv_peer_alloc (zeroed cudaMalloc of
  * ahv_peer_bytes(B)), ahv_peer_export -> 64-byte CUDA IPC handle to send to the peers, ahv_peer_open on
- * their side; ahv_peer_close / ahv_peer_free to release.  AHV_MATH_TC / AHV_MATH_TC_F16GATHER only. */
+ * their side; ahv_peer_close / ahv_peer_free to release.  AHV_MATH_TC / AHV_MATH_TC_F16GATHER only.
+ * A peer that never reaches a step is waited for ~20 s (device clock), then reported as above. */
 AHV_API size_t ahv_peer_bytes(int B);
 AHV_API int ahv_peer_alloc(size_t bytes, void** ptr);
 AHV_API int ahv_peer_free(void* ptr);
 AHV_API int ahv_peer_export(void* ptr, unsigned char* handle64);
 AHV_API int ahv_peer_open(const unsigned char* handle64, void** ptr);
 AHV_API int ahv_peer_close(void* ptr);
+/* Synchronising read of this rank's exchange header: exchanges completed, and whether one of them timed out
+ * waiting for a peer (that step returned NaN scores and index -1). */
+AHV_API int ahv_peer_status(const void* own, unsigned* exchanges_done, unsigned* timed_out);
 AHV_API int ahv_verify_sharded(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
                                const float* W1, const float* W2, const float* b2, const float* base, float* best_val,
                                int64_t* best_idx, float* R_best, int64_t idx_offset, int B, int64_t N, int math_mode,

@@ -49,6 +49,7 @@ def _worker(rank, world, port, k, out_q):
                single.topk_idx.cpu().numpy(), fused,
                (pval.cpu().numpy(), pidx.cpu().numpy(), pRb.cpu().numpy(), psingle.topk_val.cpu().numpy(),
                 psingle.topk_idx.cpu().numpy(), psingle.R_best.cpu().numpy())))
+    assert peer.check() == 3 + (2 + 3) + 1               # eager x3, graphed: 2 warm-ups + 3 replays, per-pair x1; none timed out
     dist.barrier()
     peer.close()
     dist.destroy_process_group()
