@@ -257,7 +257,7 @@ int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, c
   if ((int64_t)B * N == 0) return AHV_OK;
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   return dispatch(vol_src, vol_dtype, f16_gather, nullptr, tgt_feat, R, r_per_pair, W1, W2, b2, base, scores, false,
-                  B, N, tc::carve(ws, B), tc::Finalize{nullptr, nullptr, nullptr, 0, nullptr}, s);
+                  B, N, tc::carve(ws, B), tc::Finalize{}, s);
 }
 
 // the whole verification step with arg-max selection in two launches: prologue (target features, key
@@ -270,7 +270,11 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
   if ((int64_t)B * N == 0) return world > 1 ? AHV_EINVAL : AHV_OK;  // a sharded step needs every rank in the exchange
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   const tc::Scratch sc = tc::carve(ws, B);
-  tc::Finalize fin{best_val, best_idx, R_best, idx_offset, nullptr};
+  tc::Finalize fin;
+  fin.val = best_val;
+  fin.idx = best_idx;
+  fin.R_best = R_best;
+  fin.idx_offset = idx_offset;
   if (world > 1) {
     if (world > tc::kMaxPeers || rank < 0 || rank >= world || !peers) return AHV_EINVAL;
     fin.rank = rank;

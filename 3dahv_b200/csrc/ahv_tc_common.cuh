@@ -45,15 +45,15 @@ __device__ __forceinline__ float opaque_one(int flag01) { return __uint_as_float
 // Fused selection epilogue (modules/model.py:195-196): the last CTA to finish decodes the arg-max keys
 // into (score, global index, sampled_R[pred_index]) per pair.  val == nullptr disables it.
 struct Finalize {
-  float* val;
-  int64_t* idx;
-  float* R_best;
-  int64_t idx_offset;
-  unsigned* counter;  // zero at kernel start (cleared with the keys), reset by the last CTA
+  float* val = nullptr;
+  int64_t* idx = nullptr;
+  float* R_best = nullptr;
+  int64_t idx_offset = 0;
+  unsigned* counter = nullptr;  // zero at kernel start (cleared with the keys), reset by the last CTA
   // hypothesis set sharded over `world` GPUs: the winners are exchanged through peer memory
   // by this kernel itself (no NCCL call, no merge kernel); peers[r] = rank r's exchange buffer, mapped here
-  int rank, world;
-  unsigned char* peers[kMaxPeers];
+  int rank = 0, world = 1;
+  unsigned char* peers[kMaxPeers] = {};
 };
 
 // ---- peer exchange buffer (one per rank, cudaMalloc'ed by ahv_peer_alloc, IPC-mapped into every peer) ----
