@@ -142,6 +142,129 @@ void ahv_oracle_forward_3d2d_one(const float *v, const float *W1, const float *W
   }
 }
 
+/* ---- training variant: gradient of the scores (modules/model.py:53-56 under autograd, inside infoNCE_loss :43-63) ----
+ * Explicit chain rule in double precision, one (pair, hypothesis) at a time, deliberately in the textbook
+ * SCATTER form for the resampling adjoint (the CUDA kernel uses a gather):
+ *   X = rotate(V_b, R_n) (utils.py:113-131), A = tri-plane(X), H1 = relu(A W1^T), H2 = H1 W2^T + b2,
+ *   F = H2 / max(|H2|, eps) (modules/modules.py:112-124), s = mean_p <F_p, T_p>  (modules/model.py:55)
+ * grad_scores [B][N] -> g_vol [B][16][512], g_tgt [B][32][64], g_W1 [32][384], g_W2 [32][32], g_b2 [32]
+ * (all double, ADDED into).  tgt = forward_3d2d(vol_tgt) is an input: its own backward is not part of the
+ * hot path.  Single-threaded: small cases only. */
+void ahv_oracle_score_backward(const float *vol_src, const float *tgt, const float *R, int r_per_pair,
+                               const float *W1, const float *W2, const float *b2, const float *base, int B,
+                               int64_t N, const float *grad_scores, double *g_vol, double *g_tgt, double *g_W1,
+                               double *g_W2, double *g_b2) {
+  static double X[AC][AVOX], dX[AC][AVOX], tri[AK][AP], dtri[AK][AP], h1[AO][AP], h2[AO][AP], dh1[AO][AP], dh2[AO][AP];
+  for (int b = 0; b < B; ++b)
+    for (int64_t n = 0; n < N; ++n) {
+      const float *Rn = R + (r_per_pair ? ((int64_t)b * N + n) : n) * 9;
+      const float *V = vol_src + (int64_t)b * AC * AVOX;
+      const float *T = tgt + (int64_t)b * AO * AP;
+      const double g = (double)grad_scores[(int64_t)b * N + n] / (double)AP;
+      /* forward, recording each output voxel's taps (same float arithmetic as ahv_oracle_rotate_one) */
+      static int tap_src[AVOX][8];
+      static double tap_w[AVOX][8];
+      for (int d = 0; d < AS; ++d)
+        for (int h = 0; h < AS; ++h)
+          for (int w = 0; w < AS; ++w) {
+            const float x = base[w], y = base[h], z = base[d];
+            const float gx = (Rn[0] * x + Rn[1] * y) + Rn[2] * z;
+            const float gy = (Rn[3] * x + Rn[4] * y) + Rn[5] * z;
+            const float gz = (Rn[6] * x + Rn[7] * y) + Rn[8] * z;
+            const float ix = ((gx + 1.0f) * 8.0f - 1.0f) / 2.0f;
+            const float iy = ((gy + 1.0f) * 8.0f - 1.0f) / 2.0f;
+            const float iz = ((gz + 1.0f) * 8.0f - 1.0f) / 2.0f;
+            const float fx0 = floorf(ix), fy0 = floorf(iy), fz0 = floorf(iz);
+            const float tx = ix - fx0, ty = iy - fy0, tz = iz - fz0;
+            const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+            const int v = (d * AS + h) * AS + w;
+            for (int c = 0; c < AC; ++c) X[c][v] = 0.0;
+            for (int t = 0; t < 8; ++t) {
+              const int dx = t & 1, dy = (t >> 1) & 1, dz = t >> 2;
+              const int xx = x0 + dx, yy = y0 + dy, zz = z0 + dz;
+              tap_src[v][t] = -1;
+              tap_w[v][t] = 0.0;
+              if (xx < 0 || xx >= AS || yy < 0 || yy >= AS || zz < 0 || zz >= AS) continue;
+              const float wgt = (dx ? tx : 1.0f - tx) * (dy ? ty : 1.0f - ty) * (dz ? tz : 1.0f - tz);
+              tap_src[v][t] = (zz * AS + yy) * AS + xx;
+              tap_w[v][t] = (double)wgt;
+              for (int c = 0; c < AC; ++c) X[c][v] += (double)wgt * (double)V[c * AVOX + tap_src[v][t]];
+            }
+          }
+      for (int c = 0; c < AC; ++c)
+        for (int k = 0; k < AS; ++k)
+          for (int p = 0; p < AS; ++p)
+            for (int q = 0; q < AS; ++q) {
+              tri[c * 8 + k][p * 8 + q] = X[c][(p * 8 + q) * 8 + k];
+              tri[128 + c * 8 + k][p * 8 + q] = X[c][(p * 8 + k) * 8 + q];
+              tri[256 + c * 8 + k][p * 8 + q] = X[c][(k * 8 + p) * 8 + q];
+            }
+      for (int o = 0; o < AO; ++o)
+        for (int p = 0; p < AP; ++p) {
+          double a = 0.0;
+          for (int k = 0; k < AK; ++k) a += (double)W1[o * AK + k] * tri[k][p];
+          h1[o][p] = a > 0.0 ? a : 0.0;
+        }
+      for (int o = 0; o < AO; ++o)
+        for (int p = 0; p < AP; ++p) {
+          double a = (double)b2[o];
+          for (int i = 0; i < AO; ++i) a += (double)W2[o * AO + i] * h1[i][p];
+          h2[o][p] = a;
+        }
+      /* backward */
+      for (int p = 0; p < AP; ++p) {
+        double ss = 0.0, ft = 0.0;
+        for (int o = 0; o < AO; ++o) ss += h2[o][p] * h2[o][p];
+        const double nraw = sqrt(ss), nr = nraw < 1e-12 ? 1e-12 : nraw;
+        for (int o = 0; o < AO; ++o) ft += h2[o][p] / nr * (double)T[o * AP + p];
+        for (int o = 0; o < AO; ++o) {
+          const double F = h2[o][p] / nr, t = (double)T[o * AP + p];
+          dh2[o][p] = g / nr * (nraw < 1e-12 ? t : t - F * ft);
+          g_tgt[((int64_t)b * AO + o) * AP + p] += g * F;
+          g_b2[o] += dh2[o][p];
+        }
+      }
+      for (int o = 0; o < AO; ++o)
+        for (int i = 0; i < AO; ++i) {
+          double a = 0.0;
+          for (int p = 0; p < AP; ++p) a += dh2[o][p] * h1[i][p];
+          g_W2[o * AO + i] += a;
+        }
+      for (int i = 0; i < AO; ++i)
+        for (int p = 0; p < AP; ++p) {
+          double a = 0.0;
+          for (int o = 0; o < AO; ++o) a += dh2[o][p] * (double)W2[o * AO + i];
+          dh1[i][p] = h1[i][p] > 0.0 ? a : 0.0;
+        }
+      for (int o = 0; o < AO; ++o)
+        for (int k = 0; k < AK; ++k) {
+          double a = 0.0;
+          for (int p = 0; p < AP; ++p) a += dh1[o][p] * tri[k][p];
+          g_W1[o * AK + k] += a;
+        }
+      for (int k = 0; k < AK; ++k)
+        for (int p = 0; p < AP; ++p) {
+          double a = 0.0;
+          for (int o = 0; o < AO; ++o) a += dh1[o][p] * (double)W1[o * AK + k];
+          dtri[k][p] = a;
+        }
+      for (int c = 0; c < AC; ++c)
+        for (int v = 0; v < AVOX; ++v) dX[c][v] = 0.0;
+      for (int c = 0; c < AC; ++c)
+        for (int k = 0; k < AS; ++k)
+          for (int p = 0; p < AS; ++p)
+            for (int q = 0; q < AS; ++q) {
+              dX[c][(p * 8 + q) * 8 + k] += dtri[c * 8 + k][p * 8 + q];
+              dX[c][(p * 8 + k) * 8 + q] += dtri[128 + c * 8 + k][p * 8 + q];
+              dX[c][(k * 8 + p) * 8 + q] += dtri[256 + c * 8 + k][p * 8 + q];
+            }
+      for (int v = 0; v < AVOX; ++v)
+        for (int t = 0; t < 8; ++t)
+          if (tap_src[v][t] >= 0)
+            for (int c = 0; c < AC; ++c) g_vol[((int64_t)b * AC + c) * AVOX + tap_src[v][t]] += tap_w[v][t] * dX[c][v];
+    }
+}
+
 /* modules/model.py:186-193.  vol_src/vol_tgt [B][16][512]; R [N][9] shared
  * (r_per_pair=0) or [B][N][9]; scores [B][N].  The B*N independent
  * (pair, hypothesis) items are split evenly over `nthreads` pthreads. */

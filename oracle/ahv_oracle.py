@@ -316,7 +316,9 @@ def c_lib(build: bool = True):
     lib.ahv_oracle_so3_grid.restype = None
     lib.ahv_oracle_score.argtypes = [fp, fp, fp, ctypes.c_int, fp, fp, fp, fp, ctypes.c_int, ctypes.c_int64, fp, ctypes.c_int]
     lib.ahv_oracle_argmax.argtypes = [fp, ctypes.c_int, ctypes.c_int64, fp, ctypes.POINTER(ctypes.c_int64)]
-    for fn in (lib.ahv_oracle_so3_from_normals, lib.ahv_oracle_score, lib.ahv_oracle_argmax):
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ahv_oracle_score_backward.argtypes = [fp, fp, fp, ctypes.c_int, fp, fp, fp, fp, ctypes.c_int, ctypes.c_int64, fp, dp, dp, dp, dp, dp]
+    for fn in (lib.ahv_oracle_so3_from_normals, lib.ahv_oracle_score, lib.ahv_oracle_argmax, lib.ahv_oracle_score_backward):
         fn.restype = None
     _C_LIB = lib
     return lib
@@ -362,3 +364,29 @@ def score_c(vol_src, vol_tgt, R, W1, W2, b2, base=None, nthreads: int | None = N
     out = np.empty((B, N), dtype=f)
     c_lib().ahv_oracle_score(_fp(vs), _fp(vt), _fp(Rc), int(per_pair), _fp(W1c), _fp(W2c), _fp(b2c), _fp(base), B, N, _fp(out), int(nthreads))
     return out
+
+
+def score_backward_c(vol_src, tgt_feat, R, W1, W2, b2, grad_scores, base=None):
+    """C restatement (double accumulation, scatter-form adjoint) of the gradient of the scores with respect
+    to the source volumes, the target FEATURES, W1, W2 and b2 (modules/model.py:53-56 under autograd).
+    Returns float64 arrays (g_vol [B,16,8,8,8], g_tgt [B,32,64], g_W1 [32,384], g_W2 [32,32], g_b2 [32])."""
+    import ctypes
+
+    f = np.float32
+    vs = np.ascontiguousarray(vol_src, dtype=f)
+    tg = np.ascontiguousarray(tgt_feat, dtype=f)
+    Rc = np.ascontiguousarray(R, dtype=f)
+    gs = np.ascontiguousarray(grad_scores, dtype=f)
+    per_pair = Rc.ndim == 4
+    B = vs.shape[0]
+    N = Rc.shape[1] if per_pair else Rc.shape[0]
+    base = base_coords_np() if base is None else np.ascontiguousarray(base, dtype=f)
+    W1c = np.ascontiguousarray(W1, dtype=f).reshape(OCH, KTRI)
+    W2c = np.ascontiguousarray(W2, dtype=f).reshape(OCH, OCH)
+    b2c = np.ascontiguousarray(b2, dtype=f)
+    g_vol, g_tgt = np.zeros((B, 16, 8, 8, 8)), np.zeros((B, OCH, 64))
+    g_W1, g_W2, g_b2 = np.zeros((OCH, KTRI)), np.zeros((OCH, OCH)), np.zeros(OCH)
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    c_lib().ahv_oracle_score_backward(_fp(vs), _fp(tg), _fp(Rc), int(per_pair), _fp(W1c), _fp(W2c), _fp(b2c), _fp(base), B, N,
+                                      _fp(gs), dp(g_vol), dp(g_tgt), dp(g_W1), dp(g_W2), dp(g_b2))
+    return g_vol, g_tgt, g_W1, g_W2, g_b2

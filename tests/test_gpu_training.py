@@ -148,3 +148,21 @@ def test_infonce_gradients_match_the_reference_fixture(ahv, golden, math_name):
         ref = tr[name].astype(np.float64)
         err = np.abs(leaf.grad.detach().cpu().numpy().reshape(ref.shape) - ref).max()
         assert err <= tol_g * np.abs(ref).max(), (name, err, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("per_pair", [False, True])
+def test_backward_kernel_matches_the_c_oracle(ahv, golden, oracle, per_pair):
+    """ahv_score_backward called directly through the binding against oracle/ahv_oracle.c::ahv_oracle_score_backward
+    (double accumulation, scatter-form adjoint) on a ragged case; the outputs are ADDED into the buffers."""
+    dev = torch.device("cuda", 0)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    B, N = 3, 7
+    R = g["R"][100:100 + B * N].reshape(B, N, 3, 3) if per_pair else g["R"][200:200 + N]
+    gs = np.random.default_rng(5).standard_normal((B, N)).astype(np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    tgt = ahv.ops.forward_3d2d(T(g["vol_tgt"]), T(w["W1"]), T(w["W2"]), T(w["b2"]))
+    ref = oracle.score_backward_c(g["vol_src"], tgt.cpu().numpy(), R, w["W1"], w["W2"], w["b2"], gs)
+    got = ahv.ops.score_backward(T(g["vol_src"]), tgt, T(R), T(w["W1"]), T(w["W2"]), T(w["b2"]), T(gs))
+    for name, a, r in zip(("vol", "tgt", "W1", "W2", "b2"), got, ref):
+        err = np.abs(a.cpu().numpy().astype(np.float64) - r).max()
+        assert err <= 1e-4 * np.abs(r).max(), (name, err, np.abs(r).max())

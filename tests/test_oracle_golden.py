@@ -163,3 +163,32 @@ def test_training_oracle_matches_reference_autograd(golden, oracle):
     for name, leaf in (("g_vol_src", vs), ("g_vol_tgt", vt), ("g_W1", W1), ("g_W2", W2), ("g_b2", b2)):
         ref = tr[name].astype(np.float64)
         np.testing.assert_allclose(leaf.grad.numpy(), ref, rtol=0, atol=2e-6 * np.abs(ref).max(), err_msg=name)
+
+
+def test_c_oracle_backward_matches_reference_autograd(golden, oracle):
+    """oracle/ahv_oracle.c::ahv_oracle_score_backward (explicit chain rule, double accumulation, scatter-form
+    adjoint of the resampling) against the gradients the reference's own autograd produced
+    (tests/golden/training_grads.npz).  The C oracle stops at the target FEATURES; the B target volumes go
+    through the differentiable restatement of forward_3d2d."""
+    import torch
+
+    g, w, tr = golden["shared_n3000_b3"], golden["weights"], golden["training_grads"]
+    T = lambda a: torch.from_numpy(np.asarray(a)).double()
+    R, gt = T(tr["sampled_R"]), T(tr["gt_R"])
+    sim = T(tr["sim"]).requires_grad_(True)
+    gt_sim = ((R.flatten(2) * gt.reshape(-1, 1, 9)).sum(-1).clamp(-1, 3) - 1) / 2
+    pos = 180.0 * torch.arccos(gt_sim) / np.pi <= float(tr["acc_thr"])
+    e = torch.exp(sim / 0.1)
+    (-torch.log((e * pos).sum(-1) / e.sum(-1).clamp(min=1e-8))).mean().backward()
+    grad_scores = sim.grad.numpy()                                   # dL/dscore [B,N]
+    vt = T(g["vol_tgt"]).requires_grad_(True)
+    W1, W2, b2 = (T(w[k]).requires_grad_(True) for k in ("W1", "W2", "b2"))
+    tgt = oracle.forward_3d2d_torch(vt, W1, W2, b2)
+    g_vol, g_tgt, g_W1, g_W2, g_b2 = oracle.score_backward_c(g["vol_src"], tgt.detach().numpy(), tr["sampled_R"], w["W1"],
+                                                             w["W2"], w["b2"], grad_scores)
+    tgt.backward(torch.from_numpy(g_tgt))                            # target side: B volumes
+    got = {"g_vol_src": g_vol, "g_vol_tgt": vt.grad.numpy(), "g_W1": g_W1 + W1.grad.numpy(),
+           "g_W2": g_W2 + W2.grad.numpy(), "g_b2": g_b2 + b2.grad.numpy()}
+    for name, val in got.items():
+        ref = tr[name].astype(np.float64)
+        np.testing.assert_allclose(val.reshape(ref.shape), ref, rtol=0, atol=2e-5 * np.abs(ref).max(), err_msg=name)
