@@ -6,8 +6,9 @@
  * cites the reference code it replaces.  All pointers are DEVICE pointers to
  * contiguous, 16-byte-aligned buffers owned by the caller unless the name ends
  * in `_host`.  `stream` is a `cudaStream_t` passed as `void*`.  Calls are
- * asynchronous and stream-ordered, allocate nothing, keep no global state, and
- * are CUDA-graph capturable.  Return value: 0 on success, negative `AHV_E*`.
+ * asynchronous and stream-ordered, allocate nothing (ahv_predict_host and the
+ * explicit ahv_peer_alloc aside), keep no global state, and are CUDA-graph
+ * capturable.  Return value: 0 on success, negative `AHV_E*`.
  * There is NO CPU fallback: on a device that is not sm_100 the compute entry
  * points return AHV_ENOTSUP.
  *
