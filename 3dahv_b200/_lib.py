@@ -36,15 +36,22 @@ SIGNATURES = {
     "ahv_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ahv_gather_rotations": (_i, [_vp, _i, _vp, _i64, _i, _i64, _i, _vp, _vp]),
     "ahv_diag_smem_read": (_i, [_vp, _i, _i, ctypes.POINTER(ctypes.c_ulonglong), _vp]),
-    "ahv_peer_bytes": (_sz, [_i]),
-    "ahv_peer_alloc": (_i, [_sz, ctypes.POINTER(ctypes.c_void_p)]),
+    "ahv_peer_bytes": (_sz, [_i, _i]),
+    "ahv_peer_alloc": (_i, [_i, _i, ctypes.POINTER(ctypes.c_void_p)]),
     "ahv_peer_free": (_i, [_vp]),
     "ahv_peer_export": (_i, [_vp, ctypes.c_char_p]),
     "ahv_peer_open": (_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "ahv_peer_close": (_i, [_vp]),
     "ahv_peer_status": (_i, [_vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]),
-    "ahv_verify_sharded": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i64, _i, _vp, _sz, _i, _i,
-                                ctypes.POINTER(ctypes.c_void_p), _vp]),
+    "ahv_peer_capacity": (_i, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "ahv_topk_exchange": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _vp, _vp, _vp, _i, _i, ctypes.POINTER(ctypes.c_void_p),
+                               _i, _i, _vp]),
+    "ahv_verify_sharded": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i64, _i, _vp, _sz, _i, _i,
+                                ctypes.POINTER(ctypes.c_void_p), _i, _i, _vp]),
+    "ahv_host_session_create": (_i, [ctypes.POINTER(ctypes.c_void_p)]),
+    "ahv_host_session_destroy": (_i, [_vp]),
+    "ahv_predict_host_ex": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i64, _i, _i, _i,
+                                 ctypes.POINTER(ctypes.c_void_p), _i, _i, _vp]),
     "ahv_predict_host": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp]),
 }
 

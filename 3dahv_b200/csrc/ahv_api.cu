@@ -1,8 +1,9 @@
 // extern "C" surface of lib3dahv_b200 (see include/ahv_b200.h for the contract
 // and the reference interface each entry replaces).
 #include <cstring>
+#include <new>
 
-#include "ahv_common.cuh"
+#include "ahv_peer.cuh"
 
 using namespace ahv;
 
@@ -98,11 +99,12 @@ AHV_API int ahv_forward_3d2d(const float* vol, const float* W1, const float* W2,
   return launch_forward_3d2d(vol, W1, W2, b2, feat, m, (cudaStream_t)stream);
 }
 
-// workspace = [scores B*N fp32 | top-k partial keys | tensor-core path scratch]
+// workspace = [scores B*N fp32 | top-k partial keys | tensor-core path scratch | per-shard top-k lists]
 AHV_API size_t ahv_workspace_bytes(int B, int64_t N, int k) {
   if (B < 0 || N < 0) return 0;
   return align_up((size_t)B * (size_t)N * sizeof(float), 256) +
-         align_up(topk_workspace_bytes(B, N, k), 256) + align_up(score_tc_workspace_bytes(B, N), 256);
+         align_up(topk_workspace_bytes(B, N, k), 256) + align_up(score_tc_workspace_bytes(B, N), 256) +
+         align_up((size_t)B * (size_t)(k > 0 ? k : 1) * (sizeof(float) + sizeof(int64_t)), 256);
 }
 
 AHV_API int ahv_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* topk_val,
@@ -213,14 +215,23 @@ AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt,
 }
 
 // ---- hypothesis set sharded over the GPUs of one node: winners exchanged through peer memory -------------
-AHV_API size_t ahv_peer_bytes(int B) { return B < 0 ? 0 : peer_exchange_bytes(B); }
+AHV_API size_t ahv_peer_bytes(int max_pairs, int max_k) {
+  return (max_pairs < 1 || max_k < 1 || max_k > kMaxK) ? 0 : peer::buffer_bytes(max_pairs, max_k);
+}
 
-AHV_API int ahv_peer_alloc(size_t bytes, void** ptr) {
-  if (!ptr || bytes == 0) return AHV_EINVAL;
+AHV_API int ahv_peer_alloc(int max_pairs, int max_k, void** ptr) {
+  if (!ptr || max_pairs < 1 || max_k < 1 || max_k > kMaxK) return AHV_EINVAL;
   int st = check_device();
   if (st != AHV_OK) return st;
+  const size_t bytes = peer::buffer_bytes(max_pairs, max_k);
   if (cudaMalloc(ptr, bytes) != cudaSuccess) return AHV_ECUDA;
-  if (cudaMemset(*ptr, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return AHV_ECUDA;
+  const uint32_t hdr[4] = {0u, 0u, (uint32_t)max_pairs, (uint32_t)max_k};  // seq, err, capacity
+  if (cudaMemset(*ptr, 0, bytes) != cudaSuccess || cudaMemcpy(*ptr, hdr, sizeof(hdr), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return AHV_ECUDA;
+  }
   return AHV_OK;
 }
 
@@ -252,67 +263,177 @@ AHV_API int ahv_peer_status(const void* own, unsigned* exchanges_done, unsigned*
   return AHV_OK;
 }
 
+AHV_API int ahv_peer_capacity(const void* buf, int* max_pairs, int* max_k) {
+  if (!buf || !max_pairs || !max_k) return AHV_EINVAL;
+  unsigned hdr[4];
+  if (cudaMemcpy(hdr, buf, sizeof(hdr), cudaMemcpyDeviceToHost) != cudaSuccess) return AHV_ECUDA;  // synchronises
+  *max_pairs = (int)hdr[2];
+  *max_k = (int)hdr[3];
+  return AHV_OK;
+}
+
 AHV_API int ahv_peer_close(void* ptr) { return (!ptr || cudaIpcCloseMemHandle(ptr) == cudaSuccess) ? AHV_OK : AHV_ECUDA; }
 
-AHV_API int ahv_verify_sharded(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
-                               const float* W1, const float* W2, const float* b2, const float* base, float* best_val,
-                               int64_t* best_idx, float* R_best, int64_t idx_offset, int B, int64_t N, int math_mode,
-                               void* workspace, size_t workspace_bytes, int rank, int world, void* const* peers,
-                               void* stream) {
-  if (B < 1 || N < 1 || N > 0x7fffffffLL || world < 1 || world > 8 || rank < 0 || rank >= world) return AHV_EINVAL;
-  if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
-  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_TC_F16GATHER) return AHV_ENOTSUP;  // the fused exchange lives in the tensor-core kernel
-  if (!vol_src || !vol_tgt || !R || !W1 || !W2 || !b2 || !base || !best_val || !best_idx || (world > 1 && !peers))
+namespace {
+int make_peer_args(int rank, int world, void* const* peers, int peer_max_pairs, int peer_max_k, peer::Args* pa) {
+  if (world < 1 || world > peer::kMaxPeers || rank < 0 || rank >= world) return AHV_EINVAL;
+  pa->rank = rank;
+  pa->world = world;
+  pa->cap_pairs = peer_max_pairs;
+  pa->cap_k = peer_max_k;
+  if (world > 1) {
+    if (!peers || peer_max_pairs < 1 || peer_max_k < 1 || peer_max_k > kMaxK) return AHV_EINVAL;
+    for (int r = 0; r < world; ++r) {
+      if (!peers[r]) return AHV_EINVAL;
+      pa->bufs[r] = static_cast<unsigned char*>(peers[r]);
+    }
+  }
+  return AHV_OK;
+}
+}  // namespace
+
+AHV_API int ahv_topk_exchange(const float* val, const int64_t* idx, const float* R, int r_per_pair, int64_t idx_offset,
+                              int64_t N, int B, int k, float* out_val, int64_t* out_idx, float* R_best, int rank,
+                              int world, void* const* peers, int peer_max_pairs, int peer_max_k, void* stream) {
+  if (B < 1 || k < 1 || k > kMaxK || N < 0 || idx_offset < 0 || !val || !idx || !out_val || !out_idx || (N > 0 && !R))
     return AHV_EINVAL;
+  if (idx_offset + N > 0x100000000LL) return AHV_EINVAL;  // keys carry 32 index bits
+  peer::Args pa;
+  int st = make_peer_args(rank, world, peers, peer_max_pairs, peer_max_k, &pa);
+  if (st != AHV_OK) return st;
+  if (world < 2) return AHV_EINVAL;
+  st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_topk_exchange(val, idx, R, r_per_pair != 0, idx_offset, N, B, k, out_val, out_idx, R_best, pa,
+                              (cudaStream_t)stream);
+}
+
+AHV_API int ahv_verify_sharded(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
+                               const float* W1, const float* W2, const float* b2, const float* base, float* topk_val,
+                               int64_t* topk_idx, float* R_best, int k, int64_t idx_offset, int B, int64_t N,
+                               int math_mode, void* workspace, size_t workspace_bytes, int rank, int world,
+                               void* const* peers, int peer_max_pairs, int peer_max_k, void* stream) {
+  if (B < 1 || N < 0 || N > 0x7fffffffLL || k < 1 || k > kMaxK || idx_offset < 0) return AHV_EINVAL;
+  if (idx_offset + N > 0x100000000LL) return AHV_EINVAL;  // keys carry 32 index bits
+  if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
+  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32 && math_mode != AHV_MATH_TC_F16GATHER) return AHV_EINVAL;
+  if (!vol_src || !vol_tgt || (N > 0 && !R) || !W1 || !W2 || !b2 || !base || !topk_val || !topk_idx) return AHV_EINVAL;
   if (!aligned16(vol_src) || !aligned16(vol_tgt) || !aligned16(R) || !aligned16(W1) || !aligned16(W2) ||
       !aligned16(workspace))
     return AHV_EINVAL;
-  int st = check_device();
+  peer::Args pa;
+  int st = make_peer_args(rank, world, peers, peer_max_pairs, peer_max_k, &pa);
   if (st != AHV_OK) return st;
-  if (!workspace || workspace_bytes < ahv_workspace_bytes(B, N, 1)) return AHV_EWORKSPACE;
+  if (world > 1 && (B > peer_max_pairs || k > peer_max_k)) return AHV_EINVAL;  // exchange buffer too small for this call
+  st = check_device();
+  if (st != AHV_OK) return st;
+  if (world == 1)
+    return N == 0 ? AHV_EINVAL
+                  : ahv_verify(vol_src, vol_dtype, vol_tgt, R, r_per_pair, W1, W2, b2, base, nullptr, topk_val, topk_idx,
+                               R_best, k, idx_offset, B, N, math_mode, workspace, workspace_bytes, stream);
+  if (!workspace || workspace_bytes < ahv_workspace_bytes(B, N, k)) return AHV_EWORKSPACE;
   unsigned char* ws = static_cast<unsigned char*>(workspace);
-  const size_t off_tc = align_up((size_t)B * (size_t)N * sizeof(float), 256) + align_up(topk_workspace_bytes(B, N, 1), 256);
-  return launch_verify_tc_argmax(vol_src, vol_dtype, vol_tgt, R, r_per_pair != 0, W1, W2, b2, base, nullptr, best_val,
-                                 best_idx, R_best, idx_offset, B, N, ws + off_tc, workspace_bytes - off_tc,
-                                 (cudaStream_t)stream, math_mode == AHV_MATH_TC_F16GATHER, rank, world, peers);
+  const size_t off_tc = align_up((size_t)B * (size_t)N * sizeof(float), 256) + align_up(topk_workspace_bytes(B, N, k), 256);
+  const size_t need_tc = align_up(score_tc_workspace_bytes(B, N), 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (k == 1 && N > 0 && math_mode != AHV_MATH_FP32)  // the scoring kernel exchanges and merges the winners itself
+    return launch_verify_tc_argmax(vol_src, vol_dtype, vol_tgt, R, r_per_pair != 0, W1, W2, b2, base, nullptr, topk_val,
+                                   topk_idx, R_best, idx_offset, B, N, ws + off_tc, need_tc, s,
+                                   math_mode == AHV_MATH_TC_F16GATHER, &pa);
+  // k > 1 (or an empty shard, or fp32 FFMA arithmetic): local top-k of the shard, then the exchange kernel
+  float* l_val = reinterpret_cast<float*>(ws + off_tc + need_tc);
+  int64_t* l_idx = reinterpret_cast<int64_t*>(ws + off_tc + need_tc + align_up((size_t)B * k * sizeof(float), 8));
+  const int kl = N < k ? (int)N : k;
+  if (kl < k) {  // pad with (-inf, -1), which the merge ignores
+    AHV_CUDA_OK(cudaMemsetAsync(l_val, 0xff, (size_t)B * k * sizeof(float), s));
+    AHV_CUDA_OK(cudaMemsetAsync(l_idx, 0xff, (size_t)B * k * sizeof(int64_t), s));
+  }
+  if (N > 0) {
+    float* tgt = scratch_tgt_feat(ws + off_tc, B);
+    st = launch_forward_3d2d(vol_tgt, W1, W2, b2, tgt, B, s);
+    if (st != AHV_OK) return st;
+    if (kl == k) {
+      st = ahv_score(vol_src, vol_dtype, tgt, R, r_per_pair, W1, W2, b2, base, nullptr, l_val, l_idx, k, idx_offset, B, N,
+                     math_mode, workspace, workspace_bytes, stream);
+    } else {  // fewer hypotheses than k on this shard: compact [B,kl] lists (in the output buffers, which the
+              // exchange overwrites afterwards), then spread into the padded [B,k]
+      st = ahv_score(vol_src, vol_dtype, tgt, R, r_per_pair, W1, W2, b2, base, nullptr, topk_val, topk_idx, kl, idx_offset, B,
+                     N, math_mode, workspace, workspace_bytes, stream);
+      if (st != AHV_OK) return st;
+      AHV_CUDA_OK(cudaMemcpy2DAsync(l_val, (size_t)k * sizeof(float), topk_val, (size_t)kl * sizeof(float),
+                                    (size_t)kl * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+      AHV_CUDA_OK(cudaMemcpy2DAsync(l_idx, (size_t)k * sizeof(int64_t), topk_idx, (size_t)kl * sizeof(int64_t),
+                                    (size_t)kl * sizeof(int64_t), B, cudaMemcpyDeviceToDevice, s));
+    }
+    if (st != AHV_OK) return st;
+  }
+  return launch_topk_exchange(l_val, l_idx, R, r_per_pair != 0, idx_offset, N, B, k, topk_val, topk_idx, R_best, pa, s);
 }
 
-AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_host, const float* R_host,
-                     int r_per_pair, const float* W1_host, const float* W2_host,
-                     const float* b2_host, const float* base_host, float* scores_host,
-                     float* topk_val_host, int64_t* topk_idx_host, float* R_best_host, int k, int B,
-                     int64_t N, int math_mode, void* stream) {
-  if (B < 1 || N < 1 || k < 1 || k > kMaxK) return AHV_EINVAL;
-  if (!vol_src_host || !vol_tgt_host || !R_host || !W1_host || !W2_host || !b2_host || !base_host)
-    return AHV_EINVAL;
-  if (!topk_val_host || !topk_idx_host) return AHV_EINVAL;
+// ---- host-buffer entries -------------------------------------------------------------------------------
+// A session owns the device scratch of the host-buffer entry, grown on demand and reused across calls
+// (explicit caller-owned state; nothing process-global is touched).
+struct ahv_host_session {
+  unsigned char* d = nullptr;
+  size_t bytes = 0;
+  int device = -1;
+};
+
+AHV_API int ahv_host_session_create(ahv_host_session** session) {
+  if (!session) return AHV_EINVAL;
   int st = check_device();
   if (st != AHV_OK) return st;
+  ahv_host_session* hs = new (std::nothrow) ahv_host_session();
+  if (!hs) return AHV_ECUDA;
+  if (cudaGetDevice(&hs->device) != cudaSuccess) { delete hs; return AHV_ECUDA; }
+  *session = hs;
+  return AHV_OK;
+}
+
+AHV_API int ahv_host_session_destroy(ahv_host_session* session) {
+  if (!session) return AHV_OK;
+  const bool ok = !session->d || cudaFree(session->d) == cudaSuccess;
+  delete session;
+  return ok ? AHV_OK : AHV_ECUDA;
+}
+
+AHV_API int ahv_predict_host_ex(ahv_host_session* session, const void* vol_src_host, int vol_dtype,
+                                const float* vol_tgt_host, const float* R_host, int r_per_pair, const float* W1_host,
+                                const float* W2_host, const float* b2_host, const float* base_host, float* scores_host,
+                                float* topk_val_host, int64_t* topk_idx_host, float* R_best_host, int k,
+                                int64_t idx_offset, int B, int64_t N, int math_mode, int rank, int world,
+                                void* const* peers, int peer_max_pairs, int peer_max_k, void* stream) {
+  if (!session || B < 1 || N < 1 || k < 1 || k > kMaxK) return AHV_EINVAL;
+  if (vol_dtype != AHV_VOL_F32 && vol_dtype != AHV_VOL_BF16) return AHV_EINVAL;
+  if (!vol_src_host || !vol_tgt_host || !R_host || !W1_host || !W2_host || !b2_host || !base_host) return AHV_EINVAL;
+  if (!topk_val_host || !topk_idx_host) return AHV_EINVAL;
+  if (world > 1 && scores_host) return AHV_EINVAL;  // a sharded step returns the selection only
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != session->device) return AHV_EINVAL;
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t vol_b = (size_t)B * kC * kVox * sizeof(float);
+  const size_t src_b = (size_t)B * kC * kVox * (vol_dtype == AHV_VOL_BF16 ? 2 : 4);
+  const size_t tgt_b = (size_t)B * kC * kVox * sizeof(float);
   const size_t r_b = (size_t)(r_per_pair ? B : 1) * N * 9 * sizeof(float);
-  const size_t feat_b = (size_t)B * kO * kP * sizeof(float);
   const size_t w_b = (size_t)(kO * kK + kO * kO + kO + 8) * sizeof(float);
   const size_t out_b = (size_t)B * k * (sizeof(float) + sizeof(int64_t) + 9 * sizeof(float));
   const size_t ws_b = ahv_workspace_bytes(B, N, k);
-  const size_t total = align_up(vol_b, 256) * 2 + align_up(r_b, 256) + align_up(feat_b, 256) +
-                       align_up(w_b, 256) + align_up(out_b, 256) + ws_b;
-  unsigned char* d = nullptr;
-  {  // keep the stream-ordered pool's memory across calls instead of returning it to the OS at every sync
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+  const size_t total = align_up(src_b, 256) + align_up(tgt_b, 256) + align_up(r_b, 256) + align_up(w_b, 256) +
+                       align_up(out_b, 256) + ws_b;
+  if (session->bytes < total) {  // grow (rare): the stream may still use the old block
+    if (cudaStreamSynchronize(s) != cudaSuccess) return AHV_ECUDA;
+    if (session->d && cudaFree(session->d) != cudaSuccess) return AHV_ECUDA;
+    session->d = nullptr;
+    session->bytes = 0;
+    if (cudaMalloc((void**)&session->d, total) != cudaSuccess) return AHV_ECUDA;
+    session->bytes = total;
   }
-  AHV_CUDA_OK(cudaMallocAsync((void**)&d, total, s));
-  unsigned char* p = d;
+  unsigned char* p = session->d;
   auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 256); return r; };
-  float* d_src = (float*)take(vol_b);
-  float* d_tgt = (float*)take(vol_b);
+  void* d_src = take(src_b);
+  float* d_tgt = (float*)take(tgt_b);
   float* d_R = (float*)take(r_b);
-  float* d_feat = (float*)take(feat_b);
   float* d_w = (float*)take(w_b);
   unsigned char* d_out = take(out_b);
   void* d_ws = p;
@@ -323,16 +444,21 @@ AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_hos
   float* d_Rb = d_val + (size_t)B * k;
   st = AHV_ECUDA;
   do {
-    if (cudaMemcpyAsync(d_src, vol_src_host, vol_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
-    if (cudaMemcpyAsync(d_tgt, vol_tgt_host, vol_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_src, vol_src_host, src_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_tgt, vol_tgt_host, tgt_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (cudaMemcpyAsync(d_R, R_host, r_b, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (cudaMemcpyAsync(d_W1, W1_host, kO * kK * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (cudaMemcpyAsync(d_W2, W2_host, kO * kO * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (cudaMemcpyAsync(d_b2, b2_host, kO * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
     if (cudaMemcpyAsync(d_base, base_host, 8 * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) break;
-    st = ahv_verify(d_src, AHV_VOL_F32, d_tgt, d_R, r_per_pair, d_W1, d_W2, d_b2, d_base,
-                    scores_host ? (float*)d_ws : nullptr, d_val, d_idx, d_Rb, k, 0, B, N, math_mode, d_ws, ws_b,
-                    stream);
+    if (world > 1)
+      st = ahv_verify_sharded(d_src, vol_dtype, d_tgt, d_R, r_per_pair, d_W1, d_W2, d_b2, d_base, d_val, d_idx, d_Rb, k,
+                              idx_offset, B, N, math_mode, d_ws, ws_b, rank, world, peers, peer_max_pairs, peer_max_k,
+                              stream);
+    else
+      st = ahv_verify(d_src, vol_dtype, d_tgt, d_R, r_per_pair, d_W1, d_W2, d_b2, d_base,
+                      scores_host ? (float*)d_ws : nullptr, d_val, d_idx, d_Rb, k, idx_offset, B, N, math_mode, d_ws, ws_b,
+                      stream);
     if (st != AHV_OK) break;
     st = AHV_ECUDA;
     if (scores_host &&
@@ -345,9 +471,23 @@ AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_hos
       break;
     st = AHV_OK;
   } while (0);
-  cudaFreeAsync(d, s);
   if (cudaStreamSynchronize(s) != cudaSuccess && st == AHV_OK) st = AHV_ECUDA;
   return st;
+}
+
+AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_host, const float* R_host,
+                     int r_per_pair, const float* W1_host, const float* W2_host,
+                     const float* b2_host, const float* base_host, float* scores_host,
+                     float* topk_val_host, int64_t* topk_idx_host, float* R_best_host, int k, int B,
+                     int64_t N, int math_mode, void* stream) {
+  ahv_host_session* hs = nullptr;
+  int st = ahv_host_session_create(&hs);
+  if (st != AHV_OK) return st;
+  st = ahv_predict_host_ex(hs, vol_src_host, AHV_VOL_F32, vol_tgt_host, R_host, r_per_pair, W1_host, W2_host, b2_host,
+                           base_host, scores_host, topk_val_host, topk_idx_host, R_best_host, k, 0, B, N, math_mode, 0, 1,
+                           nullptr, 0, 0, stream);
+  const int st2 = ahv_host_session_destroy(hs);
+  return st != AHV_OK ? st : st2;
 }
 
 }  // extern "C"

@@ -82,6 +82,8 @@ __device__ __forceinline__ float key_score(u64 key) {
 __device__ __forceinline__ uint32_t key_index(u64 key) { return 0xFFFFFFFFu - (uint32_t)key; }
 
 
+namespace peer { struct Args; }  // ahv_peer.cuh
+
 // Launch-side helpers implemented in the .cu files --------------------------
 int launch_so3_from_normals(const float* normals, float* R, int64_t n, cudaStream_t s);
 int launch_so3_sample(uint64_t seed, int64_t first, float* R, int64_t n, cudaStream_t s);
@@ -111,8 +113,10 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
                             int r_per_pair, const float* W1, const float* W2, const float* b2,
                             const float* base, float* scores, float* best_val, int64_t* best_idx,
                             float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
-                            cudaStream_t s, bool f16_gather, int rank = 0, int world = 1, void* const* peers = nullptr);
-size_t peer_exchange_bytes(int B);  // exchange buffer of the sharded step (ahv_peer_alloc)
+                            cudaStream_t s, bool f16_gather, const peer::Args* pa = nullptr);
+int launch_topk_exchange(const float* val, const int64_t* idx, const float* R, int r_per_pair, int64_t idx_offset,
+                         int64_t N, int B, int k, float* out_val, int64_t* out_idx, float* R_best,
+                         const peer::Args& pa, cudaStream_t s);
 int launch_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* val,
                 int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t s);
 size_t topk_workspace_bytes(int B, int64_t N, int k);

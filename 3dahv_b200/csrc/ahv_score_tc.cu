@@ -28,12 +28,11 @@
 // pair's scale while staging its volume (gather warps), so the kernel depends on the target-feature
 // prologue only through its epilogue warps (programmatic dependent launch).
 //
-//   score_tc_ts_kernel  (default)  view x of conv1 and conv2's A operand go register -> TMEM
-//                        (tcgen05.st) and are consumed in the TS form of tcgen05.mma; only the YZ
-//                        operand copy lives in shared memory; a stage is a hypothesis pair.
-//   score_tc_kernel     (AHV_TC_VARIANT=ss)  both operand copies (YZ and X) and A2 in shared memory,
-//                        SS form only; a stage is one hypothesis.
-// Both exist for fp32-staged volumes (fp32 FFMA interpolation) and for 16-bit staged volumes
+//   score_tc_ts_kernel   view x of conv1 and conv2's A operand go register -> TMEM (tcgen05.st) and are
+//                        consumed in the TS form of tcgen05.mma; only the YZ operand copy lives in shared
+//                        memory; a stage is a hypothesis pair.  (An earlier SS-form kernel - both operand
+//                        copies and A2 in shared memory - is gone from the build; see git history.)
+// It exists for fp32-staged volumes (fp32 FFMA interpolation) and for 16-bit staged volumes
 // (K16: bf16 inputs or AHV_MATH_TC_F16GATHER; x-pair lines, packed HFMA2 interpolation).
 //
 // Precision: normalisation and correlation are fp32; the two 1x1 convs use fp16 operands (10-bit
@@ -41,12 +40,9 @@
 // power of two (exact) so fp16 can neither overflow nor go subnormal; the scale is undone after
 // conv2 (ReLU and the bias-free conv1 are positively homogeneous).
 //
-// Files: ahv_tc_ptx.cuh (PTX wrappers), ahv_tc_common.cuh (roles, tile iterator, weight packing, volume
-// staging, epilogue), ahv_score_tc_ss.cuh / ahv_score_tc_ts.cuh (the two kernels), this file (target-feature
-// prologue, workspace carve-up, launchers).
-#include <cstdlib>
-
-#include "ahv_score_tc_ss.cuh"
+// Files: ahv_tc_ptx.cuh (PTX wrappers), ahv_peer.cuh (NVLink exchange buffer), ahv_tc_common.cuh (roles, tile
+// iterator, weight packing, volume staging, epilogue), ahv_score_tc_ts.cuh (the kernel), this file
+// (target-feature prologue, workspace carve-up, launchers).
 #include "ahv_score_tc_ts.cuh"
 
 namespace ahv {
@@ -192,17 +188,9 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   if (((int64_t)B * N) / grid >= 0xffffffffLL) return AHV_EINVAL;  // per-CTA tile iterator is 32-bit
   const float* tgt = prologue ? sc.tgt_feat : tgt_feat_in;
   u64* keys = want_argmax ? sc.best_keys : nullptr;
-  static const bool use_ts = [] { const char* e = getenv("AHV_TC_VARIANT"); return !(e && e[0] == 's'); }();
-  static const bool use_pdl = [] { const char* e = getenv("AHV_PDL"); return !(e && e[0] == '0'); }();
-  if (use_ts) {
-    AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
-    return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue && use_pdl, vol_src, tgt, R, r_per_pair,
-                      b2, base, W1, W2, scores, keys, B, N, fin);
-  }
-  constexpr int kSmemBytes = Map<K16>::smem_bytes;
-  AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  return launch_pdl(score_tc_kernel<T, K16>, grid, kSmemBytes, s, prologue && use_pdl, vol_src, tgt, R, r_per_pair, b2, base,
-                    W1, W2, scores, keys, B, N, fin);
+  AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
+  return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue, vol_src, tgt, R, r_per_pair, b2, base, W1,
+                    W2, scores, keys, B, N, fin);
 }
 
 }  // namespace tc
@@ -266,7 +254,8 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
                             int r_per_pair, const float* W1, const float* W2, const float* b2,
                             const float* base, float* scores, float* best_val, int64_t* best_idx,
                             float* R_best, int64_t idx_offset, int B, int64_t N, void* ws, size_t ws_bytes,
-                            cudaStream_t s, bool f16_gather, int rank, int world, void* const* peers) {
+                            cudaStream_t s, bool f16_gather, const peer::Args* pa) {
+  const int world = pa ? pa->world : 1;
   if ((int64_t)B * N == 0) return world > 1 ? AHV_EINVAL : AHV_OK;  // a sharded step needs every rank in the exchange
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   const tc::Scratch sc = tc::carve(ws, B);
@@ -276,19 +265,14 @@ int launch_verify_tc_argmax(const void* vol_src, int vol_dtype, const float* vol
   fin.R_best = R_best;
   fin.idx_offset = idx_offset;
   if (world > 1) {
-    if (world > tc::kMaxPeers || rank < 0 || rank >= world || !peers) return AHV_EINVAL;
-    fin.rank = rank;
-    fin.world = world;
-    for (int r = 0; r < world; ++r) {
-      if (!peers[r]) return AHV_EINVAL;
-      fin.peers[r] = static_cast<unsigned char*>(peers[r]);
-    }
+    if (world > peer::kMaxPeers || pa->rank < 0 || pa->rank >= world || B > pa->cap_pairs || pa->cap_k < 1) return AHV_EINVAL;
+    for (int r = 0; r < world; ++r)
+      if (!pa->bufs[r]) return AHV_EINVAL;
+    fin.peers = *pa;
   }
   return dispatch(vol_src, vol_dtype, f16_gather, vol_tgt, nullptr, R, r_per_pair, W1, W2, b2, base, scores, true,
                   B, N, sc, fin, s);
 }
-
-size_t peer_exchange_bytes(int B) { return tc::peer_entry_off(2, 0, B, 0); }
 
 }  // namespace ahv
 

@@ -388,7 +388,7 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     __syncwarp();
   } else {
     // =========================== EPILOGUE ===========================
-    epilogue_role<true>(work, warp - kEpiWarp0, lane, tmem, bar0, nullptr, M::tmem_a2, partial, tgt_feat, b2, inv_ring,
+    epilogue_role(work, warp - kEpiWarp0, lane, tmem, bar0, M::tmem_a2, partial, tgt_feat, b2, inv_ring,
                         scores, best_keys, N, B, R, r_per_pair, fin);
   }
 

@@ -1,8 +1,9 @@
-// Pieces shared by the SS and TS tensor-core scoring kernels (see ahv_score_tc.cu for the overview):
+// Building blocks of the tensor-core scoring kernel (see ahv_score_tc.cu for the overview):
 // warp roles and pipeline barriers, the per-CTA work range and 32-bit tile iterator, in-kernel weight
 // packing and pair-volume staging (power-of-two pre-scale), and the epilogue role (ReLU -> conv2 operand,
 // normalise -> correlate -> mean -> score, running arg-max, fused winner decode).
 #pragma once
+#include "ahv_peer.cuh"
 #include "ahv_tc_ptx.cuh"
 
 namespace ahv {
@@ -27,12 +28,10 @@ constexpr int kEpiWarp0 = 8;
 constexpr int kMmaWarp = 12;
 constexpr int kThreadsTC = 13 * 32;
 constexpr int kStages = 3;
-constexpr int kMaxPeers = 8;  // GPUs of one NVSwitch node
 
 // ---- shared memory map (bytes) ----
 constexpr int kW1Bytes = 24 * 1024;  // 24 MMA slices x [2 chalf][4 ngroup][8][8] fp16
 constexpr int kW2Bytes = 2 * 1024;
-constexpr int kA2Bytes = 8192;  // conv2 A operand of the SS kernel: [4 kc][16 rowgroup][8][8] fp16
 
 enum Bar { kFull = 0, kEmpty = 3, kD1Full = 6, kD1Empty = 8, kA2Full = 10, kD2Full = 12 };
 
@@ -50,93 +49,61 @@ struct Finalize {
   float* R_best = nullptr;
   int64_t idx_offset = 0;
   unsigned* counter = nullptr;  // zero at kernel start (cleared with the keys), reset by the last CTA
-  // hypothesis set sharded over `world` GPUs: the winners are exchanged through peer memory
-  // by this kernel itself (no NCCL call, no merge kernel); peers[r] = rank r's exchange buffer, mapped here
-  int rank = 0, world = 1;
-  unsigned char* peers[kMaxPeers] = {};
+  // hypothesis set sharded over `peers.world` GPUs: the winners are exchanged through peer
+  // memory by this kernel itself (no NCCL call, no merge kernel); see ahv_peer.cuh for the buffer
+  peer::Args peers;
 };
-
-// ---- peer exchange buffer (one per rank, cudaMalloc'ed by ahv_peer_alloc, IPC-mapped into every peer) ----
-//   [0,256)    header: uint32 seq (number of exchanges this rank has completed), uint32 err
-//   [256,512)  flags[2 parity][8 ranks] uint32: flags[par][r] == s  <=>  rank r's entries of exchange s are here
-//   [512,...)  entries[2 parity][8 ranks][B] x 64 B: {int64 global index, float score, float R[9], pad}
-// Exchange s uses parity s & 1.  A rank can only finish exchange s+1 after every peer has sent s+1, i.e. after
-// every peer is done reading exchange s, so two parities suffice; sequence numbers make the flags
-// self-cleaning (CUDA-graph replay needs no host-side reset).
-constexpr int kPeerFlagsOff = 256, kPeerEntriesOff = 512, kPeerEntryBytes = 64;
-__host__ __device__ inline size_t peer_entry_off(int par, int r, int B, int b) {
-  return (size_t)kPeerEntriesOff + (((size_t)par * kMaxPeers + r) * B + b) * kPeerEntryBytes;
-}
-__device__ __forceinline__ uint32_t ordered_bits(float score) {  // same order as make_key()
-  uint32_t u = __float_as_uint(score + 0.0f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
 
 // Last CTA of rank `rank`: publish this shard's winners to every peer, wait for theirs, merge
 // (higher score wins, ties -> lowest global index, like torch.max on the unsharded set; every rank computes
-// the same result).  One warp.
+// the same result).  One warp.  A step that timed out waiting for a peer returns NaN score, index -1 and a NaN
+// rotation, and sets the header's error word.
 __device__ __forceinline__ void peer_exchange_and_merge(const Finalize& fin, const u64* best_keys, const float* R,
                                                         int r_per_pair, int64_t N, int B, int lane) {
-  unsigned char* mine = fin.peers[fin.rank];
+  const peer::Args& pa = fin.peers;
+  unsigned char* mine = pa.bufs[pa.rank];
   uint32_t* hdr = reinterpret_cast<uint32_t*>(mine);
   const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(hdr) + 1u;
   const int par = (int)(seq & 1u);
   for (int b = lane; b < B; b += 32) {
     const u64 key = __ldcg(best_keys + b);
     const uint32_t n = key_index(key);
-    const int64_t gidx = (int64_t)n + fin.idx_offset;
     const float* src = R + ((r_per_pair ? (size_t)b * N : 0) + (size_t)n) * 9;
     float r9[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) r9[e] = __ldg(src + e);
-    const uint4 q0 = make_uint4((uint32_t)gidx, (uint32_t)((u64)gidx >> 32), __float_as_uint(key_score(key)), __float_as_uint(r9[0]));
-    const uint4 q1 = make_uint4(__float_as_uint(r9[1]), __float_as_uint(r9[2]), __float_as_uint(r9[3]), __float_as_uint(r9[4]));
-    const uint4 q2 = make_uint4(__float_as_uint(r9[5]), __float_as_uint(r9[6]), __float_as_uint(r9[7]), __float_as_uint(r9[8]));
-    for (int p = 0; p < fin.world; ++p) {  // NVLink peer stores (p == rank: local)
-      uint4* dst = reinterpret_cast<uint4*>(fin.peers[p] + peer_entry_off(par, fin.rank, B, b));
-      dst[0] = q0; dst[1] = q1; dst[2] = q2;
-    }
+    const peer::Entry ent = peer::pack_entry((int64_t)n + fin.idx_offset, key_score(key), r9);
+    for (int p = 0; p < pa.world; ++p)  // NVLink peer stores (p == rank: local)
+      peer::store_entry(pa.bufs[p] + peer::entry_off(par, pa.rank, pa.cap_pairs, pa.cap_k, b, 0), ent);
   }
   __threadfence_system();  // entries before the flag, system scope
   __syncwarp();
-  if (lane < fin.world) {
-    volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(fin.peers[lane] + kPeerFlagsOff) + par * kMaxPeers + fin.rank;
-    *flag = seq;
-  }
-  bool ok = true;
-  if (lane < fin.world) {
-    const volatile uint32_t* flag = reinterpret_cast<const volatile uint32_t*>(mine + kPeerFlagsOff) + par * kMaxPeers + lane;
-    const long long t0 = clock64();
-    while (*flag != seq) {
-      // ~20 s at 2 GHz: ranks may reach a step seconds apart (host-side skew); only a peer that never arrives
-      // is turned into an error (NaN scores, index -1, header error word) instead of a GPU that hangs forever
-      if (clock64() - t0 > 40000000000LL) { ok = false; break; }
-    }
-  }
-  ok = __all_sync(0xffffffffu, ok);
+  peer::publish_flags(pa, seq, par, lane);
+  const bool ok = __all_sync(0xffffffffu, peer::wait_flags(pa, seq, par, lane));
   __threadfence_system();
   for (int b = lane; b < B; b += 32) {
     float bv = 0.0f;
     uint32_t bo = 0;
     int64_t bi = -1;
     uint4 bq0 = make_uint4(0, 0, 0, 0), bq1 = bq0, bq2 = bq0;
-    for (int r = 0; r < fin.world; ++r) {
-      const uint4* e = reinterpret_cast<const uint4*>(mine + peer_entry_off(par, r, B, b));
+    for (int r = 0; r < pa.world; ++r) {
+      const uint4* e = reinterpret_cast<const uint4*>(mine + peer::entry_off(par, r, pa.cap_pairs, pa.cap_k, b, 0));
       const uint4 q0 = __ldcv(e);
-      const int64_t gi = (int64_t)(((u64)q0.y << 32) | q0.x);
+      const int64_t gi = peer::entry_index(q0);
       const float v = __uint_as_float(q0.z);
-      const uint32_t o = ordered_bits(v);
+      const uint32_t o = peer::ordered_bits(v);
       if (bi < 0 || o > bo || (o == bo && gi < bi)) {
         bo = o; bv = v; bi = gi; bq0 = q0; bq1 = __ldcv(e + 1); bq2 = __ldcv(e + 2);
       }
     }
-    fin.val[b] = ok ? bv : __int_as_float(0x7fc00000);
+    const float nanv = __int_as_float(0x7fc00000);
+    fin.val[b] = ok ? bv : nanv;
     fin.idx[b] = ok ? bi : -1;
     if (fin.R_best) {
-      float* o9 = fin.R_best + b * 9;
-      o9[0] = __uint_as_float(bq0.w);
-      o9[1] = __uint_as_float(bq1.x); o9[2] = __uint_as_float(bq1.y); o9[3] = __uint_as_float(bq1.z); o9[4] = __uint_as_float(bq1.w);
-      o9[5] = __uint_as_float(bq2.x); o9[6] = __uint_as_float(bq2.y); o9[7] = __uint_as_float(bq2.z); o9[8] = __uint_as_float(bq2.w);
+      float o9[9];
+      peer::unpack_rotation(bq0, bq1, bq2, o9);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) fin.R_best[b * 9 + e] = ok ? o9[e] : nanv;
     }
   }
   __syncwarp();
@@ -310,23 +277,21 @@ __device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* 
   return 1.0f / sc;
 }
 
-// ---- epilogue role, shared by the SS and TS kernels ---------------------------------------------------
+// ---- epilogue role ---------------------------------------------------
 // 4 warps, warp s = TMEM sub-partition s.  Per hypothesis pair (tile):
-//   phase A: tcgen05.ld D1 -> ReLU (modules/modules.py:68) -> fp16 -> conv2's A operand, either as the
-//            K-major core-matrix tile in shared memory (SS kernel) or straight into TMEM (TS kernel);
+//   phase A: tcgen05.ld D1 -> ReLU (modules/modules.py:68) -> fp16 -> conv2's A operand, straight into TMEM
+//            (tcgen05.st; conv2 runs in the TS form);
 //   phase B (one tile later, after conv2): tcgen05.ld D2 -> undo the pair scale, + bias -> L2 norm with
 //            F.normalize's eps (:122) -> dot with the target features (registers) -> mean over the 64
 //            positions (modules/model.py:193) -> score, and the running arg-max key (:195).
-template <bool kA2InTmem>
 __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane, uint32_t tmem, uint32_t bar0,
-                                              unsigned char* a2_smem, uint32_t tmem_a2, float* partial,
+                                              uint32_t tmem_a2, float* partial,
                                               const float* __restrict__ tgt_feat, const float* __restrict__ b2,
                                               const float* inv_ring, float* __restrict__ scores,
                                               u64* __restrict__ best_keys, int64_t N, int B,
                                               const float* __restrict__ R, int r_per_pair, const Finalize& fin) {
   const int slot = lane >> 4;            // which hypothesis of the tile
   const int pos = 16 * s + (lane & 15);  // position p*8+q of the folded plane
-  const uint32_t row = 32 * s + lane;    // TMEM lane == row of the conv2 A operand
   float b2r[kO], tg[kO];
 #pragma unroll
   for (int o = 0; o < kO; ++o) b2r[o] = __ldg(b2 + o);
@@ -397,16 +362,8 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
       const __half2 hh = __floats2half2_rn(fmaxf(__uint_as_float(r[2 * e]), 0.0f), fmaxf(__uint_as_float(r[2 * e + 1]), 0.0f));
       wq[e] = *reinterpret_cast<const uint32_t*>(&hh);
     }
-    if constexpr (kA2InTmem) {
-      tmem_st16(tmem + ((uint32_t)(32 * s) << 16) + tmem_a2 + gb * 16, wq);  // 16 TMEM columns of conv2's A operand
-      tmem_st_wait();
-    } else {
-      unsigned char* a2 = a2_smem + gb * kA2Bytes + row * 16;  // [kc][rowgroup][8][8] fp16 core matrices
-#pragma unroll
-      for (int kc = 0; kc < 4; ++kc)
-        *reinterpret_cast<uint4*>(a2 + kc * 2048) = make_uint4(wq[4 * kc], wq[4 * kc + 1], wq[4 * kc + 2], wq[4 * kc + 3]);
-      fence_proxy_async();
-    }
+    tmem_st16(tmem + ((uint32_t)(32 * s) << 16) + tmem_a2 + gb * 16, wq);  // 16 TMEM columns of conv2's A operand
+    tmem_st_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) {
@@ -436,7 +393,7 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
       last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
     }
     last = __shfl_sync(0xffffffffu, last, 0);
-    if (last && fin.world > 1) {
+    if (last && fin.peers.world > 1) {
       __threadfence();
       peer_exchange_and_merge(fin, best_keys, R, r_per_pair, N, B, lane);
       if (lane == 0) *fin.counter = 0u;

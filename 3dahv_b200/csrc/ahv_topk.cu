@@ -8,47 +8,9 @@
 // order-preserving uint32 (-0.0 canonicalised to +0.0), low word: ~index — and
 // keeping, per warp, a sorted list of 32 keys distributed one per lane that is
 // updated with a shuffle-based bitonic sort + bitonic merge.
-#include "ahv_common.cuh"
+#include "ahv_topk.cuh"
 
 namespace ahv {
-
-__device__ __forceinline__ u64 umax64(u64 a, u64 b) { return a > b ? a : b; }
-__device__ __forceinline__ u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
-
-// full bitonic sort of one key per lane, descending (lane 0 = largest)
-__device__ __forceinline__ u64 warp_sort_desc(u64 v, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
-      const bool desc = (lane & k) == 0;
-      const bool lower = (lane & j) == 0;
-      v = (lower == desc) ? umax64(v, o) : umin64(v, o);
-    }
-  }
-  return v;
-}
-// sort a bitonic sequence descending
-__device__ __forceinline__ u64 warp_bitonic_merge_desc(u64 v, int lane) {
-#pragma unroll
-  for (int j = 16; j > 0; j >>= 1) {
-    const u64 o = __shfl_xor_sync(0xffffffffu, v, j);
-    v = ((lane & j) == 0) ? umax64(v, o) : umin64(v, o);
-  }
-  return v;
-}
-// merge a descending-sorted candidate list into the descending-sorted best list
-__device__ __forceinline__ u64 warp_merge_sorted(u64 best, u64 cand_sorted, int lane) {
-  const u64 rev = __shfl_sync(0xffffffffu, cand_sorted, 31 - lane);
-  return warp_bitonic_merge_desc(umax64(best, rev), lane);
-}
-// offer one arbitrary candidate per lane
-__device__ __forceinline__ u64 warp_offer(u64 best, u64 cand, int lane) {
-  const u64 thr = __shfl_sync(0xffffffffu, best, 31);
-  if (__any_sync(0xffffffffu, cand > thr)) best = warp_merge_sorted(best, warp_sort_desc(cand, lane), lane);
-  return best;
-}
 
 constexpr int kTopkThreads = 256;
 
@@ -89,28 +51,36 @@ topk_final_kernel(const u64* __restrict__ partial, int S, int k, int64_t idx_off
   }
 }
 
-// merge [parts,B,k] lists of (value, global index)
+// merge [parts,B,k] lists of (value, global index).  Keys order by (score, low 32 bits of the index); the
+// full 64-bit index is then read back from the winning entry, so global indices >= 2^32 are reported intact
+// (only the tie order between equal scores whose indices agree in the low 32 bits is unspecified).
 __global__ void __launch_bounds__(32)
 topk_merge_kernel(const float* __restrict__ vals, const int64_t* __restrict__ idx, int parts, int B,
                   int k, float* __restrict__ out_val, int64_t* __restrict__ out_idx) {
   const int lane = threadIdx.x, b = blockIdx.x;
   const int total = parts * k;
+  auto key_at = [&](int e) -> u64 {
+    const int p = e / k, j = e % k;
+    const size_t at = ((size_t)p * B + b) * k + j;
+    const int64_t gi = idx[at];
+    return gi >= 0 ? make_key(vals[at], (uint32_t)gi) : 0ull;
+  };
   u64 best = 0;
   for (int i = 0; i < total; i += 32) {
     const int e = i + lane;
-    u64 cand = 0;
-    if (e < total) {
-      const int p = e / k, j = e % k;
-      const size_t at = ((size_t)p * B + b) * k + j;
-      const int64_t gi = idx[at];
-      if (gi >= 0) cand = make_key(vals[at], (uint32_t)gi);
-    }
-    best = warp_offer(best, cand, lane);
+    best = warp_offer(best, e < total ? key_at(e) : 0ull, lane);
   }
   if (lane < k) {
-    const bool valid = best != 0ull;
-    out_val[(size_t)b * k + lane] = valid ? key_score(best) : -INFINITY;
-    out_idx[(size_t)b * k + lane] = valid ? (int64_t)key_index(best) : (int64_t)-1;
+    float v = -INFINITY;
+    int64_t gi = -1;
+    if (best != 0ull) {
+      v = key_score(best);
+      gi = (int64_t)key_index(best);
+      for (int e = 0; e < total; ++e)
+        if (key_at(e) == best) { gi = idx[((size_t)(e / k) * B + b) * k + e % k]; break; }
+    }
+    out_val[(size_t)b * k + lane] = v;
+    out_idx[(size_t)b * k + lane] = gi;
   }
 }
 

@@ -48,9 +48,10 @@ class PeerExchange:
     """Exchange buffers for the fused sharded step (`ahv_verify_sharded`): every rank allocates one buffer
     (`ahv_peer_alloc`), sends its CUDA IPC handle to the peers (one all-gather of 64 bytes at set-up) and maps
     theirs, after which the scoring kernels talk to each other through NVLink peer memory and a verification
-    step involves no NCCL call at all.  One instance per (process group, max pairs B)."""
+    step involves no NCCL call at all.  One instance per process group; it serves any call with B <= max_pairs and
+    k <= max_k (the entry stride depends on the capacity only, so B and k may change from step to step)."""
 
-    def __init__(self, max_pairs: int, device, group=None):
+    def __init__(self, max_pairs: int, device, group=None, max_k: int = 1):
         import ctypes
 
         from . import _lib
@@ -59,7 +60,9 @@ class PeerExchange:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 8:
             raise ValueError("the peer exchange covers the GPUs of one node (<= 8)")
-        self.max_pairs = max_pairs
+        if not (1 <= max_k <= 32) or max_pairs < 1:
+            raise ValueError("max_pairs >= 1 and 1 <= max_k <= 32 expected")
+        self.max_pairs, self.max_k = max_pairs, max_k
         self.device = torch.device(device)
         lib = _lib.lib()
         self._lib = lib
@@ -71,7 +74,7 @@ class PeerExchange:
         own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         with torch.cuda.device(self.device):
-            if lib.ahv_peer_alloc(lib.ahv_peer_bytes(max_pairs), ctypes.byref(own)) != 0:
+            if lib.ahv_peer_alloc(max_pairs, max_k, ctypes.byref(own)) != 0:
                 ok = False
             elif lib.ahv_peer_export(own, handle) != 0:
                 ok = False
@@ -135,10 +138,13 @@ class ShardedVerifier:
     rank (36 B per hypothesis, replicated like the 40 KB/pair volumes) and
     scores only this rank's slice."""
 
-    def __init__(self, verifier, group=None, merge=None, score_fn=None, peer: "PeerExchange | None" = None):
+    def __init__(self, verifier, group=None, merge=None, score_fn=None, peer: "PeerExchange | None" = None,
+                 check_every: int = 0):
         self.verifier = verifier
         self.group = group
-        self.peer = peer   # fused NVLink exchange for k == 1 (else: NCCL all-gather + merge kernel)
+        self.peer = peer   # NVLink peer exchange by the kernels themselves (None: NCCL all-gather + merge kernel)
+        self.check_every = check_every   # synchronising error check (a peer that never arrived) every so many steps
+        self._steps = 0
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._merge = merge or ops.topk_merge
@@ -157,17 +163,20 @@ class ShardedVerifier:
         k = min(k, N)
         lo, hi = shard_bounds(N, self.rank, self.world)
         B = vol_src.shape[0]
-        last_lo, _ = shard_bounds(N, self.world - 1, self.world)
-        if (self.peer is not None and k == 1 and self.world > 1 and last_lo < N and B <= self.peer.max_pairs
-                and self._score_fn == self._score_local and self.verifier.math != ops.MATH_FP32):
-            # every rank has a non-empty slice: one fused call, the kernels exchange and merge the winners themselves
+        if (self.peer is not None and self.world > 1 and B <= self.peer.max_pairs and k <= self.peer.max_k
+                and self._score_fn == self._score_local):
+            # one C call: shard scoring + NVLink exchange + merge (k == 1: all inside the scoring kernel); empty
+            # slices take part in the exchange with empty lists
             v = self.verifier
             W1, W2, b2 = v._weights_on(vol_src.device)
             Rs = (R[:, lo:hi] if per_pair else R[lo:hi]).contiguous()
             vs = vol_src if vol_src.dtype == torch.bfloat16 else vol_src.float()
-            val, idx, Rb = ops.verify_sharded(vs, vol_tgt.float(), Rs, W1, W2, b2, lo, self.rank, self.world, self.peer.ptrs,
-                                              math=v.math, workspace=v._workspace(B, hi - lo, 1, vol_src.device))
-            return val[:, None], idx[:, None], Rb[:, None]
+            val, idx, Rb = ops.verify_sharded(vs, vol_tgt.float(), Rs, W1, W2, b2, lo, self.peer, k=k, math=v.math,
+                                              workspace=v._workspace(B, hi - lo, k, vol_src.device))
+            self._steps += 1
+            if self.check_every and self._steps % self.check_every == 0:
+                self.peer.check()
+            return val, idx, Rb
         if hi > lo:
             Rs = (R[:, lo:hi] if per_pair else R[lo:hi]).contiguous()
             val, idx = self._score_fn(vol_src, vol_tgt, Rs, min(k, hi - lo), lo)

@@ -242,35 +242,62 @@ def verify(vol_src, vol_tgt, R, W1, W2, b2, k: int = 1, idx_offset: int = 0, mat
     return scores, val, idx, Rb
 
 
-def verify_sharded(vol_src, vol_tgt, R, W1, W2, b2, idx_offset: int, rank: int, world: int, peer_ptrs, math: int = MATH_TC,
-                   workspace: torch.Tensor | None = None):
-    """ahv_verify_sharded: k == 1 on this rank's slice `R` of the rotation set; the scoring kernel exchanges the
-    winners with the peers' kernels through NVLink peer memory and merges.  Returns (best_val [B], best_idx [B]
-    global, R_best [B,3,3]) over the whole set, identical on every rank."""
+def _peer_array(peer):
     import ctypes
 
+    return (ctypes.c_void_p * peer.world)(*[int(p) for p in peer.ptrs])
+
+
+def verify_sharded(vol_src, vol_tgt, R, W1, W2, b2, idx_offset: int, peer, k: int = 1, math: int = MATH_TC,
+                   workspace: torch.Tensor | None = None):
+    """ahv_verify_sharded on this rank's slice `R` of the rotation set (global index = local + idx_offset); `peer`
+    is a `dist.PeerExchange`.  The kernels exchange the per-shard winners through NVLink peer memory and merge
+    them (k == 1 with tensor-core arithmetic: inside the scoring kernel; otherwise one exchange kernel after the
+    shard's top-k).  Returns (topk_val [B,k], topk_idx [B,k] global, R_best [B,k,3,3]) over the whole set,
+    identical on every rank.  An empty slice ([0,3,3]) is allowed."""
     vs = _dev(vol_src, "vol_src", vol_src.dtype if vol_src.dtype == torch.bfloat16 else torch.float32)
     vt, R = _dev(vol_tgt, "vol_tgt"), _dev(R, "R")
     W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
     B = vs.shape[0]
     per_pair = R.dim() == 4
     N = R.shape[1] if per_pair else R.shape[0]
+    if tuple(vs.shape[1:]) != (16, 8, 8, 8) or tuple(vt.shape) != (B, 16, 8, 8, 8):
+        raise ValueError("vol_src / vol_tgt must be [B,16,8,8,8]")
+    if B > peer.max_pairs or k > peer.max_k:
+        raise ValueError(f"exchange buffer holds {peer.max_pairs} pairs x top-{peer.max_k}; got B={B}, k={k}")
     dev = vs.device
-    val = torch.empty(B, device=dev, dtype=torch.float32)
-    idx = torch.empty(B, device=dev, dtype=torch.int64)
-    Rb = torch.empty(B, 3, 3, device=dev, dtype=torch.float32)
-    need = workspace_bytes(B, N, 1)
+    val = torch.empty(B, k, device=dev, dtype=torch.float32)
+    idx = torch.empty(B, k, device=dev, dtype=torch.int64)
+    Rb = torch.empty(B, k, 3, 3, device=dev, dtype=torch.float32)
+    need = workspace_bytes(B, N, k)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
-    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
     base = base_coords(dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().ahv_verify_sharded(
-            vs.data_ptr(), VOL_BF16 if vs.dtype == torch.bfloat16 else VOL_F32, vt.data_ptr(), R.data_ptr(), int(per_pair),
-            W1.data_ptr(), W2.data_ptr(), b2.data_ptr(), base.data_ptr(), val.data_ptr(), idx.data_ptr(), Rb.data_ptr(),
-            idx_offset, B, N, math, workspace.data_ptr(), workspace.numel() * workspace.element_size(), rank, world, arr,
-            _stream(vs)), "ahv_verify_sharded")
+            vs.data_ptr(), VOL_BF16 if vs.dtype == torch.bfloat16 else VOL_F32, vt.data_ptr(), R.data_ptr() if N else None,
+            int(per_pair), W1.data_ptr(), W2.data_ptr(), b2.data_ptr(), base.data_ptr(), val.data_ptr(), idx.data_ptr(),
+            Rb.data_ptr(), k, idx_offset, B, N, math, workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+            peer.rank, peer.world, _peer_array(peer), peer.max_pairs, peer.max_k, _stream(vs)), "ahv_verify_sharded")
     return val, idx, Rb
+
+
+def topk_exchange(val, idx, R, idx_offset: int, peer):
+    """ahv_topk_exchange: this shard's [B,k] list (global indices, -1 = empty) -> the whole set's top-k on every
+    rank, with the winning rotations.  Returns (topk_val [B,k], topk_idx [B,k], R_best [B,k,3,3])."""
+    v, i, R = _dev(val, "val"), _dev(idx, "idx", torch.int64), _dev(R, "R")
+    B, k = v.shape
+    per_pair = R.dim() == 4
+    N = R.shape[1] if per_pair else R.shape[0]
+    dev = v.device
+    out_v = torch.empty(B, k, device=dev, dtype=torch.float32)
+    out_i = torch.empty(B, k, device=dev, dtype=torch.int64)
+    Rb = torch.empty(B, k, 3, 3, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ahv_topk_exchange(v.data_ptr(), i.data_ptr(), R.data_ptr() if N else None, int(per_pair), idx_offset,
+                                                N, B, k, out_v.data_ptr(), out_i.data_ptr(), Rb.data_ptr(), peer.rank, peer.world,
+                                                _peer_array(peer), peer.max_pairs, peer.max_k, _stream(v)), "ahv_topk_exchange")
+    return out_v, out_i, Rb
 
 
 def topk(scores: torch.Tensor, k: int, idx_offset: int = 0):
@@ -312,11 +339,35 @@ def gather_rotations(R: torch.Tensor, idx: torch.Tensor, idx_offset: int = 0) ->
     return out
 
 
+class HostSession:
+    """Caller-owned device scratch of the host-buffer entry (`ahv_host_session_create`), reused across calls."""
+
+    def __init__(self, device="cuda"):
+        import ctypes
+
+        self.device = torch.device(device)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ahv_host_session_create(ctypes.byref(h)), "ahv_host_session_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None) is not None:
+            with torch.cuda.device(self.device):
+                _lib.lib().ahv_host_session_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+
 def predict_host(vol_src, vol_tgt, R, W1, W2, b2, k: int = 1, math: int = MATH_TC, return_scores: bool = False,
-                 device="cuda"):
-    """ahv_predict_host: HOST tensors in, HOST results out (copies inside)."""
+                 device="cuda", session: HostSession | None = None, idx_offset: int = 0, peer=None):
+    """HOST tensors in, HOST results out (copies inside the call): `ahv_predict_host`, or with a `session`
+    (reused device scratch), bf16 source volumes, an index offset or a `peer` exchange (`R` = this rank's slice
+    of a sharded rotation set; results over the whole set) `ahv_predict_host_ex`."""
     f = torch.float32
-    vs, vt = vol_src.to(f).contiguous(), vol_tgt.to(f).contiguous()
+    bf16 = vol_src.dtype == torch.bfloat16
+    vs, vt = (vol_src if bf16 else vol_src.to(f)).contiguous(), vol_tgt.to(f).contiguous()
     Rc = R.to(f).contiguous()
     if vs.is_cuda or vt.is_cuda or Rc.is_cuda:
         raise RuntimeError("predict_host takes host tensors")
@@ -330,10 +381,27 @@ def predict_host(vol_src, vol_tgt, R, W1, W2, b2, k: int = 1, math: int = MATH_T
     Rb = torch.empty(B, k, 3, 3, dtype=f)
     base = base_coords()
     device = torch.device(device)
+    extended = session is not None or bf16 or idx_offset != 0 or peer is not None
     with torch.cuda.device(device):
-        st = _lib.lib().ahv_predict_host(
-            vs.data_ptr(), vt.data_ptr(), Rc.data_ptr(), int(per_pair), W1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(),
-            base.data_ptr(), scores.data_ptr() if scores is not None else None, val.data_ptr(), idx.data_ptr(),
-            Rb.data_ptr(), k, B, N, math, torch.cuda.current_stream(device).cuda_stream)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        if not extended:
+            st = _lib.lib().ahv_predict_host(
+                vs.data_ptr(), vt.data_ptr(), Rc.data_ptr(), int(per_pair), W1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(),
+                base.data_ptr(), scores.data_ptr() if scores is not None else None, val.data_ptr(), idx.data_ptr(),
+                Rb.data_ptr(), k, B, N, math, stream)
+        else:
+            own = session is None
+            if own:
+                session = HostSession(device)
+            try:
+                st = _lib.lib().ahv_predict_host_ex(
+                    session.handle, vs.data_ptr(), VOL_BF16 if bf16 else VOL_F32, vt.data_ptr(), Rc.data_ptr(), int(per_pair),
+                    W1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), base.data_ptr(),
+                    scores.data_ptr() if scores is not None else None, val.data_ptr(), idx.data_ptr(), Rb.data_ptr(), k,
+                    idx_offset, B, N, math, peer.rank if peer else 0, peer.world if peer else 1,
+                    _peer_array(peer) if peer else None, peer.max_pairs if peer else 0, peer.max_k if peer else 0, stream)
+            finally:
+                if own:
+                    session.close()
     _lib.check(st, "ahv_predict_host")
     return scores, val, idx, Rb

@@ -130,16 +130,14 @@ class GraphedVerifier:
         self.vol_tgt = torch.zeros(B, 16, 8, 8, 8, device=dev)
         self.R = torch.eye(3, device=dev).repeat(*((B, N) if per_pair_R else (N,)), 1, 1).contiguous()
         self.k = min(k, N)
-        if peer is not None and self.k != 1:
-            raise ValueError("the fused peer exchange selects the arg-max (k = 1)")
 
         def run():
             if peer is None:
                 return self.v.score(self.vol_src, self.vol_tgt, self.R, k=self.k, return_scores=False, idx_offset=idx_offset)
             W1, W2, b2 = self.v._weights_on(dev)
-            val, idx, Rb = ops.verify_sharded(self.vol_src, self.vol_tgt, self.R, W1, W2, b2, idx_offset, peer.rank, peer.world,
-                                              peer.ptrs, math=self.v.math, workspace=self.v._workspace(B, N, 1, dev))
-            return VerifyResult(None, val[:, None], idx[:, None], Rb[:, None])
+            val, idx, Rb = ops.verify_sharded(self.vol_src, self.vol_tgt, self.R, W1, W2, b2, idx_offset, peer, k=self.k,
+                                              math=self.v.math, workspace=self.v._workspace(B, N, self.k, dev))
+            return VerifyResult(None, val, idx, Rb)
 
         stream = torch.cuda.Stream(device=dev)
         stream.wait_stream(torch.cuda.current_stream(dev))

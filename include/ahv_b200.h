@@ -6,8 +6,9 @@
  * cites the reference code it replaces.  All pointers are DEVICE pointers to
  * contiguous, 16-byte-aligned buffers owned by the caller unless the name ends
  * in `_host`.  `stream` is a `cudaStream_t` passed as `void*`.  Calls are
- * asynchronous and stream-ordered, allocate nothing (ahv_predict_host and the
- * explicit ahv_peer_alloc aside), keep no global state, and are CUDA-graph
+ * asynchronous and stream-ordered, allocate nothing (the `_host` entries, whose
+ * scratch lives in a caller-owned session, and the explicit ahv_peer_alloc aside),
+ * keep no global state, read no environment variables, and are CUDA-graph
  * capturable.  Return value: 0 on success, negative `AHV_E*`.
  * There is NO CPU fallback: on a device that is not sm_100 the compute entry
  * points return AHV_ENOTSUP.
@@ -31,7 +32,7 @@ extern "C" {
 #define AHV_API
 #endif
 
-#define AHV_VERSION 100 /* 0.1.0 */
+#define AHV_VERSION 200 /* 0.2.0 */
 
 enum {
   AHV_OK = 0,
@@ -157,38 +158,66 @@ AHV_API int ahv_topk_merge(const float* vals, const int64_t* idx, int parts, int
 AHV_API int ahv_gather_rotations(const float* R, int r_per_pair, const int64_t* idx, int64_t idx_offset,
                          int B, int64_t N, int k, float* R_out, void* stream);
 
-/* Hypothesis set sharded over the GPUs of one NVSwitch node (the reference is single GPU).
- * ahv_verify_sharded is ahv_verify with k == 1 on THIS rank's slice of the rotation set (global index =
- * local + idx_offset) whose scoring kernel also performs the exchange: its last CTA writes this shard's
- * winners (score, global index, rotation) into every peer's exchange buffer over NVLink, waits for the
- * peers' flags and merges (higher score, ties -> lowest global index), so best_val/best_idx/R_best are the
- * result over the WHOLE set, identical on every rank, with no NCCL call and no merge launch.
- * peers[r] = rank r's exchange buffer as mapped in this process (peers[rank] = own).  Every rank must make
- * the same sequence of calls with the same B.  Buffers: ahv_peer_alloc (zeroed cudaMalloc of
- * ahv_peer_bytes(B)), ahv_peer_export -> 64-byte CUDA IPC handle to send to the peers, ahv_peer_open on
- * their side; ahv_peer_close / ahv_peer_free to release.  AHV_MATH_TC / AHV_MATH_TC_F16GATHER only.
- * A peer that never reaches a step is waited for ~20 s (device clock), then reported as above. */
-AHV_API size_t ahv_peer_bytes(int B);
-AHV_API int ahv_peer_alloc(size_t bytes, void** ptr);
+/* Hypothesis set sharded over the GPUs of one NVSwitch node (the reference is single GPU,
+ * batch 1, test_co3d.py:133).  Every rank scores ITS slice of the rotation set (global index = local +
+ * idx_offset) for all pairs; the per-shard winners are exchanged through NVLink peer memory by the kernels
+ * themselves, so the step contains no NCCL call, no merge launch and no winner gather, is identical on every
+ * rank bit for bit (score descending, ties -> lowest global index) and CUDA-graph capturable.
+ *
+ * Exchange buffers: one per rank, ahv_peer_alloc(max_pairs, max_k) (a zeroed cudaMalloc whose header records
+ * the capacity; the entry stride depends on the capacity only, so calls with different B and k may follow one
+ * another on one buffer); ahv_peer_export -> 64-byte CUDA IPC handle to send to the peers, ahv_peer_open on
+ * their side; ahv_peer_close / ahv_peer_free to release.  peers[r] = rank r's buffer as mapped in this process
+ * (peers[rank] = own); peer_max_pairs / peer_max_k = the capacity all buffers were allocated with (calls with
+ * B > peer_max_pairs or k > peer_max_k are rejected with AHV_EINVAL).  Every rank must make the same sequence
+ * of exchanging calls.  A peer that never reaches a step is waited for ~20 s (device clock); that step then
+ * returns NaN scores, index -1 and NaN rotations, and ahv_peer_status reports it.
+ *
+ * ahv_verify_sharded = ahv_verify on this rank's slice + the exchange: topk_val/topk_idx [B,k], R_best
+ * [B,k,3,3] (or NULL) are the result over the WHOLE set.  With k == 1 and tensor-core arithmetic the scoring
+ * kernel's last CTA performs the exchange itself (two launches per step, as on one GPU); otherwise the
+ * shard's top-k is followed by one exchange kernel (ahv_topk_exchange, also callable on its own: val/idx [B,k]
+ * = this shard's list with global indices, -1 = empty slot; R = this shard's rotations).  An empty slice
+ * (N == 0) is allowed when world > 1.  idx_offset + N must not exceed 2^32. */
+AHV_API size_t ahv_peer_bytes(int max_pairs, int max_k);
+AHV_API int ahv_peer_alloc(int max_pairs, int max_k, void** ptr);
 AHV_API int ahv_peer_free(void* ptr);
 AHV_API int ahv_peer_export(void* ptr, unsigned char* handle64);
 AHV_API int ahv_peer_open(const unsigned char* handle64, void** ptr);
 AHV_API int ahv_peer_close(void* ptr);
 /* Synchronising read of this rank's exchange header: exchanges completed, and whether one of them timed out
- * waiting for a peer (that step returned NaN scores and index -1). */
+ * waiting for a peer. */
 AHV_API int ahv_peer_status(const void* own, unsigned* exchanges_done, unsigned* timed_out);
+/* Synchronising read of the capacity recorded in a (own or mapped) exchange buffer. */
+AHV_API int ahv_peer_capacity(const void* buf, int* max_pairs, int* max_k);
+AHV_API int ahv_topk_exchange(const float* val, const int64_t* idx, const float* R, int r_per_pair, int64_t idx_offset,
+                              int64_t N, int B, int k, float* out_val, int64_t* out_idx, float* R_best, int rank,
+                              int world, void* const* peers, int peer_max_pairs, int peer_max_k, void* stream);
 AHV_API int ahv_verify_sharded(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
-                               const float* W1, const float* W2, const float* b2, const float* base, float* best_val,
-                               int64_t* best_idx, float* R_best, int64_t idx_offset, int B, int64_t N, int math_mode,
-                               void* workspace, size_t workspace_bytes, int rank, int world, void* const* peers,
-                               void* stream);
+                               const float* W1, const float* W2, const float* b2, const float* base, float* topk_val,
+                               int64_t* topk_idx, float* R_best, int k, int64_t idx_offset, int B, int64_t N,
+                               int math_mode, void* workspace, size_t workspace_bytes, int rank, int world,
+                               void* const* peers, int peer_max_pairs, int peer_max_k, void* stream);
 
-/* Convenience entry taking HOST buffers (pageable or pinned): copies the
- * inputs to the device, computes the target features, runs ahv_score and
- * copies the selection back; synchronises `stream` before returning.  This is
- * the call a non-PyTorch host (ctypes / cgo / JNI) would bind. vol_src_host and
- * vol_tgt_host [B,16,8,8,8] fp32; R_host as R above; outputs as above (scores
- * may be NULL).  Allocates and frees its own device scratch. */
+/* Entries taking HOST buffers (pageable or pinned) - what a non-PyTorch host (ctypes / cgo / JNI) binds: copy
+ * the inputs to the device, run the whole verification step (ahv_verify, or ahv_verify_sharded when world > 1)
+ * and copy the selection back; `stream` is synchronised before returning.  vol_tgt_host [B,16,8,8,8] fp32;
+ * R_host as R above; outputs as above (scores_host may be NULL and must be NULL when world > 1).
+ *
+ * ahv_predict_host_ex takes fp32 or bf16 source volumes (vol_dtype), an index offset and the sharding
+ * arguments of ahv_verify_sharded (world == 1: peers may be NULL), and keeps its device scratch in a
+ * caller-owned session (ahv_host_session_create on the current device; grown on demand, reused across calls,
+ * one call at a time per session).  ahv_predict_host is the one-shot form: fp32, one GPU, a temporary session
+ * per call.  Neither touches process-global state. */
+typedef struct ahv_host_session ahv_host_session;
+AHV_API int ahv_host_session_create(ahv_host_session** session);
+AHV_API int ahv_host_session_destroy(ahv_host_session* session);
+AHV_API int ahv_predict_host_ex(ahv_host_session* session, const void* vol_src_host, int vol_dtype,
+                                const float* vol_tgt_host, const float* R_host, int r_per_pair, const float* W1_host,
+                                const float* W2_host, const float* b2_host, const float* base_host, float* scores_host,
+                                float* topk_val_host, int64_t* topk_idx_host, float* R_best_host, int k,
+                                int64_t idx_offset, int B, int64_t N, int math_mode, int rank, int world,
+                                void* const* peers, int peer_max_pairs, int peer_max_k, void* stream);
 AHV_API int ahv_predict_host(const float* vol_src_host, const float* vol_tgt_host, const float* R_host,
                      int r_per_pair, const float* W1_host, const float* W2_host,
                      const float* b2_host, const float* base_host, float* scores_host,

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(ahv):
     for s in declared_symbols():
         assert hasattr(lib, s), s
     assert set(ahv._lib.SIGNATURES) == set(declared_symbols())
-    assert lib.ahv_version() == 100
+    assert lib.ahv_version() == 200
 
 
 def test_status_strings(ahv):

@@ -42,7 +42,7 @@ def _top1_ok(scores_gpu, ref_scores, idx_gpu, tol):
 def test_library_loaded_and_device_is_sm100(ahv):
     dev = _dev()
     assert torch.cuda.get_device_capability(dev)[0] == 10
-    assert ahv._lib.lib().ahv_version() == 100
+    assert ahv._lib.lib().ahv_version() == 200
 
 
 def test_so3_from_normals_bit_exact(ahv, golden, oracle):
