@@ -25,6 +25,7 @@ SIGNATURES = {
     "ahv_so3_from_normals": (_i, [_vp, _vp, _i64, _vp]),
     "ahv_so3_sample": (_i, [_u64, _i64, _vp, _i64, _vp]),
     "ahv_so3_grid": (_i, [_i64, _i64, _vp, _i64, _vp]),
+    "ahv_so3_perturb": (_i, [_vp, _i64, _i, ctypes.c_float, _u64, _vp, _vp]),
     "ahv_rotate_volume": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _vp]),
     "ahv_rotate_volume_backward": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _vp]),
     "ahv_score_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
@@ -32,6 +33,9 @@ SIGNATURES = {
     "ahv_workspace_bytes": (_sz, [_i, _i64, _i]),
     "ahv_score": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i64, _i, _vp, _sz, _vp]),
     "ahv_verify": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i64, _i, _vp, _sz, _vp]),
+    "ahv_refine_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
+    "ahv_refine": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                        _i, _i64, _i, _vp, _sz, _vp]),
     "ahv_topk": (_i, [_vp, _i, _i64, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "ahv_topk_merge": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "ahv_gather_rotations": (_i, [_vp, _i, _vp, _i64, _i, _i64, _i, _vp, _vp]),

@@ -61,6 +61,14 @@ AHV_API int ahv_so3_grid(int64_t n_total, int64_t first_index, float* R, int64_t
   return launch_so3_grid(n_total, first_index, R, count, (cudaStream_t)stream);
 }
 
+AHV_API int ahv_so3_perturb(const float* R_center, int64_t n, int m, float max_angle_deg, uint64_t seed, float* R_out,
+                            void* stream) {
+  if (n < 0 || m < 1 || !(max_angle_deg >= 0.0f) || max_angle_deg > 180.0f || (n > 0 && (!R_center || !R_out))) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_so3_perturb(R_center, n, m, max_angle_deg, seed, R_out, (cudaStream_t)stream);
+}
+
 AHV_API int ahv_rotate_volume(const float* vol, int vol_per_rotation, const float* R, const float* base,
                       float* out, int64_t n, void* stream) {
   if (n < 0 || (n > 0 && (!vol || !R || !base || !out))) return AHV_EINVAL;
@@ -212,6 +220,35 @@ AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt,
   if (R_best)
     st = launch_gather_rotations(R, r_per_pair != 0, topk_idx, idx_offset, B, N, k, R_best, s);
   return st;
+}
+
+// ---- two-pass selection: dense set -> top-k -> local refinement (BASELINE config 4; extension) -----------
+AHV_API size_t ahv_refine_workspace_bytes(int B, int64_t N, int k, int m) {
+  if (B < 0 || N < 0 || k < 1 || k > kMaxK || m < 1) return 0;
+  return ahv_workspace_bytes(B, N, k) + ahv_workspace_bytes(B, (int64_t)k * m, 1);
+}
+
+AHV_API int ahv_refine(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
+                       const float* W1, const float* W2, const float* b2, const float* base, int k, int m,
+                       float max_angle_deg, uint64_t seed, float* first_val, int64_t* first_idx, float* first_R,
+                       float* cand, float* best_val, int64_t* best_idx, float* R_best, int B, int64_t N,
+                       int math_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 1 || N < 1 || k < 1 || k > kMaxK || k > N || m < 1 || (int64_t)k * m > 0x7fffffffLL) return AHV_EINVAL;
+  if (!first_val || !first_idx || !first_R || !cand || !best_val || !best_idx || !workspace) return AHV_EINVAL;
+  if (!aligned16(cand)) return AHV_EINVAL;
+  const size_t ws1 = ahv_workspace_bytes(B, N, k), ws2 = ahv_workspace_bytes(B, (int64_t)k * m, 1);
+  if (workspace_bytes < ws1 + ws2) return AHV_EWORKSPACE;
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  // pass 1: the whole set, top-k and their rotations
+  int st = ahv_verify(vol_src, vol_dtype, vol_tgt, R, r_per_pair, W1, W2, b2, base, nullptr, first_val, first_idx, first_R, k,
+                      0, B, N, math_mode, ws, ws1, stream);
+  if (st != AHV_OK) return st;
+  // candidates: m rotations within max_angle_deg of each of the B*k winners (index 0 = the winner itself)
+  st = ahv_so3_perturb(first_R, (int64_t)B * k, m, max_angle_deg, seed, cand, stream);
+  if (st != AHV_OK) return st;
+  // pass 2: per-pair candidate sets [B, k*m], arg-max
+  return ahv_verify(vol_src, vol_dtype, vol_tgt, cand, 1, W1, W2, b2, base, nullptr, best_val, best_idx, R_best, 1, 0, B,
+                    (int64_t)k * m, math_mode, ws + ws1, ws2, stream);
 }
 
 // ---- hypothesis set sharded over the GPUs of one node: winners exchanged through peer memory -------------

@@ -88,6 +88,8 @@ namespace peer { struct Args; }  // ahv_peer.cuh
 int launch_so3_from_normals(const float* normals, float* R, int64_t n, cudaStream_t s);
 int launch_so3_sample(uint64_t seed, int64_t first, float* R, int64_t n, cudaStream_t s);
 int launch_so3_grid(int64_t n_total, int64_t first, float* R, int64_t count, cudaStream_t s);
+int launch_so3_perturb(const float* centers, int64_t n, int m, float max_angle_deg, uint64_t seed, float* out,
+                       cudaStream_t s);
 int launch_rotate_volume(const float* vol, int per_rot, const float* R, const float* base,
                          float* out, int64_t n, cudaStream_t s);
 int launch_rotate_volume_bwd(const float* grad_out, int per_rot, const float* R, const float* base,

@@ -105,6 +105,59 @@ __global__ void __launch_bounds__(256) so3_grid_kernel(int64_t n_total, int64_t 
   for (int e = 0; e < 9; ++e) R[t * 9 + e] = m[e];
 }
 
+// Local refinement set around given rotations (extension, BASELINE config 4 "top-k refinement pass"; the
+// reference has no refinement): out[i,0] = center[i]; out[i,j>0] = dR(i,j) @ center[i] where dR is a Haar
+// rotation (Philox counter i*m+j, same normal -> quaternion map as the sampler) whose rotation ANGLE theta in
+// [0,pi] is rescaled to theta/pi * max_angle about the same axis.  Restated in oracle/ahv_oracle.c.
+__global__ void __launch_bounds__(256) so3_perturb_kernel(const float* __restrict__ centers, int64_t n, int m,
+                                                          float max_angle_rad, uint64_t seed, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * m) return;
+  const int64_t i = t / m;
+  const int j = (int)(t - i * m);
+  float c[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) c[e] = __ldg(centers + i * 9 + e);
+  float* o = out + t * 9;
+  if (j == 0) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) o[e] = c[e];
+    return;
+  }
+  const uint4 u = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)((uint64_t)t >> 32), 0x7065u, 0x7274u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float inv32 = 2.3283064365386963e-10f;
+  const float u0 = ((float)(u.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (float)u.y * inv32;
+  const float u2 = ((float)(u.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (float)u.w * inv32;
+  const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  const float qa = r0 * c0, qb = r0 * s0, qc = r1 * c1, qd = r1 * s1;  // Haar quaternion, unnormalised
+  const float vn = sqrtf(qb * qb + qc * qc + qd * qd);
+  const float theta = 2.0f * atan2f(vn, fabsf(qa));                    // rotation angle in [0, pi]
+  const float phi = theta * (max_angle_rad * 0.318309886183790672f);   // rescaled into the cone
+  float sh, ch;
+  sincosf(0.5f * phi, &sh, &ch);
+  const float k = vn > 0.0f ? sh / vn : 0.0f;
+  float d[9];
+  quat_to_matrix_exact(ch, k * qb, k * qc, k * qd, d);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      o[r * 3 + q] = fmaf(d[r * 3 + 2], c[6 + q], fmaf(d[r * 3 + 1], c[3 + q], d[r * 3] * c[q]));
+}
+
+int launch_so3_perturb(const float* centers, int64_t n, int m, float max_angle_deg, uint64_t seed, float* out,
+                       cudaStream_t s) {
+  if (n * m == 0) return AHV_OK;
+  so3_perturb_kernel<<<(unsigned)((n * m + 255) / 256), 256, 0, s>>>(centers, n, m, max_angle_deg * 0.017453292519943295f,
+                                                                    seed, out);
+  AHV_CUDA_OK(cudaGetLastError());
+  return AHV_OK;
+}
+
 int launch_so3_grid(int64_t n_total, int64_t first, float* R, int64_t count, cudaStream_t s) {
   if (count == 0) return AHV_OK;
   so3_grid_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(n_total, first, R, count);

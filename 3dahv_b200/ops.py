@@ -78,6 +78,19 @@ def grid_rotations(n_total: int, first_index: int = 0, count: int | None = None,
     return R
 
 
+def perturb_rotations(R_center: torch.Tensor, m: int, max_angle_deg: float, seed: int = 0) -> torch.Tensor:
+    """ahv_so3_perturb: [...,3,3] centres -> [...,m,3,3] rotations within `max_angle_deg` of them (index 0 = the
+    centre itself)."""
+    c = _dev(R_center, "R_center")
+    lead = c.shape[:-2]
+    n = c.numel() // 9
+    out = torch.empty(*lead, m, 3, 3, device=c.device, dtype=torch.float32)
+    with torch.cuda.device(c.device):
+        _lib.check(_lib.lib().ahv_so3_perturb(c.data_ptr(), n, m, float(max_angle_deg), seed & (2**64 - 1), out.data_ptr(),
+                                              _stream(c)), "ahv_so3_perturb")
+    return out
+
+
 def rotate_volume(volume: torch.Tensor, R: torch.Tensor) -> torch.Tensor:
     """utils.rotate_volume (utils.py:113-131) on the GPU.  `volume` is
     [16,8,8,8] (one volume under n rotations) or [n,16,8,8,8] (one per rotation)."""
@@ -240,6 +253,45 @@ def verify(vol_src, vol_tgt, R, W1, W2, b2, k: int = 1, idx_offset: int = 0, mat
             workspace.numel() * workspace.element_size(), _stream(vs))
     _lib.check(st, "ahv_verify")
     return scores, val, idx, Rb
+
+
+def refine(vol_src, vol_tgt, R, W1, W2, b2, k: int = 32, m: int = 64, max_angle_deg: float = 5.0, seed: int = 0,
+           math: int = MATH_TC, workspace: torch.Tensor | None = None, out=None):
+    """ahv_refine: top-k over the set, m local candidates around each winner, arg-max over them - one C call, no
+    torch ops, CUDA-graph capturable (pass `out` = the tuple a previous call returned to reuse its buffers).
+    Returns (first_val [B,k], first_idx [B,k], first_R [B,k,3,3], cand [B,k*m,3,3], best_val [B], best_idx [B],
+    R_best [B,3,3], workspace)."""
+    if vol_src.dtype == torch.bfloat16:
+        vs, vdt = _dev(vol_src, "vol_src", torch.bfloat16), VOL_BF16
+    else:
+        vs, vdt = _dev(vol_src, "vol_src"), VOL_F32
+    vt, R = _dev(vol_tgt, "vol_tgt"), _dev(R, "R")
+    B = vs.shape[0]
+    per_pair = R.dim() == 4
+    N = R.shape[1] if per_pair else R.shape[0]
+    if tuple(vs.shape[1:]) != (16, 8, 8, 8) or tuple(vt.shape) != (B, 16, 8, 8, 8):
+        raise ValueError("vol_src / vol_tgt must be [B,16,8,8,8]")
+    if not (1 <= k <= min(32, N)) or m < 1:
+        raise ValueError("1 <= k <= min(32, N) and m >= 1 expected")
+    W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
+    dev = vs.device
+    if out is None:
+        f = dict(device=dev, dtype=torch.float32)
+        out = (torch.empty(B, k, **f), torch.empty(B, k, device=dev, dtype=torch.int64), torch.empty(B, k, 3, 3, **f),
+               torch.empty(B, k * m, 3, 3, **f), torch.empty(B, **f), torch.empty(B, device=dev, dtype=torch.int64),
+               torch.empty(B, 3, 3, **f))
+    fv, fi, fR, cand, bv, bi, bR = out[:7]
+    need = int(_lib.lib().ahv_refine_workspace_bytes(B, N, k, m))
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    base = base_coords(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ahv_refine(
+            vs.data_ptr(), vdt, vt.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+            base.data_ptr(), k, m, float(max_angle_deg), seed & (2**64 - 1), fv.data_ptr(), fi.data_ptr(), fR.data_ptr(),
+            cand.data_ptr(), bv.data_ptr(), bi.data_ptr(), bR.data_ptr(), B, N, math, workspace.data_ptr(),
+            workspace.numel() * workspace.element_size(), _stream(vs)), "ahv_refine")
+    return fv, fi, fR, cand, bv, bi, bR, workspace
 
 
 def _peer_array(peer):

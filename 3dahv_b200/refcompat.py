@@ -5,7 +5,9 @@
     random_rotations(n)                                             pytorch3d (modules/model.py:184)
     verify(feature_aligner, img_feat_src, img_feat_tgt, sampled_R)  the idiom modules/model.py:186-196
 
-All of them run on the GPU through lib3dahv_b200 and raise on CPU tensors.
+All of them run on the GPU through lib3dahv_b200 and raise on CPU tensors.  `rotate_volume` and `forward_3d2d`
+stay differentiable when autograd is recording and their inputs require a gradient (the reference trains through
+them, modules/model.py:53-56); otherwise they are single kernels with no autograd graph.
 """
 from __future__ import annotations
 
@@ -22,15 +24,17 @@ def rotate_volume(volume: torch.Tensor, rotation_matrix: torch.Tensor, padding_m
         raise NotImplementedError("the reference only ever uses padding_mode='zeros' (utils.py:113)")
     if volume.dim() != 5:
         raise ValueError("volume must be [N,16,8,8,8]")
-    if volume.stride(0) == 0 or volume.shape[0] == 1:
-        return ops.rotate_volume(volume[0].float(), rotation_matrix.float())
-    return ops.rotate_volume(volume.float(), rotation_matrix.float())
+    shared = volume.stride(0) == 0 or volume.shape[0] == 1
+    v = volume[0].float() if shared else volume.float()
+    if torch.is_grad_enabled() and volume.requires_grad:   # the reference back-propagates through this call (modules/model.py:53)
+        from . import training
+        return training.rotate_volume(v, rotation_matrix.float())
+    return ops.rotate_volume(v, rotation_matrix.float())
 
 
 def forward_3d2d(feature_aligner, img_feat: torch.Tensor) -> torch.Tensor:
     """Feature_Aligner.forward_3d2d (modules/modules.py:112-124): [M,16,8,8,8] -> [M,32,64]."""
-    head = feature_aligner.feature_embedding_2d
-    return ops.forward_3d2d(img_feat.float(), head[0].weight.detach(), head[2].weight.detach(), head[2].bias.detach())
+    return feature_aligner.forward_3d2d(img_feat)   # kernel for inference, differentiable formulation under autograd
 
 
 def random_rotations(n: int, dtype=None, device=None) -> torch.Tensor:

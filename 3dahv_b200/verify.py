@@ -97,17 +97,18 @@ class HypothesisVerifier:
 
     @torch.no_grad()
     def refine(self, vol_src, vol_tgt, R, k: int = 32, m: int = 64, max_angle_deg: float = 5.0, seed: int = 0):
-        """Two-pass selection (BASELINE config 4; extension): score the set, keep
-        the top-k, score m local perturbations of each, return the best."""
-        from . import so3
-
-        tgt = self.target_features(vol_tgt)
-        first = self.score(vol_src, vol_tgt, R, k=k, return_scores=False, tgt_feat=tgt)
-        cand = so3.perturb_rotations(first.R_best, m, max_angle_deg, seed)      # [B,k,m,3,3]
-        B = vol_src.shape[0]
-        cand = cand.reshape(B, -1, 3, 3).contiguous()
-        second = self.score(vol_src, vol_tgt, cand, k=1, return_scores=False, tgt_feat=tgt)
-        return second.R_best[:, 0], second.topk_val[:, 0], first, cand
+        """Two-pass selection (BASELINE config 4; extension): score the set, keep the top-k, score m local
+        perturbations of each, return the best - one C call (`ahv_refine`), no torch ops in between.
+        Returns (R_best [B,3,3], score [B], first pass as a VerifyResult, candidate set [B,k*m,3,3])."""
+        dev = vol_src.device
+        W1, W2, b2 = self._weights_on(dev)
+        per_pair = R.dim() == 4
+        k = min(k, R.shape[1] if per_pair else R.shape[0])
+        vs = vol_src if vol_src.dtype == torch.bfloat16 else vol_src.float()
+        fv, fi, fR, cand, bv, bi, bR, self._ws_refine = ops.refine(vs, vol_tgt.float(), R, W1, W2, b2, k=k, m=m,
+                                                                  max_angle_deg=max_angle_deg, seed=seed, math=self.math,
+                                                                  workspace=getattr(self, "_ws_refine", None))
+        return bR, bv, VerifyResult(None, fv, fi, fR), cand
 
 
 class GraphedVerifier:

@@ -79,6 +79,14 @@ AHV_API int ahv_so3_sample(uint64_t seed, int64_t first_index, float* R, int64_t
  * matrices.  Evaluated in fp64, rounded once: bit-identical to oracle/ahv_oracle.c. */
 AHV_API int ahv_so3_grid(int64_t n_total, int64_t first_index, float* R, int64_t count, void* stream);
 
+/* Local refinement set (extension, BASELINE config 4 "top-k refinement pass"; the reference has none):
+ * R_out[i,0] = R_center[i]; R_out[i,j] = dR(i,j) @ R_center[i] for 0 < j < m, dR a Haar rotation (Philox
+ * counter i*m+j keyed by seed) whose angle is rescaled from [0,pi] to [0,max_angle_deg] about its axis.
+ * R_center [n,3,3] -> R_out [n,m,3,3].  Restated (to rounding of the transcendental functions) in
+ * oracle/ahv_oracle.c. */
+AHV_API int ahv_so3_perturb(const float* R_center, int64_t n, int m, float max_angle_deg, uint64_t seed, float* R_out,
+                            void* stream);
+
 /* utils.rotate_volume (utils.py:113-131): F.affine_grid + F.grid_sample
  * (trilinear, zeros padding, align_corners=False), materialised.
  * vol: [16,8,8,8] when vol_per_rotation==0 (the stride-0 `expand` of
@@ -143,6 +151,20 @@ AHV_API int ahv_verify(const void* vol_src, int vol_dtype, const float* vol_tgt,
                        const float* W1, const float* W2, const float* b2, const float* base, float* scores,
                        float* topk_val, int64_t* topk_idx, float* R_best, int k, int64_t idx_offset, int B,
                        int64_t N, int math_mode, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Two-pass selection in one call (extension, BASELINE config 4 "dense SO(3) grid with top-k refinement pass";
+ * the reference stops at torch.max over its random set, test_linemod.py:62-63): ahv_verify over the N
+ * rotations keeping the top k (first_val/first_idx [B,k], first_R [B,k,3,3]); ahv_so3_perturb builds m local
+ * candidates around every winner (cand [B,k*m,3,3], caller-provided, 16-byte aligned; candidate j*m is winner
+ * j itself); ahv_verify over each pair's own k*m candidates keeping the best (best_val [B], best_idx [B] = index
+ * into that pair's candidate set, R_best [B,3,3] or NULL).  No host synchronisation, no allocation:
+ * CUDA-graph capturable.  k <= min(32, N).  Workspace: ahv_refine_workspace_bytes. */
+AHV_API size_t ahv_refine_workspace_bytes(int B, int64_t N, int k, int m);
+AHV_API int ahv_refine(const void* vol_src, int vol_dtype, const float* vol_tgt, const float* R, int r_per_pair,
+                       const float* W1, const float* W2, const float* b2, const float* base, int k, int m,
+                       float max_angle_deg, uint64_t seed, float* first_val, int64_t* first_idx, float* first_R,
+                       float* cand, float* best_val, int64_t* best_idx, float* R_best, int B, int64_t N,
+                       int math_mode, void* workspace, size_t workspace_bytes, void* stream);
 
 /* torch.max / top-k over an existing score matrix (modules/model.py:195). */
 AHV_API int ahv_topk(const float* scores, int B, int64_t N, int k, int64_t idx_offset, float* topk_val,

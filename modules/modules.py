@@ -107,8 +107,12 @@ class Feature_Aligner(nn.Module):
         return src, tgt
 
     def forward_3d2d(self, img_feat):
-        """[M,16,8,8,8] -> [M,32,64] unit feature vectors (modules/modules.py:112-124),
-        computed by `ahv_forward_3d2d` on the GPU (inference only; no autograd)."""
+        """[M,16,8,8,8] -> [M,32,64] unit feature vectors (modules/modules.py:112-124).  Inference: one kernel
+        (`ahv_forward_3d2d`).  When autograd is recording and the input or the head can receive a gradient - the
+        reference trains through this call (modules/model.py:53-56) - the differentiable formulation is used
+        instead, so reference-style training code keeps its gradients."""
         head = self.feature_embedding_2d
-        return _ahv().ops.forward_3d2d(img_feat.float(), head[0].weight.detach(), head[2].weight.detach(),
-                                       head[2].bias.detach())
+        w1, w2, b2 = head[0].weight, head[2].weight, head[2].bias
+        if torch.is_grad_enabled() and (img_feat.requires_grad or w1.requires_grad or w2.requires_grad or b2.requires_grad):
+            return _ahv().training.head_torch(img_feat.float(), w1, w2, b2)
+        return _ahv().ops.forward_3d2d(img_feat.float(), w1.detach(), w2.detach(), b2.detach())

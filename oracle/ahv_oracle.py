@@ -115,6 +115,74 @@ def random_rotations_torch(n: int, generator=None):
 
 
 # --------------------------------------------------------------------------
+# extensions beyond the reference: the native Philox sampler and
+# the local refinement set, restated so the CUDA generators have an independent check
+# (integer part exact; the transcendental functions agree to rounding, so the
+# comparison is to ~1e-6, not bit-exact)
+# --------------------------------------------------------------------------
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox-4x32-10 (Salmon et al. 2011) on uint32 numpy arrays."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3))
+    k0 = np.uint32(k0) + np.zeros_like(c0)
+    k1 = np.uint32(k1) + np.zeros_like(c0)
+    m32 = np.uint64(0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c0.astype(np.uint64)
+            p1 = M1 * c2.astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & m32).astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & m32).astype(np.uint32)
+            c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+            k0 = k0 + W0
+            k1 = k1 + W1
+    return c0, c1, c2, c3
+
+
+def _philox_quaternions(counter: np.ndarray, seed: int, s2: int, s3: int):
+    """Four standard normals per counter (two Box-Muller pairs), as csrc/ahv_so3.cu draws them."""
+    f = np.float32
+    counter = np.asarray(counter, dtype=np.uint64)
+    u = _philox4x32_10((counter & np.uint64(0xFFFFFFFF)).astype(np.uint32), (counter >> np.uint64(32)).astype(np.uint32),
+                       np.full(counter.shape, s2, np.uint32), np.full(counter.shape, s3, np.uint32),
+                       seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    inv32 = f(2.3283064365386963e-10)
+    u0 = ((u[0] >> np.uint32(8)).astype(f) + f(0.5)) * f(1.0 / 16777216.0)
+    u1 = u[1].astype(f) * inv32
+    u2 = ((u[2] >> np.uint32(8)).astype(f) + f(0.5)) * f(1.0 / 16777216.0)
+    u3 = u[3].astype(f) * inv32
+    r0, r1 = np.sqrt(f(-2.0) * np.log(u0)).astype(f), np.sqrt(f(-2.0) * np.log(u2)).astype(f)
+    a0, a1 = (f(2.0) * u1).astype(np.float64) * np.pi, (f(2.0) * u3).astype(np.float64) * np.pi
+    return (r0 * np.cos(a0).astype(f), r0 * np.sin(a0).astype(f), r1 * np.cos(a1).astype(f), r1 * np.sin(a1).astype(f))
+
+
+def sample_rotations_np(n: int, seed: int = 0, first_index: int = 0) -> np.ndarray:
+    """Restatement of ahv_so3_sample: hypothesis i = quaternion map of the normals Philox(seed, first_index+i)."""
+    q = _philox_quaternions(np.arange(first_index, first_index + n, dtype=np.uint64), seed, 0x3d41, 0x4856)
+    return rotations_from_normals_np(np.stack(q, axis=-1))
+
+
+def perturb_rotations_np(R_center: np.ndarray, m: int, max_angle_deg: float, seed: int = 0) -> np.ndarray:
+    """Restatement of ahv_so3_perturb: [...,3,3] -> [...,m,3,3]; index 0 = the centre, index j a Haar rotation
+    (Philox counter i*m+j) with its angle rescaled from [0,pi] to [0,max_angle] about the same axis, applied on
+    the left of the centre."""
+    f = np.float32
+    c = np.ascontiguousarray(R_center, dtype=f).reshape(-1, 3, 3)
+    n = c.shape[0]
+    t = np.arange(n * m, dtype=np.uint64)
+    qa, qb, qc, qd = _philox_quaternions(t, seed, 0x7065, 0x7274)
+    vn = np.sqrt(qb * qb + qc * qc + qd * qd).astype(f)
+    theta = (f(2.0) * np.arctan2(vn, np.abs(qa))).astype(f)
+    phi = theta * f(np.deg2rad(max_angle_deg) / np.pi)
+    sh, ch = np.sin(f(0.5) * phi).astype(f), np.cos(f(0.5) * phi).astype(f)
+    k = np.where(vn > 0, sh / np.maximum(vn, f(1e-30)), f(0)).astype(f)
+    dR = rotations_from_normals_np(np.stack([ch, k * qb, k * qc, k * qd], axis=-1)).reshape(n, m, 3, 3)
+    out = np.einsum("nmij,njk->nmik", dR.astype(np.float64), c.astype(np.float64)).astype(f)
+    out[:, 0] = c
+    return out.reshape(*np.shape(R_center)[:-2], m, 3, 3)
+
+
+# --------------------------------------------------------------------------
 # base coordinates of F.affine_grid(align_corners=False) for size 8
 # ATen builds linspace(-1,1,8)*(7/8); two entries are not exactly (2i+1)/8-1.
 # --------------------------------------------------------------------------
@@ -272,7 +340,7 @@ def score_torch(vol_src, vol_tgt, R, W1, W2, b2, chunk: int = 5000):
         per_pair = R.dim() == 4
         N = R.shape[1] if per_pair else R.shape[0]
         tgt = forward_3d2d_torch(vol_tgt, W1, W2, b2)         # [B,32,64]
-        out = torch.empty(B, N, dtype=torch.float32)
+        out = torch.empty(B, N, dtype=torch.float32, device=vol_src.device)
         for b in range(B):
             Rb = R[b] if per_pair else R
             for a in range(0, N, chunk):

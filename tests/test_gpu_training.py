@@ -166,3 +166,42 @@ def test_backward_kernel_matches_the_c_oracle(ahv, golden, oracle, per_pair):
     for name, a, r in zip(("vol", "tgt", "W1", "W2", "b2"), got, ref):
         err = np.abs(a.cpu().numpy().astype(np.float64) - r).max()
         assert err <= 1e-4 * np.abs(r).max(), (name, err, np.abs(r).max())
+
+
+def test_reference_style_training_code_keeps_its_gradients(ahv, golden, oracle):
+    """The reference trains THROUGH rotate_volume -> forward_3d2d (modules/model.py:53-56).  The drop-in
+    `refcompat.rotate_volume` and `Feature_Aligner.forward_3d2d` are single kernels for inference but must stay
+    differentiable when autograd records and their inputs require a gradient - checked against autograd through
+    the oracle's restatement of the same five lines."""
+    from modules.modules import Feature_Aligner
+
+    dev = torch.device("cuda", 0)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    T = torch.from_numpy
+    B, N = 2, 24
+    vs, vt, R = T(g["vol_src"][:B]), T(g["vol_tgt"][:B]), T(g["R"][:N])
+    W1, W2, b2 = T(w["W1"]), T(w["W2"]), T(w["b2"])
+    gs = torch.randn(B, N, generator=torch.Generator().manual_seed(5))
+    ref_s, ref_g = _cpu_reference(oracle, vs, vt, R, W1, W2, b2, gs)
+    fa = Feature_Aligner(in_channel=768, mid_channel=256, out_channel=32, n_heads=4, depth=1).to(dev)
+    head = fa.feature_embedding_2d
+    with torch.no_grad():
+        head[0].weight.copy_(W1.reshape(32, 384, 1, 1)); head[2].weight.copy_(W2.reshape(32, 32, 1, 1)); head[2].bias.copy_(b2)
+    v_src, v_tgt = vs.to(dev).requires_grad_(True), vt.to(dev).requires_grad_(True)
+    Rd = R.to(dev)
+    # modules/model.py:53-56, verbatim shape
+    rot = torch.stack([ahv.refcompat.rotate_volume(v[None].expand(N, -1, -1, -1, -1), Rd) for v in v_src]).reshape(-1, 16, 8, 8, 8)
+    f = fa.forward_3d2d(rot).reshape(B, N, -1, 64)
+    t = fa.forward_3d2d(v_tgt)
+    sim = (f * t[:, None]).sum(dim=2).mean(dim=-1)
+    assert sim.requires_grad
+    assert torch.allclose(sim.detach().cpu().double(), ref_s, rtol=2e-5, atol=0)
+    (sim * gs.to(dev)).sum().backward()
+    got = [v_src.grad, v_tgt.grad, head[0].weight.grad.reshape(32, 384), head[2].weight.grad.reshape(32, 32), head[2].bias.grad]
+    for name, a, ref in zip(("vol_src", "vol_tgt", "W1", "W2", "b2"), got, ref_g):
+        scale = ref.abs().max().item()
+        assert torch.allclose(a.detach().cpu().double(), ref, rtol=0, atol=2e-4 * scale), name
+    # inference keeps the single-kernel path: no graph, same numbers
+    with torch.no_grad():
+        f0 = fa.forward_3d2d(rot.detach())
+    assert not f0.requires_grad and torch.allclose(f0, f.detach().reshape(B * N, -1, 64), atol=2e-6)
