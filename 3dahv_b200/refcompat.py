@@ -34,7 +34,12 @@ def rotate_volume(volume: torch.Tensor, rotation_matrix: torch.Tensor, padding_m
 
 def forward_3d2d(feature_aligner, img_feat: torch.Tensor) -> torch.Tensor:
     """Feature_Aligner.forward_3d2d (modules/modules.py:112-124): [M,16,8,8,8] -> [M,32,64]."""
-    return feature_aligner.forward_3d2d(img_feat)   # kernel for inference, differentiable formulation under autograd
+    head = feature_aligner.feature_embedding_2d
+    w1, w2, b2 = head[0].weight, head[2].weight, head[2].bias
+    if torch.is_grad_enabled() and (img_feat.requires_grad or w1.requires_grad or w2.requires_grad or b2.requires_grad):
+        from . import training   # the reference trains through this call (modules/model.py:54-55)
+        return training.head_torch(img_feat.float(), w1, w2, b2)
+    return ops.forward_3d2d(img_feat.float(), w1.detach(), w2.detach(), b2.detach())
 
 
 def random_rotations(n: int, dtype=None, device=None) -> torch.Tensor:

@@ -111,8 +111,4 @@ class Feature_Aligner(nn.Module):
         (`ahv_forward_3d2d`).  When autograd is recording and the input or the head can receive a gradient - the
         reference trains through this call (modules/model.py:53-56) - the differentiable formulation is used
         instead, so reference-style training code keeps its gradients."""
-        head = self.feature_embedding_2d
-        w1, w2, b2 = head[0].weight, head[2].weight, head[2].bias
-        if torch.is_grad_enabled() and (img_feat.requires_grad or w1.requires_grad or w2.requires_grad or b2.requires_grad):
-            return _ahv().training.head_torch(img_feat.float(), w1, w2, b2)
-        return _ahv().ops.forward_3d2d(img_feat.float(), w1.detach(), w2.detach(), b2.detach())
+        return _ahv().refcompat.forward_3d2d(self, img_feat)

@@ -59,10 +59,25 @@ def _geo(Ra, Rb):
     return torch.arccos(s) * 180.0 / math.pi
 
 
+class _Handle:
+    def __init__(self, model):
+        self.model = model
+
+    def remove(self):
+        del self.model.forward          # back to the class's method
+
+
 def _record_volumes(model):
-    rec = []
-    handle = model.register_forward_hook(lambda m, inp, out: rec.append((out[0].detach().cpu(), out[1].detach().cpu())))
-    return rec, handle
+    """Record the (vol_src, vol_tgt) every `forward` returns - called as model(...) or as self.forward(...)."""
+    rec, orig = [], model.forward
+
+    def forward(*args, **kwargs):
+        out = orig(*args, **kwargs)
+        rec.append((out[0].detach().cpu(), out[1].detach().cpu()))
+        return out
+
+    model.forward = forward
+    return rec, _Handle(model)
 
 
 def _check_against_oracle(oracle, sim_ref, picked, err, gt, proposals_cpu):

@@ -288,6 +288,13 @@ def test_refcompat_idiom(ahv, golden):
     f = ahv.refcompat.forward_3d2d(fa, rot).reshape(3, 200, -1, 64)
     t = ahv.refcompat.forward_3d2d(fa, vt)
     sim = (f * t[:, None]).sum(dim=2).mean(dim=-1)
+    # like the reference's eval loop (no torch.no_grad() around it, test_co3d.py:126-152) this records a graph,
+    # because the head's parameters require a gradient; under no_grad the same calls are single kernels
+    assert sim.requires_grad
+    with torch.no_grad():
+        f0 = ahv.refcompat.forward_3d2d(fa, rot.detach())
+    assert not f0.requires_grad and torch.allclose(f0.reshape(3, 200, -1, 64), f.detach(), atol=2e-6)
+    sim = sim.detach()
     assert _relerr(sim.cpu().numpy(), g["scores"][:, :200]) <= 2e-5
     # fused
     s, idx, Rbest = ahv.refcompat.verify(fa, vs, vt, R)
