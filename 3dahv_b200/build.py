@@ -1,6 +1,6 @@
 """Build lib3dahv_b200.so in-tree with nvcc for sm_100a (no torch headers, plain C ABI).
 
-    python 3dahv_b200/build.py [--force] [--verbose]
+    python 3dahv_b200/build.py [--force] [--verbose] [-DNAME[=VALUE] ... --out=path/to/variant.so]
 """
 from __future__ import annotations
 
@@ -27,8 +27,37 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = os.path.join(HERE, "build", "built_on.txt")
+
+
+def _machine_id() -> str:
+    import socket
+    ids = []
+    for path in ("/etc/machine-id", "/proc/sys/kernel/random/boot_id"):
+        try:
+            with open(path) as f:
+                ids.append(f.read().strip())
+        except OSError:
+            ids.append("")
+    return ":".join([socket.gethostname()] + ids)
+
+
+def _write_stamp() -> None:
+    with open(STAMP, "w") as f:
+        f.write(_machine_id() + "\n")
+
+
 def needs_build() -> bool:
+    """Rebuild when the library is missing, older than any source, or was not produced on THIS machine (a
+    prebuilt binary that travelled with a snapshot is never trusted by `build()`; the loader still uses it when
+    nobody calls build first, which is what lets the GPU box run the library built in the build container)."""
     if not os.path.exists(LIB):
+        return True
+    try:
+        with open(STAMP) as f:
+            if f.read().strip() != _machine_id():
+                return True
+    except OSError:
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
@@ -37,12 +66,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Product build: `build()` -> 3dahv_b200/lib3dahv_b200.so.  Experiment / diagnostics builds (scripts/ only):
+    `build(defines=["AHV_STAGES=2"], out="experiments/variants/lib_stages2.so")` compile the same sources with
+    extra -D flags into another file; the product loader never looks at those."""
+    variant = out is not None
+    lib_out = os.path.abspath(out) if variant else LIB
+    if not variant and not force and not needs_build():
         return LIB
-    flags = NVCC_FLAGS + (["-DAHV_TIMELINE"] if os.environ.get("AHV_TIMELINE") else [])  # diagnostics build
+    flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build", os.path.splitext(os.path.basename(lib_out))[0]) if variant else os.path.join(HERE, "build")
+    os.makedirs(os.path.dirname(lib_out), exist_ok=True)
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -61,11 +96,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [_nvcc(), "-shared", "-o", lib_out, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fvisibility=hidden"]
     subprocess.check_call(cmd)
-    return LIB
+    if not variant:
+        _write_stamp()
+    return lib_out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

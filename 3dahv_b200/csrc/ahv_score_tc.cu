@@ -147,6 +147,28 @@ __host__ inline Scratch carve(void* ws, int B) {
   return sc;
 }
 
+// Tensor map of the source volumes for the TMA staging: [B*16 channels][8 d][64 (h,w)] elements, one box = one
+// pair's whole volume (contiguous in HBM; the 3-D form keeps every box dimension <= 256).
+static int make_volume_map(const void* vol_src, int B, bool bf16, CUtensorMap* map) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  AHV_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return AHV_ECUDA;
+  const cuuint64_t esz = bf16 ? 2 : 4;
+  const cuuint64_t dims[3] = {64, 8, (cuuint64_t)B * kC};
+  const cuuint64_t strides[2] = {64 * esz, 512 * esz};  // bytes between d slices, between channels
+  const cuuint32_t box[3] = {64, 8, (cuuint32_t)kC};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = reinterpret_cast<EncodeFn>(fn)(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                                                    const_cast<void*>(vol_src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? AHV_OK : AHV_ECUDA;
+}
+
 template <typename KernelT, typename... Args>
 static int launch_pdl(KernelT kernel, unsigned grid, size_t smem, cudaStream_t s, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -188,8 +210,11 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   if (((int64_t)B * N) / grid >= 0xffffffffLL) return AHV_EINVAL;  // per-CTA tile iterator is 32-bit
   const float* tgt = prologue ? sc.tgt_feat : tgt_feat_in;
   u64* keys = want_argmax ? sc.best_keys : nullptr;
+  CUtensorMap vol_map;
+  const int mst = make_volume_map(vol_src, B, sizeof(T) == 2, &vol_map);
+  if (mst != AHV_OK) return mst;
   AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
-  return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue, vol_src, tgt, R, r_per_pair, b2, base, W1,
+  return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue, vol_map, tgt, R, r_per_pair, b2, base, W1,
                     W2, scores, keys, B, N, fin);
 }
 

@@ -17,8 +17,14 @@ namespace tc {
 // verified by experiments/ts_mma_probe.cu.  Compared with the SS kernel this removes one 16 KB
 // operand copy (stores) and one 16 KB operand read per hypothesis from the shared-memory pipe.
 struct MapTS {
-  static constexpr int yz_h = 144, yz_d = 8 * yz_h, yz_ch = 8 * yz_d, yz_bytes = 2 * yz_ch;  // 18432 per hypothesis
-  static constexpr int tile_bytes = 2 * yz_bytes;
+  // YZ operand copy of one tile (two hypotheses = slots), fp16, K-major core matrices [8 w rows][8 channels]:
+  //   address = chalf*yz_ch + (d>>1)*yz_dhi + slot*yz_slot + (d&1)*yz_dlo + h*yz_h + w*16   (yz_h = 144: 16 B pad
+  //   per core matrix keeps the operand stores conflict-free for the gather's lane map).
+  // The slot sits BETWEEN the two halves of d so that 8-row group g = (d>>1)*4 + slot*2 + (d&1) of view y advances
+  // by one constant stride: view y of BOTH hypotheses is then one M=128 MMA per K slice whose row i is TMEM lane i -
+  // exactly the rows the interleaved M=64 tiles of view z accumulate into (halves view y's W1 operand reads).
+  static constexpr int yz_h = 144, yz_dlo = 8 * yz_h, yz_slot = 2 * yz_dlo, yz_dhi = 2 * yz_slot, yz_ch = 4 * yz_dhi;
+  static constexpr int tile_bytes = 2 * yz_ch;  // 36864
   static constexpr int off_vol = 0;
   static constexpr int off_w1 = off_vol + kVolSmemBytes;
   static constexpr int off_w2 = off_w1 + kW1Bytes;
@@ -35,7 +41,7 @@ struct MapTS {
 
 template <typename T, bool K16>
 __global__ void __launch_bounds__(kThreadsTC, 1)
-score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_feat,
+score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __restrict__ tgt_feat,
                    const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
                    const float* __restrict__ base, const float* __restrict__ W1,
                    const float* __restrict__ W2, float* __restrict__ scores,
@@ -76,6 +82,8 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
         mbar_init(bar0 + (kA2Full + i) * 8, 4);
         mbar_init(bar0 + (kD2Full + i) * 8, 1);
       }
+      mbar_init(bar0 + kVolFull * 8, 1);
+      mbar_init(bar0 + (kVolFull + 1) * 8, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -86,6 +94,30 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (threadIdx.x == 0) AHV_TL(1);
+  // ---- source volumes by TMA (cp.async.bulk.tensor, 3-D map over [B*16 ch][8 d][64 hw]; one box = one pair's
+  // volume, 32 KB fp32 / 16 KB bf16).  The box of the pair that starts at tile t lands in A-operand stage buffer
+  // t % kStages - idle at that moment: the tensor core finished reading it with tile t-3 and the gather fills it only
+  // after it has turned the box into its own layout (stage_pair_volume).  Requests are made by the MMA warp, which
+  // sees every tile one tile-time before the gather reaches it plus one: after issuing tile t it looks two tiles
+  // ahead, so a pair switch never waits for HBM/L2 and the gather's loop carries no TMA code.  At most two boxes
+  // are in flight (a new pair every tile, N <= 2), hence two mbarriers used alternately.
+  uint32_t vol_req = 0;  // MMA warp: boxes requested so far
+  auto request_volume = [&](int pair, uint32_t stage_buf) {
+    const uint32_t bar = bar0 + (kVolFull + (vol_req & 1)) * 8;
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar, kC * kVox * (uint32_t)sizeof(T));
+      tma_load_3d(s_base + M::off_a + stage_buf * M::tile_bytes, &vol_map, bar, 0, 0, pair * kC);
+    }
+    ++vol_req;
+  };
+  if (warp == kMmaWarp) {  // the first tile's pair, and the second tile's if it is another pair - before anything else
+    TileIter it0(work);
+    it0.advance();
+    request_volume(it0.b, 0);
+    int b1, c1; uint32_t n1;
+    it0.peek_tile(b1, n1, c1);
+    if (it0.left > 0 && b1 != it0.b) request_volume(b1, 1 % kStages);
+  }
   if (warp >= kGatherWarps) {  // MMA + epilogue warps: weights -> fp16 operand layouts, then release the MMA warp
     pack_weights(smem + M::off_w1, W1, W2, threadIdx.x - kGatherWarps * 32);
     fence_proxy_async();  // written through the generic proxy, UMMA reads through the async proxy
@@ -109,16 +141,24 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       // the tap of step t is (t>>1)^(rot>>1): steps 0,1 share one x tap, steps 2,3 the other - compile-time)
       const int ck = K16 ? (rot ^ t) : ((rot + t) & 3);
       koff[t] = ck * 16;
+      const uint32_t row_off = sub * M::yz_dhi + slot * M::yz_slot + dlo * M::yz_dlo + h_ * M::yz_h;
       if constexpr (!K16)  // fp32: chunk ck = channels 4ck..4ck+3 (8 B of fp16)
-        syz[t] = slot * M::yz_bytes + (ck >> 1) * M::yz_ch + (ck & 1) * 8 + d * M::yz_d + h_ * M::yz_h;
+        syz[t] = (ck >> 1) * M::yz_ch + (ck & 1) * 8 + row_off;
       else                 // 16-bit: accumulator t&1 holds channel half (rot^t)&1 (16 B of fp16); t < 2 used
-        syz[t] = slot * M::yz_bytes + ((rot ^ t) & 1) * M::yz_ch + d * M::yz_d + h_ * M::yz_h;
+        syz[t] = ((rot ^ t) & 1) * M::yz_ch + row_off;
     }
     const unsigned char* volb = smem + M::off_vol;
     const int gtid = threadIdx.x;
     TileIter it(work);
     int cur_b = -1;
     uint32_t g = 0;
+    // Pair volumes arrive by TMA, requested by the MMA warp two tiles ahead of the pair switch (see there); the
+    // volume of the pair that starts at tile g sits in A-operand stage buffer g % kStages, completion on mbarrier
+    // kVolFull + (ordinal & 1) where ordinal counts the pairs this CTA has staged.
+    uint32_t vol_uses = 0;
+    // Rotation prefetch, one tile ahead, 9 loads per lane (all lanes of a slot read the same 36 bytes).  A coalesced
+    // variant - one load per warp + 9 shuffles - removes 70 LSU wavefronts per hypothesis but was 3-7 % SLOWER:
+    // the shuffles queue behind the gather's LDS.128 in the same pipe and sit on the coordinate critical path.
     float Rn[9];
     auto fetch_R = [&](int fb, uint32_t fn) {
       const float* Rg = R + (r_per_pair ? ((size_t)fb * N + fn) : (size_t)fn) * 9;
@@ -132,8 +172,9 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
       // first pair of this CTA: its volume (and the W1 row norms) ride the same memory round trip as the
       // first rotations
       cur_b = fb;
-      const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, vol_src + (size_t)fb * kC * kVox, l1max_bits, W1,
-                                                  true, red, gtid);
+      const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, reinterpret_cast<const T*>(smem + M::off_a),
+                                                  bar0 + kVolFull * 8, 0, l1max_bits, W1, true, red, gtid);
+      ++vol_uses;
       if (gtid == 0) inv_ring[fb & 7] = inv;
       named_bar_sync(1, kGatherWarps * 32);
       if (threadIdx.x == 0) AHV_TL(3);
@@ -232,8 +273,11 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
     while (it.advance()) {
       if (it.b != cur_b) {
         named_bar_sync(1, kGatherWarps * 32);
-        const T* vg = vol_src + (size_t)it.b * kC * kVox;
-        const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, vg, l1max_bits, W1, false, red, gtid);
+        // requested two tiles ago, into the stage buffer THIS tile is about to fill
+        const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, reinterpret_cast<const T*>(smem + M::off_a + (g % kStages) * M::tile_bytes),
+                                                    bar0 + (kVolFull + (vol_uses & 1)) * 8, (vol_uses >> 1) & 1, l1max_bits, W1, false,
+                                                    red, gtid);
+        ++vol_uses;
         if (gtid == 0) inv_ring[it.b & 7] = inv;
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
@@ -365,21 +409,30 @@ score_tc_ts_kernel(const T* __restrict__ vol_src, const float* __restrict__ tgt_
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_f16_ts(tmem + gb * 32, tmem + M::tmem_ax + stage * 64 + kk * 8, smem_desc(w1s + kk * 1024, 512, 128), idesc2, kk);
+        const uint32_t a_tile = s_base + M::off_a + stage * M::tile_bytes;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // view y, both hypotheses: rows (d,slot,w) in 16 groups of 8, K slice = (h=kk, c)
+          umma_f16(tmem + gb * 32, smem_desc(a_tile + kk * M::yz_h, M::yz_ch, M::yz_dlo), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc2, 1);
 #pragma unroll
         for (int sl = 0; sl < 2; ++sl) {
-          const uint32_t lane_off = (uint32_t)(16 * sl) << 16;
-          const uint32_t d1 = tmem + lane_off + gb * 32;
-          const uint32_t a = s_base + M::off_a + stage * M::tile_bytes + sl * M::yz_bytes;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // view y: rows (d,w), K slice = (h=kk, c)
-            umma_f16(d1, smem_desc(a + kk * M::yz_h, M::yz_ch, M::yz_d), smem_desc(w1s + (8 + kk) * 1024, 512, 128), idesc1, 1);
+          const uint32_t d1 = tmem + ((uint32_t)(16 * sl) << 16) + gb * 32;
+          const uint32_t a = a_tile + sl * M::yz_slot;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // view z: rows (h,w), K slice = (d=kk, c)
-            umma_f16(d1, smem_desc(a + kk * M::yz_d, M::yz_ch, M::yz_h), smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
+            umma_f16(d1, smem_desc(a + (kk >> 1) * M::yz_dhi + (kk & 1) * M::yz_dlo, M::yz_ch, M::yz_h),
+                     smem_desc(w1s + (16 + kk) * 1024, 512, 128), idesc1, 1);
         }
         umma_commit(bar0 + (kEmpty + stage) * 8);
         umma_commit(bar0 + (kD1Full + gb) * 8);
         if (lane == 0 && g == 0) AHV_TL(6);
+        {  // two tiles ahead: does tile g+2 start a new pair?  then request its volume into stage (g+2) % kStages
+          int pb2; uint32_t left2;
+          if (it.second_next_starts_pair(pb2, left2)) {
+            const uint32_t nstage = (g + 2) % kStages, nuse = (g + 2) / kStages;
+            if (nuse > 0) mbar_wait(bar0 + (kEmpty + nstage) * 8, (nuse - 1) & 1);  // tile g-1's MMAs are done with it
+            request_volume(pb2, nstage);
+          }
+        }
         if (g > 0) conv2(g - 1);
         ++g;
       }

@@ -27,13 +27,16 @@ constexpr int kGatherWarps = 8;
 constexpr int kEpiWarp0 = 8;
 constexpr int kMmaWarp = 12;
 constexpr int kThreadsTC = 13 * 32;
-constexpr int kStages = 3;
+#ifndef AHV_STAGES
+#define AHV_STAGES 3
+#endif
+constexpr int kStages = AHV_STAGES;  // A-operand pipeline depth (a stage = one tile = two hypotheses)
 
 // ---- shared memory map (bytes) ----
 constexpr int kW1Bytes = 24 * 1024;  // 24 MMA slices x [2 chalf][4 ngroup][8][8] fp16
 constexpr int kW2Bytes = 2 * 1024;
 
-enum Bar { kFull = 0, kEmpty = 3, kD1Full = 6, kD1Empty = 8, kA2Full = 10, kD2Full = 12 };
+enum Bar { kFull = 0, kEmpty = 3, kD1Full = 6, kD1Empty = 8, kA2Full = 10, kD2Full = 12, kVolFull = 14 };
 
 // 1.0f the compiler cannot fold.  The rotation prefetch is loop-carried in registers; multiplying the
 // values loaded BEFORE the loop by this makes every loop-entry value ALU-defined, so the first use at
@@ -147,6 +150,19 @@ struct TileIter {
     if (n == N) { ++pb; pn = 0; }
     pc = min(N - pn, left) >= 2 ? 2 : 1;
   }
+  // Looking two tiles ahead (after advance() produced tile t): does tile t+2 exist and start a new pair?  pb2 = that
+  // pair.  (Tiles never straddle pairs; tile t+1 = {pair b or b+1, 1 or 2 hypotheses}.)
+  __device__ __forceinline__ bool second_next_starts_pair(int& pb2, uint32_t& left2) const {
+    if (left == 0) return false;
+    int b1 = b;
+    uint32_t n1 = n;
+    if (n1 == N) { ++b1; n1 = 0; }
+    const uint32_t c1 = min(N - n1, left) >= 2 ? 2u : 1u;
+    n1 += c1;
+    left2 = left - c1;
+    pb2 = b1 + 1;
+    return left2 > 0 && n1 == N;
+  }
   // (pair, hypothesis) of the item following this tile, or the tile's own first item at the very end
   __device__ __forceinline__ void peek(int& pb, uint32_t& pn) const {
     if (left == 0) { pb = b; pn = n0; }
@@ -154,13 +170,6 @@ struct TileIter {
     else { pb = b; pn = n; }
   }
 };
-
-template <typename T>
-__device__ __forceinline__ float ld_vol(const T* p);
-template <>
-__device__ __forceinline__ float ld_vol<float>(const float* p) { return __ldg(p); }
-template <>
-__device__ __forceinline__ float ld_vol<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
 // ---- one-time per CTA: W1/W2 (fp32, global) -> fp16 UMMA B-operand layouts in shared memory ------------
 // conv1: 24 slices j = (view, kk), each [chalf][ngroup][n%8][c%8]; conv2: [kc][ngroup][8][8] behind them.
@@ -189,8 +198,9 @@ __device__ __forceinline__ void pack_weights(unsigned char* wsm, const float* __
 
 // Largest L1 norm of a W1 row (bounds |conv1 output| / max|V| for the pair scale), by the 8 gather warps:
 // warp w sums rows 4w..4w+3 (48 coalesced loads per lane in flight, fixed summation order -> the same value
-// in every CTA) and folds them into *l1max_bits (a non-negative float's bit pattern orders like the float).
-__device__ __forceinline__ void w1_l1max(uint32_t* l1max_bits, const float* __restrict__ W1, int warp, int lane) {
+// in every CTA); the caller folds the per-warp maxima into *l1max_bits (a non-negative float's bit pattern orders
+// like the float).
+__device__ __forceinline__ float w1_l1max_partial(const float* __restrict__ W1, int warp, int lane) {
   float wv[4][12];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -204,18 +214,32 @@ __device__ __forceinline__ void w1_l1max(uint32_t* l1max_bits, const float* __re
     for (int j = 0; j < 12; ++j) l1 += fabsf(wv[r][j]);
     m = fmaxf(m, warp_sum(l1));
   }
-  if (lane == 0) atomicMax(l1max_bits, __float_as_uint(m));
+  return m;  // this warp's largest row norm (identical in all lanes)
 }
 
 // ---- per pair: stage the source volume, pre-scaled by the pair's power-of-two scale -------------------
-// Called by the 256 gather threads between two named barriers.  The volume is read once into registers, its
+// Called by the 256 gather threads between two named barriers.  `raw` is the pair's volume as it lies in HBM
+// ([16 ch][512 voxels], fp32 or bf16), brought into shared memory by TMA (a 3-D tensor-map copy issued one tile
+// before the pair switch, landing in the A-operand stage the next tile will use; completion on mbarrier
+// `bar_vol`, phase `parity`).  The volume is read once into registers, its
 // max |V| reduced over the 8 warps, the scale s = 2^e chosen so that max|V|*s <= 2^12 and
 // max|V|*s*L1max <= 2^14 (fp16 max 65504; exact, undone after conv2), then the scaled values are written in
 // the gather's layout: fp32 lines [halo voxel][16 ch], or for 16-bit "x-pair lines" (every voxel is tap 0 of
 // pair xh and tap 1 of pair xh-1).  Returns 1/s.
+template <typename T>
+__device__ __forceinline__ float ld_raw(const T* p);
+template <>
+__device__ __forceinline__ float ld_raw<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_raw<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
 template <typename T, bool K16>
-__device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* __restrict__ vg, uint32_t* l1max_bits,
-                                                   const float* __restrict__ W1, bool first, float* red, int gtid) {
+__device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* raw, uint32_t bar_vol, uint32_t parity,
+                                                   uint32_t* l1max_bits, const float* __restrict__ W1, bool first,
+                                                   float* red, int gtid) {
+  float wnorm = 0.0f;
+  if (first) wnorm = w1_l1max_partial(W1, gtid >> 5, gtid & 31);  // W1 row norms: in flight while the TMA lands
+  mbar_wait(bar_vol, parity);                                      // the pair's volume is in shared memory
   float val[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -224,10 +248,9 @@ __device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* 
     const int task = gtid + 256 * (K16 ? (i >> 3) : (i >> 2));
     const int v = task & 511, grp = task >> 9;
     const int ch = K16 ? grp * 8 + (i & 7) : grp * 4 + (i & 3);
-    val[i] = ld_vol<T>(vg + ch * kVox + v);
+    val[i] = ld_raw<T>(raw + ch * kVox + v);   // lanes = consecutive voxels of one channel: conflict-free
   }
-  // first pair of the CTA: the W1 row norms ride the same memory round trip as the volume
-  if (first) w1_l1max(l1max_bits, W1, gtid >> 5, gtid & 31);
+  if (first && (gtid & 31) == 0) atomicMax(l1max_bits, __float_as_uint(wnorm));
   float mx = 0.0f;
 #pragma unroll
   for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fabsf(val[i]));

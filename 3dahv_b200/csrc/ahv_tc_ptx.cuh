@@ -1,6 +1,8 @@
 // PTX wrappers for the tensor-core scoring kernels (sm_100a): mbarrier, fences, TMEM allocation,
 // tcgen05.mma / commit / ld / st, named barriers and UMMA shared-memory / instruction descriptors.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "ahv_common.cuh"
 
 namespace ahv {
@@ -24,6 +26,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// TMA: tensor-map bulk copy global -> shared, completion signalled on an mbarrier (complete_tx)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -44,7 +56,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#ifndef AHV_DIAG_NO_MMA  // diagnostics build: the pipeline runs, the tensor core stays idle (ncu A/B of its operand traffic)
   if (elect_one())
+#else
+  if (false)
+#endif
     asm volatile(
         "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
@@ -91,7 +107,11 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
 }
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#ifndef AHV_DIAG_NO_MMA
   if (elect_one())
+#else
+  if (false)
+#endif
     asm volatile(
         "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)

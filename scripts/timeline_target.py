@@ -1,4 +1,4 @@
-"""Fixed-cost attribution of one B=1 launch (diagnostics build: AHV_TIMELINE=1 python 3dahv_b200/build.py --force)."""
+"""Fixed-cost attribution of one B=1 launch (diagnostics build: python 3dahv_b200/build.py -DAHV_TIMELINE --out=experiments/variants/lib_timeline.so, then AHV_VARIANT_LIB=that file)."""
 import ctypes, importlib, os, sys, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
