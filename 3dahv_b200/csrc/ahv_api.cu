@@ -99,6 +99,24 @@ AHV_API int ahv_score_backward(const float* vol_src, const float* tgt_feat, cons
                           grad_W1, grad_W2, grad_b2, B, N, (cudaStream_t)stream);
 }
 
+AHV_API int ahv_infonce(const float* scores, const float* R, int r_per_pair, const float* gt_R, float acc_thr_deg,
+                        float temperature, float* loss, float* grad_scores, int B, int64_t N, void* stream) {
+  if (B < 0 || N < 1 || !(temperature > 0.0f)) return AHV_EINVAL;
+  if (B > 0 && (!scores || !R || !gt_R || !loss)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_infonce(scores, R, r_per_pair != 0, gt_R, acc_thr_deg, temperature, loss, grad_scores, B, N, (cudaStream_t)stream);
+}
+
+AHV_API int ahv_resblock3d(const float* x, const float* conv1_w, const float* conv2_w, const float* down_w, float* out,
+                           int64_t m, void* stream) {
+  if (m < 0 || (m > 0 && (!x || !conv1_w || !conv2_w || !down_w || !out))) return AHV_EINVAL;
+  if (!aligned16(x) || !aligned16(out)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_resblock3d(x, conv1_w, conv2_w, down_w, out, m, (cudaStream_t)stream);
+}
+
 AHV_API int ahv_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                      float* feat, int64_t m, void* stream) {
   if (m < 0 || (m > 0 && (!vol || !W1 || !W2 || !b2 || !feat))) return AHV_EINVAL;

@@ -98,6 +98,10 @@ int launch_score_bwd(const float* vol_src, const float* tgt_feat, const float* R
                      const float* W1, const float* W2, const float* b2, const float* base,
                      const float* grad_scores, float* g_vol, float* g_tgt, float* g_W1, float* g_W2,
                      float* g_b2, int B, int64_t N, cudaStream_t s);
+int launch_resblock3d(const float* x, const float* Wc1, const float* Wc2, const float* Wd, float* out, int64_t m,
+                      cudaStream_t s);
+int launch_infonce(const float* scores, const float* R, int r_per_pair, const float* gt, float thr_deg, float temperature,
+                   float* loss, float* grad, int B, int64_t N, cudaStream_t s);
 int launch_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                         float* feat, int64_t m, cudaStream_t s);
 int launch_tgt_feat(const float* vol_tgt, const float* W1, const float* W2, const float* b2,

@@ -150,6 +150,40 @@ def score_backward(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tenso
     return g_vol, g_tgt, g_w1, g_w2, g_b2
 
 
+def infonce(scores: torch.Tensor, sampled_R: torch.Tensor, gt_delta_R: torch.Tensor, acc_thr_deg: float,
+            temperature: float = 0.1, want_grad: bool = True):
+    """ahv_infonce: (loss [B], d loss / d scores [B,N] or None) in one launch (modules/model.py:43-63)."""
+    s, R, g = _dev(scores, "scores"), _dev(sampled_R, "sampled_R"), _dev(gt_delta_R, "gt_delta_R")
+    B, N = s.shape
+    per_pair = R.dim() == 4
+    if (R.shape[1] if per_pair else R.shape[0]) != N or tuple(g.shape) != (B, 3, 3) or (per_pair and R.shape[0] != B):
+        raise ValueError("scores [B,N], sampled_R [N,3,3] or [B,N,3,3], gt_delta_R [B,3,3] expected")
+    loss = torch.empty(B, device=s.device, dtype=torch.float32)
+    grad = torch.empty(B, N, device=s.device, dtype=torch.float32) if want_grad else None
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.lib().ahv_infonce(s.data_ptr(), R.data_ptr(), int(per_pair), g.data_ptr(), float(acc_thr_deg),
+                                          float(temperature), loss.data_ptr(), grad.data_ptr() if want_grad else None, B, N,
+                                          _stream(s)), "ahv_infonce")
+    return loss, grad
+
+
+def resblock3d(x: torch.Tensor, conv1_w: torch.Tensor, conv2_w: torch.Tensor, down_w: torch.Tensor) -> torch.Tensor:
+    """ResNetBlock_3D(32->16) of the lifting stage (modules/modules.py:9-47, :100-101): [m,32,8,8,8] -> [m,16,8,8,8]
+    in one cluster launch (inference only)."""
+    v = _dev(x, "x")
+    if tuple(v.shape[1:]) != (32, 8, 8, 8):
+        raise ValueError("x must be [m,32,8,8,8]")
+    w1, w2, wd = _dev(conv1_w, "conv1_w"), _dev(conv2_w, "conv2_w"), _dev(down_w, "down_w")
+    if tuple(w1.shape) != (16, 32, 3, 3, 3) or tuple(w2.shape) != (16, 16, 3, 3, 3) or w1.numel() * 0 + wd.numel() != 16 * 32:
+        raise ValueError("weights must be conv1 [16,32,3,3,3], conv2 [16,16,3,3,3], downsample [16,32,1,1,1]")
+    m = v.shape[0]
+    out = torch.empty(m, 16, 8, 8, 8, device=v.device, dtype=torch.float32)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().ahv_resblock3d(v.data_ptr(), w1.data_ptr(), w2.data_ptr(), wd.data_ptr(), out.data_ptr(), m,
+                                             _stream(v)), "ahv_resblock3d")
+    return out
+
+
 def forward_3d2d(vol: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
     """Feature_Aligner.forward_3d2d (modules/modules.py:112-124): [m,16,8,8,8] -> [m,32,64]."""
     v = _dev(vol, "vol")

@@ -119,12 +119,37 @@ def verification_scores(vol_src, vol_tgt, R, W1, W2, b2, math: int = MATH_TC, ch
     return _VerifyScores.apply(vol_src, vol_tgt, R.contiguous(), W1, W2, b2, math, chunk, fused_backward)
 
 
+class _InfoNCE(torch.autograd.Function):
+    """modules/model.py:43-63 given the scores: loss and d loss / d scores from ONE kernel (`ahv_infonce`)."""
+
+    @staticmethod
+    def forward(ctx, scores, sampled_R, gt_delta_R, acc_thr_deg, temperature):
+        loss, grad = ops.infonce(scores.detach().float(), sampled_R, gt_delta_R, acc_thr_deg, temperature,
+                                 want_grad=scores.requires_grad)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_loss[:, None], None, None, None, None
+
+
 def infonce_loss(scores: torch.Tensor, sampled_R: torch.Tensor, gt_delta_R: torch.Tensor, acc_thr_deg: float,
-                 temperature: float = 0.1) -> torch.Tensor:
+                 temperature: float = 0.1, fused: bool = True) -> torch.Tensor:
     """modules/model.py:43-63 given the scores: positives = hypotheses within `acc_thr_deg` of the
-    ground-truth rotation; loss_b = -log(sum_pos e^{s/T} / sum_all e^{s/T}).  Returns [B]."""
+    ground-truth rotation; loss_b = -log(sum_pos e^{s/T} / sum_all e^{s/T}).  Returns [B].  `fused` (default): one
+    kernel for the loss and its gradient; otherwise the eager torch formulation below (kept as a cross-check)."""
+    if fused and scores.is_cuda:
+        return _InfoNCE.apply(scores, sampled_R.contiguous(), gt_delta_R.contiguous(), float(acc_thr_deg), float(temperature))
+    return infonce_loss_torch(scores, sampled_R, gt_delta_R, acc_thr_deg, temperature)
+
+
+def infonce_loss_torch(scores: torch.Tensor, sampled_R: torch.Tensor, gt_delta_R: torch.Tensor, acc_thr_deg: float,
+                       temperature: float = 0.1) -> torch.Tensor:
+    """The same loss in eager torch ops."""
     with torch.no_grad():
-        gt_sim = ((sampled_R.flatten(2) * gt_delta_R.reshape(-1, 1, 9)).sum(-1).clamp(-1, 3) - 1) / 2
+        gt_sim = ((sampled_R.flatten(-2) * gt_delta_R.reshape(-1, 1, 9)).sum(-1).clamp(-1, 3) - 1) / 2
         positive = (180.0 * torch.arccos(gt_sim) / math.pi) <= acc_thr_deg
     e = torch.exp(scores / temperature)
     return -torch.log((e * positive).sum(-1) / e.sum(-1).clamp(min=1e-8))

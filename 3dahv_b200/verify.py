@@ -161,3 +161,48 @@ class GraphedVerifier:
             self.R.copy_(R, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class GraphedTail:
+    """CUDA-graph replay of everything downstream of the 2D backbone for fixed (B, N, k): `forward_2d3d`
+    (1x1 conv + 2D ResNet block, bidirectional transformer, 3D ResNet block - `ahv_resblock3d` - for both views;
+    modules/modules.py:86-110) followed by the fused verification step, captured once and replayed with a single
+    launch.  This is the per-pair latency path of the reference's evaluation loops (test_co3d.py:133-146) minus
+    the backbone.  Inputs are copied into static buffers; outputs are static tensors valid until the next replay."""
+
+    def __init__(self, feature_aligner, B: int, N: int, k: int = 1, device="cuda", math: int | None = None,
+                 in_channels: int = 768):
+        dev = torch.device(device)
+        self.fa = feature_aligner
+        self.v = HypothesisVerifier.from_feature_aligner(feature_aligner, math).to(dev)
+        self.feat_src = torch.zeros(B, in_channels, 8, 8, device=dev)
+        self.feat_tgt = torch.zeros(B, in_channels, 8, 8, device=dev)
+        self.R = torch.eye(3, device=dev).repeat(N, 1, 1).contiguous()
+        self.k = min(k, N)
+
+        def run():
+            with torch.no_grad():
+                vs, vt = self.fa.forward_2d3d(self.feat_src, self.feat_tgt, random_mask=False, mask_ratio=0.0)
+                return self.v.score(vs, vt, self.R, k=self.k, return_scores=False), vs, vt
+
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            for _ in range(3):                      # warm-up outside capture (cuDNN/cuBLAS plans, module load)
+                self.out, self.vol_src, self.vol_tgt = run()
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out, self.vol_src, self.vol_tgt = run()
+
+    @torch.no_grad()
+    def __call__(self, feat_src=None, feat_tgt=None, R=None) -> VerifyResult:
+        if feat_src is not None:
+            self.feat_src.copy_(feat_src, non_blocking=True)
+        if feat_tgt is not None:
+            self.feat_tgt.copy_(feat_tgt, non_blocking=True)
+        if R is not None:
+            self.R.copy_(R, non_blocking=True)
+        self.graph.replay()
+        return self.out

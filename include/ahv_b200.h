@@ -113,6 +113,23 @@ AHV_API int ahv_score_backward(const float* vol_src, const float* tgt_feat, cons
                                const float* grad_scores, float* grad_vol, float* grad_tgt, float* grad_W1,
                                float* grad_W2, float* grad_b2, int B, int64_t N, void* stream);
 
+/* ResNetBlock_3D(32 -> 16, BN=False, stride 1) of the lifting stage (modules/modules.py:9-47 as applied at
+ * :100-101 inside Feature_Aligner.forward_2d3d) - the step immediately upstream of the path:
+ *   out = conv2(relu(conv1(x))) + downsample(x)
+ * x [m,32,8,8,8] -> out [m,16,8,8,8]; conv1_w [16,32,3,3,3], conv2_w [16,16,3,3,3], down_w [16,32(,1,1,1)]
+ * (state-dict feature_aligner.feature_embedding_3d.{conv1,conv2,downsample.0}.weight).  One launch: a cluster of
+ * 8 CTAs per volume (one depth slab each), the intermediate exchanged through distributed shared memory.
+ * fp32 FFMA.  Inference only. */
+AHV_API int ahv_resblock3d(const float* x, const float* conv1_w, const float* conv2_w, const float* down_w, float* out,
+                           int64_t m, void* stream);
+
+/* infoNCE_loss given the scores (training variant, modules/model.py:43-63 / model_co3d.py:41-61), one launch:
+ * positives of pair b = hypotheses whose rotation lies within acc_thr_deg of gt_R[b] (:46-49);
+ * loss[b] = -log(sum_pos exp(s/T) / max(sum_all exp(s/T), 1e-8)) (:58-61); grad_scores [B,N] (or NULL) receives
+ * d loss[b] / d scores[b,n].  scores [B,N]; R [N,3,3] or [B,N,3,3] (the per-pair sets of :102-103); gt_R [B,3,3]. */
+AHV_API int ahv_infonce(const float* scores, const float* R, int r_per_pair, const float* gt_R, float acc_thr_deg,
+                        float temperature, float* loss, float* grad_scores, int B, int64_t N, void* stream);
+
 /* Feature_Aligner.forward_3d2d (modules/modules.py:112-124): tri-plane fold,
  * conv1x1 384->32, ReLU, conv1x1 32->32 + bias, L2 normalise over channels.
  * vol [m,16,8,8,8] -> feat [m,32,64].  W1 [32,384], W2 [32,32], b2 [32]

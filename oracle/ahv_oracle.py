@@ -115,6 +115,32 @@ def random_rotations_torch(n: int, generator=None):
 
 
 # --------------------------------------------------------------------------
+# upstream of the path: ResNetBlock_3D(32 -> 16, BN=False, stride 1)
+# modules/modules.py:9-47 as applied at :100-101
+# --------------------------------------------------------------------------
+def _conv3d_np(x: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """Conv3d, kernel 3, padding 1, stride 1, no bias: x [m,ci,8,8,8], w [co,ci,3,3,3] (float64 accumulation)."""
+    m, ci, D, H, W_ = x.shape
+    xp = np.zeros((m, ci, D + 2, H + 2, W_ + 2), dtype=np.float64)
+    xp[:, :, 1:-1, 1:-1, 1:-1] = x
+    out = np.zeros((m, w.shape[0], D, H, W_), dtype=np.float64)
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                out += np.einsum("oc,mcdhw->modhw", w[:, :, kd, kh, kw].astype(np.float64),
+                                 xp[:, :, kd:kd + D, kh:kh + H, kw:kw + W_])
+    return out
+
+
+def resblock3d_np(x, conv1_w, conv2_w, down_w) -> np.ndarray:
+    """out = conv2(relu(conv1(x))) + downsample(x)   (modules/modules.py:32-47, bn1/bn2 empty, stride 1)."""
+    h1 = np.maximum(_conv3d_np(np.asarray(x), np.asarray(conv1_w)).astype(np.float32), 0.0)
+    out = _conv3d_np(h1, np.asarray(conv2_w))
+    out += np.einsum("oc,mcdhw->modhw", np.asarray(down_w).reshape(down_w.shape[0], -1).astype(np.float64), np.asarray(x, dtype=np.float64))
+    return out.astype(np.float32)
+
+
+# --------------------------------------------------------------------------
 # extensions beyond the reference (SURVEY.md §8f-4): the native Philox sampler and
 # the local refinement set, restated so the CUDA generators have an independent check
 # (integer part exact; the transcendental functions agree to rounding, so the

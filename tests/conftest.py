@@ -24,6 +24,11 @@ def golden():
     return out
 
 
+@pytest.fixture(scope="session")
+def golden_lift():
+    return dict(np.load(os.path.join(GOLDEN, "resblock3d.npz")))
+
+
 def _ensure_built():
     """Tests may run before the driver's build(): compile the library in-tree if it is missing
     (test convenience only - the product loader itself fails loudly on a missing library)."""

@@ -205,3 +205,28 @@ def test_reference_style_training_code_keeps_its_gradients(ahv, golden, oracle):
     with torch.no_grad():
         f0 = fa.forward_3d2d(rot.detach())
     assert not f0.requires_grad and torch.allclose(f0, f.detach().reshape(B * N, -1, 64), atol=2e-6)
+
+
+def test_fused_infonce_kernel_vs_eager_formulation(ahv):
+    """ahv_infonce (loss + d loss / d scores in one launch) against the eager torch formulation of
+    modules/model.py:43-63 under autograd: per-pair and shared rotation sets, weighted upstream gradient."""
+    dev = torch.device("cuda", 0)
+    B, N = 5, 3000
+    gen = torch.Generator().manual_seed(2)
+    gt = ahv.so3.sample_rotations(B, seed=1, device=dev)
+    Rpp = torch.cat([gt[:, None], ahv.so3.sample_rotations(B * (N - 1), seed=2, device=dev).reshape(B, N - 1, 3, 3)], 1).contiguous()
+    Rsh = ahv.so3.sample_rotations(N, seed=3, device=dev)
+    Rsh[:B] = gt                                               # every pair has at least one positive
+    upstream = torch.rand(B, generator=gen).to(dev)
+    for R in (Rpp, Rsh):
+        s0 = (torch.rand(B, N, generator=gen) * 0.4 + 0.2).to(dev)
+        sa, sb = s0.clone().requires_grad_(True), s0.clone().requires_grad_(True)
+        la = ahv.training.infonce_loss(sa, R, gt, 15.0)                      # fused kernel
+        lb = ahv.training.infonce_loss_torch(sb, R if R.dim() == 4 else R[None].expand(B, -1, -1, -1), gt, 15.0)
+        assert torch.allclose(la, lb, rtol=2e-5, atol=1e-6)
+        (la * upstream).sum().backward()
+        (lb * upstream).sum().backward()
+        assert torch.allclose(sa.grad, sb.grad, rtol=1e-4, atol=1e-7 * float(sb.grad.abs().max()))
+    # inference-style call: no gradient buffer is produced
+    loss, grad = ahv.ops.infonce(s0, Rsh, gt, 15.0, want_grad=False)
+    assert grad is None and torch.allclose(loss, lb.detach(), rtol=2e-5, atol=1e-6)

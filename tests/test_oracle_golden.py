@@ -192,3 +192,27 @@ def test_c_oracle_backward_matches_reference_autograd(golden, oracle):
     for name, val in got.items():
         ref = tr[name].astype(np.float64)
         np.testing.assert_allclose(val.reshape(ref.shape), ref, rtol=0, atol=2e-5 * np.abs(ref).max(), err_msg=name)
+
+
+def test_resblock3d_restatement_vs_reference(golden_lift, oracle):
+    """ResNetBlock_3D(32->16) (modules/modules.py:9-47, :100-101): numpy restatement against the fixture written by
+    the reference's own module (oracle/make_golden_lift.py)."""
+    g = golden_lift
+    out = oracle.resblock3d_np(g["x"], g["conv1_w"], g["conv2_w"], g["down_w"])
+    assert out.shape == (3, 16, 8, 8, 8)
+    np.testing.assert_allclose(out, g["out"], atol=2e-6, rtol=0)
+
+
+def test_generator_restatements_are_rotations(oracle):
+    """Philox sampler / refinement-set restatements (extensions): structural checks on the CPU; the CUDA generators
+    are compared with them in tests/test_gpu_configs.py."""
+    R = oracle.sample_rotations_np(5000, seed=3)
+    assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 3e-6 and np.allclose(np.linalg.det(R), 1, atol=1e-5)
+    assert np.array_equal(oracle.sample_rotations_np(100, 3, first_index=700), R[700:800])       # counter-based: shardable
+    ang = np.degrees(np.arccos(np.clip((np.trace(R, axis1=1, axis2=2) - 1) / 2, -1, 1)))
+    assert abs(ang.mean() - 126.5) < 1.5                                                          # Haar
+    P = oracle.perturb_rotations_np(R[:8], 40, 6.0, seed=2)
+    assert P.shape == (8, 40, 3, 3) and np.array_equal(P[:, 0], R[:8])
+    rel = np.einsum("nmij,nkj->nmik", P, R[:8])
+    a = np.degrees(np.arccos(np.clip((np.trace(rel, axis1=2, axis2=3) - 1) / 2, -1, 1)))
+    assert a.max() <= 6.0 + 1e-2 and a[:, 1:].mean() > 1.0
