@@ -7,6 +7,7 @@
 // One launch: a thread-block CLUSTER of 8 CTAs per volume, CTA r = depth slab d = r.  Each CTA computes conv1+ReLU
 // for its own slab into shared memory, the cluster synchronises, conv2 reads the two neighbouring slabs straight
 // out of the neighbours' shared memory (DSMEM) - nothing is recomputed and the intermediate never touches HBM.
+// Clusters are persistent: a cluster stages the 84 KB of weights once and walks its share of the volumes.
 // fp32 FFMA throughout (bit-tight against the reference's fp32 CPU path; tensor cores are not used here because
 // this stage is 1 % of the scoring kernel's time and feeds it its input, whose parity is measured in fp32).
 //
@@ -78,7 +79,7 @@ __device__ __forceinline__ void reduce_icg(float (&acc)[8][4]) {  // sum over th
 
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(kThreads, 1)
 resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, const float* __restrict__ Wc2,
-                  const float* __restrict__ Wd, float* __restrict__ out) {
+                  const float* __restrict__ Wd, float* __restrict__ out, int M) {
   extern __shared__ __align__(16) float sm[];
   float* xs = sm;
   float* w1s = xs + kXs;
@@ -89,29 +90,51 @@ resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, co
   float* hs_hi = hs_lo + kHs;
   cg::cluster_group cluster = cg::this_cluster();
   const int d = (int)cluster.block_rank();
-  const int m = blockIdx.x / 8;
   const int t = threadIdx.x, lane = t & 31, h = t >> 5, ocg = lane & 3, icg = lane >> 2;
-  const float* xm = x + (size_t)m * kCin * kVox;
 
-  // ---- stage: zero the padded buffers, then input slabs and weights ----
+  // ---- once per CTA: zero the padded buffers, stage the weights (loads batched 9 deep: one L2 round trip each) ----
   for (int i = t; i < kXs + 0; i += kThreads) xs[i] = 0.0f;
   for (int i = t; i < 3 * kHs; i += kThreads) hs_own[i] = 0.0f;
+  {
+    float v[9];
+    for (int i0 = 0; i0 < kW1s; i0 += 9 * kThreads) {  // global [oc][ic][27] -> shared [ic][27][oc]
+#pragma unroll
+      for (int j = 0; j < 9; ++j) v[j] = i0 + j * kThreads + t < kW1s ? __ldg(Wc1 + i0 + j * kThreads + t) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int i = i0 + j * kThreads + t;
+        if (i < kW1s) w1s[(((i / 27) % kCin) * 27 + i % 27) * kCout + i / (27 * kCin)] = v[j];
+      }
+    }
+    for (int i0 = 0; i0 < kW2s; i0 += 9 * kThreads) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) v[j] = i0 + j * kThreads + t < kW2s ? __ldg(Wc2 + i0 + j * kThreads + t) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const int i = i0 + j * kThreads + t;
+        if (i < kW2s) w2s[(((i / 27) % kCout) * 27 + i % 27) * kCout + i / (27 * kCout)] = v[j];
+      }
+    }
+    for (int i = t; i < kWds; i += kThreads) wds[(i % kCin) * kCout + i / kCin] = __ldg(Wd + i);
+  }
   __syncthreads();
-  for (int i = t; i < kCin * 3 * 64; i += kThreads) {  // [ic][dz][hw]: 64 consecutive floats per (ic, dz)
-    const int hw = i & 63, dz = (i >> 6) % 3, ic = i / 192;
-    const int dd = d + dz - 1;
-    if (dd >= 0 && dd < 8)
-      xs[(ic * 3 + dz) * kPlane + ((hw >> 3) + 1) * kRow + (hw & 7) + 1] = __ldg(xm + ic * kVox + dd * 64 + hw);
+
+  // ---- persistent over volumes: cluster c takes volumes c, c + #clusters, ... (weights staged once) ----
+  for (int m = blockIdx.x / 8; m < M; m += gridDim.x / 8) {
+  const float* xm = x + (size_t)m * kCin * kVox;
+  {  // input slabs d-1, d, d+1 (planes outside the volume stay zero): 24 loads per thread, all in flight
+    float v[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {  // [ic][dz][hw]: 64 consecutive floats per (ic, dz)
+      const int i = j * kThreads + t, hw = i & 63, dz = (i >> 6) % 3, ic = i / 192, dd = d + dz - 1;
+      v[j] = (dd >= 0 && dd < 8) ? __ldg(xm + ic * kVox + dd * 64 + hw) : 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+      const int i = j * kThreads + t, hw = i & 63, dz = (i >> 6) % 3, ic = i / 192;
+      xs[(ic * 3 + dz) * kPlane + ((hw >> 3) + 1) * kRow + (hw & 7) + 1] = v[j];
+    }
   }
-  for (int i = t; i < kW1s; i += kThreads) {  // global [oc][ic][27] -> shared [ic][27][oc]
-    const int tap = i % 27, ic = (i / 27) % kCin, oc = i / (27 * kCin);
-    w1s[(ic * 27 + tap) * kCout + oc] = __ldg(Wc1 + i);
-  }
-  for (int i = t; i < kW2s; i += kThreads) {
-    const int tap = i % 27, ic = (i / 27) % kCout, oc = i / (27 * kCout);
-    w2s[(ic * 27 + tap) * kCout + oc] = __ldg(Wc2 + i);
-  }
-  for (int i = t; i < kWds; i += kThreads) wds[(i % kCin) * kCout + i / kCin] = __ldg(Wd + i);
   __syncthreads();
 
   // ---- conv1 + ReLU for slab d: 4 input channels per thread ----
@@ -198,19 +221,23 @@ resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, co
       dst[1] = make_float4(acc[4][o], acc[5][o], acc[6][o], acc[7][o]);
     }
   }
+  __syncthreads();  // the input slabs are overwritten by the next volume
+  }
 }
 }  // namespace lift
 
 int launch_resblock3d(const float* x, const float* Wc1, const float* Wc2, const float* Wd, float* out, int64_t m,
                       cudaStream_t s) {
   if (m == 0) return AHV_OK;
+  if (m > 0x7fffffffLL) return AHV_EINVAL;
   AHV_CUDA_OK(cudaFuncSetAttribute(lift::resblock3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lift::kSmemBytes));
-  for (int64_t m0 = 0; m0 < m; m0 += 1 << 20) {  // grid.x limit is far away; chunking keeps the index math 32-bit
-    const int64_t nm = m - m0 < (1 << 20) ? m - m0 : (1 << 20);
-    lift::resblock3d_kernel<<<(unsigned)(nm * 8), lift::kThreads, lift::kSmemBytes, s>>>(
-        x + (size_t)m0 * lift::kCin * kVox, Wc1, Wc2, Wd, out + (size_t)m0 * lift::kCout * kVox);
-    AHV_CUDA_OK(cudaGetLastError());
-  }
+  int dev = 0, sms = 0;
+  AHV_CUDA_OK(cudaGetDevice(&dev));
+  AHV_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t resident = sms / 8 > 0 ? sms / 8 : 1;  // one CTA per SM (154 KB): clusters that fit at once
+  const int clusters = (int)(m < resident ? m : resident);
+  lift::resblock3d_kernel<<<(unsigned)(clusters * 8), lift::kThreads, lift::kSmemBytes, s>>>(x, Wc1, Wc2, Wd, out, (int)m);
+  AHV_CUDA_OK(cudaGetLastError());
   return AHV_OK;
 }
 

@@ -114,3 +114,47 @@ def test_named_backbone_architecture_shape():
     with torch.no_grad():
         out = bb(torch.randn(1, 3, 256, 256))
     assert out.shape == (1, 768, 8, 8)
+
+
+def test_reference_shaped_checkpoint_loads():
+    """A checkpoint with the reference's key layout (feature_aligner.* + the MiDaS/timm wrapper's
+    feature_extractor.pretrained.model.* + the unused DPT decoder feature_extractor.scratch.*) loads into the
+    drop-in Estimator: aligner strictly by name, backbone through the timm -> torchvision mapping."""
+    import re
+
+    from modules._backbone import load_reference_state_dict
+    from modules.model_co3d import Estimator
+
+    torch.manual_seed(0)
+    src = Estimator(_cfg()).eval()
+    ref_sd = {"feature_aligner." + k: v.clone() for k, v in src.feature_aligner.state_dict().items()}
+    for k, v in src.feature_extractor.model.state_dict().items():       # torchvision -> timm names (inverse mapping)
+        m = re.match(r"features\.(\d)\.(.+)$", k)
+        if not m:                                                        # final norm.*: same name in timm
+            ref_sd["feature_extractor.pretrained.model." + k] = v.clone()
+            continue
+        i, rest = int(m.group(1)), m.group(2)
+        if i == 0:
+            name = ("patch_embed.proj." if rest.startswith("0.") else "patch_embed.norm.") + rest.split(".", 1)[1]
+        elif i % 2 == 1:
+            j, tail = rest.split(".", 1)
+            tail = tail.replace("mlp.0.", "mlp.fc1.").replace("mlp.3.", "mlp.fc2.")
+            if tail == "attn.qkv.bias":
+                c = v.shape[0] // 3
+                ref_sd[f"feature_extractor.pretrained.model.layers.{i // 2}.blocks.{j}.attn.q_bias"] = v[:c].clone()
+                ref_sd[f"feature_extractor.pretrained.model.layers.{i // 2}.blocks.{j}.attn.v_bias"] = v[2 * c:].clone()
+                continue
+            name = f"layers.{i // 2}.blocks.{j}.{tail}"
+        else:
+            name = f"layers.{i // 2 - 1}.downsample.{rest}"
+        ref_sd["feature_extractor.pretrained.model." + name] = v.clone()
+    ref_sd["feature_extractor.scratch.output_conv.0.weight"] = torch.zeros(4, 4)       # DPT decoder: never executed
+    torch.manual_seed(1)
+    dst = Estimator(_cfg()).eval()
+    rep = load_reference_state_dict(dst, {"state_dict": ref_sd})
+    assert rep["skipped"] == ["feature_extractor.scratch.output_conv.0.weight"] and rep["backbone_missing"] == []
+    img = torch.randn(1, 3, 256, 256)
+    with torch.no_grad():
+        a, b = src(img, img.flip(-1)), dst(img, img.flip(-1))
+    # qkv.bias carries a k-bias in torchvision that timm does not have: the stand-in zeroes it at construction
+    assert torch.allclose(a[0], b[0], atol=1e-5) and torch.allclose(a[1], b[1], atol=1e-5)
