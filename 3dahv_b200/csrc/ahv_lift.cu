@@ -26,13 +26,19 @@ namespace lift {
 constexpr int kCin = 32, kCout = 16, kRow = 12, kPlane = 10 * kRow;  // padded planes: [10 h][12 w] (w index 0 = w -1)
 constexpr int kThreads = 256;
 // shared memory (floats)
-constexpr int kXs = kCin * 3 * kPlane;          // input slabs d-1, d, d+1 with zero halo          11520
-constexpr int kW1s = kCin * 27 * kCout;         // conv1 weights [ic][kd][kh][kw][oc]               13824
-constexpr int kW2s = kCout * 27 * kCout;        // conv2 weights [ic][kd][kh][kw][oc]                6912
+// A thread's input-channel group (icg = lane >> 2) selects a slice of the inputs and of the weights; the slices are
+// padded by 16 floats so that consecutive groups start 64 B apart modulo 128: the two groups of a quarter-warp then
+// hit opposite bank halves (LDS.128: 4 lanes x 16 B of weights per group, one broadcast address of inputs per group).
+constexpr int kXsIcg = 4 * 3 * kPlane + 16;     // conv1: 4 input channels per group
+constexpr int kW1Icg = 4 * 27 * kCout + 16;
+constexpr int kW2Icg = 2 * 27 * kCout + 16;     // conv2: 2 input channels per group
+constexpr int kXs = 8 * kXsIcg;                 // input slabs d-1, d, d+1 with zero halo
+constexpr int kW1s = 8 * kW1Icg;                // conv1 weights [icg][ic%4][kd][kh][kw][oc]
+constexpr int kW2s = 8 * kW2Icg;                // conv2 weights [icg][ic%2][kd][kh][kw][oc]
 constexpr int kWds = kCin * kCout;              // downsample   [ic][oc]                               512
 constexpr int kHs = kCout * kPlane;             // one conv1 output slab with zero halo (own: DSMEM-visible)  1920
 constexpr int kSmemFloats = kXs + kW1s + kW2s + kWds + 3 * kHs;
-constexpr int kSmemBytes = kSmemFloats * 4;     // 154 112 B
+constexpr int kSmemBytes = kSmemFloats * 4;     // 155 648 B
 
 // acc[w][o] += sum over the thread's channels / taps.  `in` points at channel 0 of the thread's group, plane dz = 0.
 template <int kChannels, int kChStride, int kPlaneStride>
@@ -97,22 +103,28 @@ resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, co
   for (int i = t; i < 3 * kHs; i += kThreads) hs_own[i] = 0.0f;
   {
     float v[9];
-    for (int i0 = 0; i0 < kW1s; i0 += 9 * kThreads) {  // global [oc][ic][27] -> shared [ic][27][oc]
+    for (int i0 = 0; i0 < kCin * 27 * kCout; i0 += 9 * kThreads) {  // global [oc][ic][27] -> shared [ic][27][oc]
 #pragma unroll
-      for (int j = 0; j < 9; ++j) v[j] = i0 + j * kThreads + t < kW1s ? __ldg(Wc1 + i0 + j * kThreads + t) : 0.0f;
+      for (int j = 0; j < 9; ++j) v[j] = i0 + j * kThreads + t < kCin * 27 * kCout ? __ldg(Wc1 + i0 + j * kThreads + t) : 0.0f;
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int i = i0 + j * kThreads + t;
-        if (i < kW1s) w1s[(((i / 27) % kCin) * 27 + i % 27) * kCout + i / (27 * kCin)] = v[j];
+        if (i < kCin * 27 * kCout) {
+          const int ic = (i / 27) % kCin;
+          w1s[(ic >> 2) * kW1Icg + ((ic & 3) * 27 + i % 27) * kCout + i / (27 * kCin)] = v[j];
+        }
       }
     }
-    for (int i0 = 0; i0 < kW2s; i0 += 9 * kThreads) {
+    for (int i0 = 0; i0 < kCout * 27 * kCout; i0 += 9 * kThreads) {
 #pragma unroll
-      for (int j = 0; j < 9; ++j) v[j] = i0 + j * kThreads + t < kW2s ? __ldg(Wc2 + i0 + j * kThreads + t) : 0.0f;
+      for (int j = 0; j < 9; ++j) v[j] = i0 + j * kThreads + t < kCout * 27 * kCout ? __ldg(Wc2 + i0 + j * kThreads + t) : 0.0f;
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
         const int i = i0 + j * kThreads + t;
-        if (i < kW2s) w2s[(((i / 27) % kCout) * 27 + i % 27) * kCout + i / (27 * kCout)] = v[j];
+        if (i < kCout * 27 * kCout) {
+          const int ic = (i / 27) % kCout;
+          w2s[(ic >> 1) * kW2Icg + ((ic & 1) * 27 + i % 27) * kCout + i / (27 * kCout)] = v[j];
+        }
       }
     }
     for (int i = t; i < kWds; i += kThreads) wds[(i % kCin) * kCout + i / kCin] = __ldg(Wd + i);
@@ -132,7 +144,7 @@ resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, co
 #pragma unroll
     for (int j = 0; j < 24; ++j) {
       const int i = j * kThreads + t, hw = i & 63, dz = (i >> 6) % 3, ic = i / 192;
-      xs[(ic * 3 + dz) * kPlane + ((hw >> 3) + 1) * kRow + (hw & 7) + 1] = v[j];
+      xs[(ic >> 2) * kXsIcg + ((ic & 3) * 3 + dz) * kPlane + ((hw >> 3) + 1) * kRow + (hw & 7) + 1] = v[j];
     }
   }
   __syncthreads();
@@ -143,7 +155,7 @@ resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, co
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int o = 0; o < 4; ++o) acc[i][o] = 0.0f;
-  conv_rows<4, 3 * kPlane, kPlane>(acc, xs + icg * 4 * 3 * kPlane, w1s + icg * 4 * 27 * kCout, h, ocg);
+  conv_rows<4, 3 * kPlane, kPlane>(acc, xs + icg * kXsIcg, w1s + icg * kW1Icg, h, ocg);
   reduce_icg(acc);
   if (icg == 0) {
 #pragma unroll
@@ -182,7 +194,7 @@ resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, co
         const float4 a = *reinterpret_cast<const float4*>(row), b = *reinterpret_cast<const float4*>(row + 4);
         const float2 e = *reinterpret_cast<const float2*>(row + 8);
         const float xv[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, e.x, e.y};
-        const float* wp = w2s + ((ic * 3 + kd) * 3 + kh) * 3 * kCout + ocg * 4;
+        const float* wp = w2s + icg * kW2Icg + ((c * 3 + kd) * 3 + kh) * 3 * kCout + ocg * 4;
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
           const float4 wv = *reinterpret_cast<const float4*>(wp + kw * kCout);
@@ -200,7 +212,7 @@ resblock3d_kernel(const float* __restrict__ x, const float* __restrict__ Wc1, co
 #pragma unroll
   for (int c = 0; c < 4; ++c) {  // downsample: 1x1x1 conv of the input slab d (plane dz = 1)
     const int ic = icg * 4 + c;
-    const float* row = xs + (ic * 3 + 1) * kPlane + (h + 1) * kRow + 1;
+    const float* row = xs + icg * kXsIcg + (c * 3 + 1) * kPlane + (h + 1) * kRow + 1;
     const float4 wv = *reinterpret_cast<const float4*>(wds + ic * kCout + ocg * 4);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {

@@ -233,8 +233,11 @@ __device__ __forceinline__ float ld_raw<float>(const float* p) { return *p; }
 template <>
 __device__ __forceinline__ float ld_raw<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
+#ifndef AHV_STAGE_INLINE
+#define AHV_STAGE_INLINE __forceinline__
+#endif
 template <typename T, bool K16>
-__device__ __forceinline__ float stage_pair_volume(unsigned char* vsm, const T* raw, uint32_t bar_vol, uint32_t parity,
+__device__ AHV_STAGE_INLINE float stage_pair_volume(unsigned char* vsm, const T* raw, uint32_t bar_vol, uint32_t parity,
                                                    uint32_t* l1max_bits, const float* __restrict__ W1, bool first,
                                                    float* red, int gtid) {
   float wnorm = 0.0f;

@@ -1,4 +1,4 @@
-"""p50 per-pair latency (B=1) through CUDA-graph replay: AHV_NS="3000,50000", AHV_PDL=0|1, AHV_VOL=f32|bf16."""
+"""p50 per-pair latency (B=1) through CUDA-graph replay: AHV_NS="3000,50000", AHV_VOL=f32|bf16."""
 import importlib, os, statistics, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -21,4 +21,4 @@ for n in ns:
         a.record(); gv(); b.record()
     torch.cuda.synchronize()
     t = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
-    print(f"N={n} pdl={os.environ.get('AHV_PDL', '1')} p50={statistics.median(t):.1f}us p10={t[20]:.1f} p90={t[180]:.1f} idx={int(gv.out.topk_idx[0, 0])}")
+    print(f"N={n} p50={statistics.median(t):.1f}us p10={t[20]:.1f} p90={t[180]:.1f} idx={int(gv.out.topk_idx[0, 0])}")
