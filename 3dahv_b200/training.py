@@ -12,6 +12,13 @@ through PyTorch autograd (`head_torch`, negligible).  Gradients therefore flow t
 the hot path (`forward_2d3d`, the backbone).  `fused_backward=False` selects the earlier chunked
 recomputation (library `ahv_rotate_volume` / `ahv_rotate_volume_backward` + PyTorch head), kept as an
 independent cross-check.
+
+Arithmetic: with the default `math=MATH_TC` the FORWARD scores carry the tensor-core path's fp16-operand error
+(~1e-4 relative) while the fused backward recomputes the forward in fp32, i.e. the gradient is that of a function
+1e-4 away from the loss reported (tests/test_gpu_training.py holds the end-to-end gradients to 5e-3 of their maximum
+against the reference's autograd in this mode, 2e-4 with `math=MATH_FP32`, which is 8x slower in the forward only).
+The backward accumulates dV, dT, dW1, dW2, db2 across CTAs with float atomics, so gradients are reproducible to
+rounding, not bit for bit, from run to run.
 """
 from __future__ import annotations
 

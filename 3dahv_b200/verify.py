@@ -131,6 +131,7 @@ class GraphedVerifier:
         self.vol_tgt = torch.zeros(B, 16, 8, 8, 8, device=dev)
         self.R = torch.eye(3, device=dev).repeat(*((B, N) if per_pair_R else (N,)), 1, 1).contiguous()
         self.k = min(k, N)
+        self.peer = peer
 
         def run():
             if peer is None:
@@ -161,6 +162,58 @@ class GraphedVerifier:
             self.R.copy_(R, non_blocking=True)
         self.graph.replay()
         return self.out
+
+    def check(self) -> int:
+        """Sharded replays only: synchronises and raises if an exchange timed out waiting for a peer (that step's
+        results are NaN / index -1); returns the number of exchanges this rank has completed."""
+        return self.peer.check() if self.peer is not None else 0
+
+
+class GraphedRefiner:
+    """CUDA-graph replay of the two-pass selection (`ahv_refine`: dense set -> top-k -> m local candidates each ->
+    arg-max; BASELINE config 4) for fixed (B, N, k, m): the whole chain - target features, both scoring passes, top-k,
+    candidate generation, selection - is one C call with no host step or torch op inside, so it captures as it stands.
+    Outputs are static tensors valid until the next replay."""
+
+    def __init__(self, verifier: HypothesisVerifier, B: int, N: int, k: int = 32, m: int = 64, max_angle_deg: float = 5.0,
+                 seed: int = 0, device="cuda", vol_dtype=torch.float32):
+        dev = torch.device(device)
+        self.v = verifier.to(dev)
+        self.vol_src = torch.zeros(B, 16, 8, 8, 8, device=dev, dtype=vol_dtype)
+        self.vol_tgt = torch.zeros(B, 16, 8, 8, 8, device=dev)
+        self.R = torch.eye(3, device=dev).repeat(N, 1, 1).contiguous()
+        k = min(k, N)
+        W1, W2, b2 = self.v._weights_on(dev)
+
+        def run(out=None, ws=None):
+            return ops.refine(self.vol_src, self.vol_tgt, self.R, W1, W2, b2, k=k, m=m, max_angle_deg=max_angle_deg, seed=seed,
+                              math=self.v.math, workspace=ws, out=out)
+
+        stream = torch.cuda.Stream(device=dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(stream):
+            res = run()
+            res = run(res[:7], res[7])             # warm-up on the buffers the graph will use
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        torch.cuda.synchronize(dev)
+        self._bufs, self._ws = res[:7], res[7]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            run(self._bufs, self._ws)
+        fv, fi, fR, self.candidates, self.best_val, self.best_idx, self.R_best = self._bufs
+        self.first = VerifyResult(None, fv, fi, fR)
+
+    @torch.no_grad()
+    def __call__(self, vol_src=None, vol_tgt=None, R=None):
+        """Returns (R_best [B,3,3], score [B]); `.first` holds the first pass's top-k, `.candidates` the refinement set."""
+        if vol_src is not None:
+            self.vol_src.copy_(vol_src, non_blocking=True)
+        if vol_tgt is not None:
+            self.vol_tgt.copy_(vol_tgt, non_blocking=True)
+        if R is not None:
+            self.R.copy_(R, non_blocking=True)
+        self.graph.replay()
+        return self.R_best, self.best_val
 
 
 class GraphedTail:

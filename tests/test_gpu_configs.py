@@ -184,3 +184,18 @@ def test_generators_vs_restatements(ahv, oracle):
     rel = P @ c[:, None].transpose(-1, -2)
     ang = torch.rad2deg(torch.arccos(((rel.diagonal(dim1=-2, dim2=-1).sum(-1) - 1) / 2).clamp(-1, 1)))
     assert float(ang.max()) <= 7.5 + 1e-2
+
+
+def test_graphed_refiner_equals_eager(ahv, golden):
+    """The two-pass selection is one C call with nothing on the host in between: it captures into a CUDA graph."""
+    B, N, k, m = 3, 5000, 16, 32
+    vs, vt = _volumes(B, 7)
+    R = ahv.so3.grid_rotations(N, device=DEV)
+    v = _verifier(ahv, golden)
+    gr = ahv.GraphedRefiner(v, B, N, k=k, m=m, max_angle_deg=3.0, seed=9, device=DEV)
+    for flip in (False, True):
+        a, b = (vs.flip(0), vt.flip(0)) if flip else (vs, vt)
+        Rb, val = gr(a.to(DEV), b.to(DEV), R)
+        R_ref, val_ref, first, cand = v.refine(a.to(DEV), b.to(DEV), R, k=k, m=m, max_angle_deg=3.0, seed=9)
+        assert torch.equal(Rb, R_ref) and torch.equal(val, val_ref)
+        assert torch.equal(gr.first.topk_idx, first.topk_idx) and torch.equal(gr.candidates, cand)
