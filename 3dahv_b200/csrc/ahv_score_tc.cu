@@ -153,10 +153,16 @@ static int make_volume_map(const void* vol_src, int B, bool bf16, CUtensorMap* m
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  AHV_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  if (!fn || qres != cudaDriverEntryPointSuccess) return AHV_ECUDA;
+  // the driver's encoder, looked up once (an immutable function pointer, not state)
+  static void* const fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return f;
+  }();
+  if (!fn) return AHV_ECUDA;
   const cuuint64_t esz = bf16 ? 2 : 4;
   const cuuint64_t dims[3] = {64, 8, (cuuint64_t)B * kC};
   const cuuint64_t strides[2] = {64 * esz, 512 * esz};  // bytes between d slices, between channels
@@ -214,8 +220,12 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   const int mst = make_volume_map(vol_src, B, sizeof(T) == 2, &vol_map);
   if (mst != AHV_OK) return mst;
   AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
+  // CTAs that inherit the prologue's SMs start late; only worth compensating when the prologue is smaller than this
+  // grid and every CTA has tiles to spare (see the work split in the kernel)
+  int late = 0;
+  if (prologue && kTgtCtasPerPair * (int64_t)B <= grid / 2 && (int64_t)B * N / grid >= 8) late = kTgtCtasPerPair * B;
   return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue, vol_map, tgt, R, r_per_pair, b2, base, W1,
-                    W2, scores, keys, B, N, fin);
+                    W2, scores, keys, B, N, fin, late);
 }
 
 }  // namespace tc

@@ -4,8 +4,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 ahv = importlib.import_module("3dahv_b200")
+if os.environ.get("AHV_VARIANT_LIB"):   # scripts-only: point the loader at the diagnostics build
+    ahv._lib.LIB_PATH = os.path.abspath(os.environ["AHV_VARIANT_LIB"])
+    ahv._lib.SIGNATURES["ahv_diag_timeline"] = (ctypes.c_int, [ctypes.c_void_p])
 dev = torch.device("cuda", 0)
-N = int(os.environ.get("AHV_N", "296"))
+N = int(os.environ.get("AHV_N", "3000"))
 W1, W2, b2, vs, vt, normals = bench.synthetic_inputs(torch, 1, N)
 v = ahv.HypothesisVerifier(W1.to(dev), W2.to(dev), b2.to(dev))
 R = ahv.ops.rotations_from_normals(normals.to(dev))
