@@ -82,27 +82,6 @@ score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __r
     reinterpret_cast<uint4*>(vol)[i] = make_uint4(0, 0, 0, 0);  // halo stays zero for the whole kernel
   if (threadIdx.x < 8) sbase[threadIdx.x] = base[threadIdx.x];
   if (threadIdx.x == 8) *l1max_bits = 0u;
-  if (warp == kMmaWarp) {
-    if (lane == 0) {
-      for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(bar0 + (kD1Full + i) * 8, 1);
-        mbar_init(bar0 + (kD1Empty + i) * 8, 4);
-        mbar_init(bar0 + (kA2Full + i) * 8, 4);
-        mbar_init(bar0 + (kD2Full + i) * 8, 1);
-      }
-      mbar_init(bar0 + kVolFull * 8, 1);
-      mbar_init(bar0 + (kVolFull + 1) * 8, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), M::tmem_cols);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (threadIdx.x == 0) AHV_TL(1);
   // ---- source volumes by TMA (cp.async.bulk.tensor, 3-D map over [B*16 ch][8 d][64 hw]; one box = one pair's
   // volume, 32 KB fp32 / 16 KB bf16).  The box of the pair that starts at tile t lands in A-operand stage buffer
   // t % kStages - idle at that moment: the tensor core finished reading it with tile t-3 and the gather fills it only
@@ -119,14 +98,36 @@ score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __r
     }
     ++vol_req;
   };
-  if (warp == kMmaWarp) {  // the first tile's pair, and the second tile's if it is another pair - before anything else
-    TileIter it0(work);
-    it0.advance();
-    request_volume(it0.b, 0);
-    int b1, c1; uint32_t n1;
-    it0.peek_tile(b1, n1, c1);
-    if (it0.left > 0 && b1 != it0.b) request_volume(b1, 1 % kStages);
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      for (int i = 0; i < 3; ++i) { mbar_init(bar0 + (kFull + i) * 8, kGatherWarps); mbar_init(bar0 + (kEmpty + i) * 8, 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar0 + (kD1Full + i) * 8, 1);
+        mbar_init(bar0 + (kD1Empty + i) * 8, 4);
+        mbar_init(bar0 + (kA2Full + i) * 8, 4);
+        mbar_init(bar0 + (kD2Full + i) * 8, 1);
+      }
+      mbar_init(bar0 + kVolFull * 8, 1);
+      mbar_init(bar0 + (kVolFull + 1) * 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    {  // the first tile's pair, and the second tile's if it is another pair - before anything else in this CTA (the
+       // barriers were initialised by this warp; nobody else touches the stage buffers yet)
+      TileIter it0(work);
+      it0.advance();
+      request_volume(it0.b, 0);
+      int b1, c1; uint32_t n1;
+      it0.peek_tile(b1, n1, c1);
+      if (it0.left > 0 && b1 != it0.b) request_volume(b1, 1 % kStages);
+    }
+    tmem_alloc(smem_u32(tmem_slot), M::tmem_cols);
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (threadIdx.x == 0) AHV_TL(1);
   if (warp >= kGatherWarps) {  // MMA + epilogue warps: weights -> fp16 operand layouts, then release the MMA warp
     pack_weights(smem + M::off_w1, W1, W2, threadIdx.x - kGatherWarps * 32);
     fence_proxy_async();  // written through the generic proxy, UMMA reads through the async proxy
