@@ -562,3 +562,66 @@ def test_misaligned_slices_are_accepted(ahv, golden):
         assert torch.equal(part.scores, full.scores[:, lo:])
         vs_view = T(g["vol_src"])[1:]                      # volumes: 32 KB per pair, always aligned; still a view
         assert v.score(vs_view, T(g["vol_tgt"])[1:], R[lo:], k=1).topk_idx.shape == (2, 1)
+
+
+def test_peer_exchange_protocol_on_one_gpu(ahv, golden):
+    """The NVLink exchange of the sharded step, exercised on ONE GPU: two "ranks" live in this process, each with its
+    own exchange buffer (plain device pointers - no IPC needed inside one process), its own stream and its own shard of
+    the rotation set.  Rank 0's kernel publishes its winners into both buffers and spins on rank 1's flag while rank 1's
+    kernel runs beside it on the other stream (only the LAST CTA of a scoring kernel waits, so the two grids need not
+    be co-resident).  Covers the fused k = 1 exchange, the top-k exchange kernel, B and k changing from step to step on
+    one buffer, an empty shard and the sequence counter - the multi-process version (CUDA IPC, NCCL bootstrap, graph
+    replay, host entry) is tests/test_gpu_dist.py, which needs two devices."""
+    import ctypes
+    from types import SimpleNamespace
+
+    dev = _dev()
+    lib = ahv._lib.lib()
+    g = golden["shared_n3000_b3"]
+    W1, W2, b2 = _weights(golden, dev)
+    v = ahv.HypothesisVerifier(W1, W2, b2)
+    vs, vt, R = (torch.from_numpy(g[k]).to(dev) for k in ("vol_src", "vol_tgt", "R"))
+    cap_pairs, cap_k, world = 4, 8, 2
+    bufs = []
+    for _ in range(world):
+        p = ctypes.c_void_p()
+        ahv._lib.check(lib.ahv_peer_alloc(cap_pairs, cap_k, ctypes.byref(p)), "ahv_peer_alloc")
+        bufs.append(p.value)
+    peers = [SimpleNamespace(rank=r, world=world, ptrs=bufs, max_pairs=cap_pairs, max_k=cap_k) for r in range(world)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    try:
+        steps = 0
+        for B, N, k in ((3, 3000, 1), (1, 1000, 1), (3, 2000, 8), (2, 501, 5), (3, 1, 1), (3, 3, 4), (3, 3000, 1)):
+            want = v.score(vs[:B], vt[:B], R[:N], k=k, return_scores=False)
+            torch.cuda.synchronize()
+            out = [None] * world
+            for r in range(world):
+                lo, hi = ahv.dist.shard_bounds(N, r, world)
+                streams[r].wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(streams[r]):
+                    out[r] = ahv.ops.verify_sharded(vs[:B], vt[:B], R[lo:hi].contiguous(), W1, W2, b2, lo, peers[r], k=k)
+            for s in streams:
+                s.synchronize()
+            steps += 1
+            kk = min(k, N)
+            for r in range(world):
+                val, idx, Rb = out[r]
+                if bool(torch.isnan(val).any()):      # a 20 s spin that timed out: the two streams were serialised
+                    pytest.skip("the two ranks' kernels were not scheduled concurrently on this device")
+                assert torch.equal(idx[:, :kk], want.topk_idx) and torch.equal(val[:, :kk], want.topk_val), (B, N, k, r)
+                assert torch.equal(Rb[:, :kk], want.R_best), (B, N, k, r)
+                assert bool((idx[:, kk:] == -1).all())
+            seq, err = ctypes.c_uint32(), ctypes.c_uint32()
+            for r in range(world):
+                ahv._lib.check(lib.ahv_peer_status(bufs[r], ctypes.byref(seq), ctypes.byref(err)), "ahv_peer_status")
+                assert seq.value == steps and err.value == 0
+        # a call larger than the capacity the buffers were allocated with is rejected before anything is launched
+        with pytest.raises(ValueError):
+            ahv.ops.verify_sharded(vs, vt, R[:100].contiguous(), W1, W2, b2, 0, peers[0], k=cap_k + 1)
+        mp, mk = ctypes.c_int(), ctypes.c_int()
+        ahv._lib.check(lib.ahv_peer_capacity(bufs[0], ctypes.byref(mp), ctypes.byref(mk)), "ahv_peer_capacity")
+        assert (mp.value, mk.value) == (cap_pairs, cap_k)
+    finally:
+        torch.cuda.synchronize()
+        for p in bufs:
+            lib.ahv_peer_free(p)
