@@ -64,3 +64,31 @@ def test_ops_refuse_cpu_tensors(ahv):
         ahv.ops.forward_3d2d(torch.zeros(1, 16, 8, 8, 8), torch.zeros(32, 384), torch.zeros(32, 32), torch.zeros(32))
     with pytest.raises(RuntimeError):
         ahv.so3.random_rotations(4, device="cpu")
+
+
+def test_argument_validation_of_round2_entries_without_gpu(ahv):
+    """Every entry added in round 2 rejects malformed arguments before it touches the device."""
+    import ctypes
+
+    lib, E = ahv._lib.lib(), ahv._lib.AHV_EINVAL
+    assert lib.ahv_peer_bytes(0, 1) == 0 and lib.ahv_peer_bytes(4, 33) == 0
+    assert lib.ahv_peer_bytes(4, 8) == 512 + 2 * 8 * 4 * 8 * 64                     # header + flags + entries[2][8][pairs][k]
+    p = ctypes.c_void_p()
+    assert lib.ahv_peer_alloc(0, 1, ctypes.byref(p)) == E and lib.ahv_peer_alloc(4, 0, ctypes.byref(p)) == E
+    assert lib.ahv_so3_perturb(None, 4, 0, 5.0, 0, None, None) == E                  # m >= 1
+    assert lib.ahv_so3_perturb(None, 4, 8, -1.0, 0, None, None) == E                 # angle in [0, 180]
+    assert lib.ahv_resblock3d(None, None, None, None, None, 3, None) == E
+    assert lib.ahv_infonce(None, None, 0, None, 15.0, 0.0, None, None, 2, 10, None) == E    # temperature > 0
+    assert lib.ahv_refine_workspace_bytes(2, 1000, 0, 8) == 0 and lib.ahv_refine_workspace_bytes(2, 1000, 33, 8) == 0
+    assert lib.ahv_refine_workspace_bytes(2, 1000, 8, 8) >= lib.ahv_workspace_bytes(2, 1000, 8) + lib.ahv_workspace_bytes(2, 64, 1)
+    args = [None] * 9
+    assert lib.ahv_refine(None, 0, None, None, 0, None, None, None, None, 8, 4, 5.0, 0, None, None, None, None, None, None, None,
+                          2, 4, 0, None, 0, None) == E                               # k > N
+    assert lib.ahv_topk_exchange(None, None, None, 0, 0, 10, 2, 1, None, None, None, 0, 2, None, 4, 1, None) == E
+    assert lib.ahv_verify_sharded(None, 0, None, None, 0, None, None, None, None, None, None, None, 0, 0, 2, 10, 0, None, 0, 0, 2,
+                                  None, 4, 1, None) == E                             # k >= 1
+    s = ctypes.c_void_p()
+    assert lib.ahv_predict_host_ex(None, None, 0, None, None, 0, None, None, None, None, None, None, None, None, 1, 0, 1, 1, 0,
+                                   0, 1, None, 0, 0, None) == E                      # no session
+    assert lib.ahv_host_session_destroy(None) == 0
+    assert lib.ahv_version() == 200

@@ -199,3 +199,31 @@ def test_graphed_refiner_equals_eager(ahv, golden):
         R_ref, val_ref, first, cand = v.refine(a.to(DEV), b.to(DEV), R, k=k, m=m, max_angle_deg=3.0, seed=9)
         assert torch.equal(Rb, R_ref) and torch.equal(val, val_ref)
         assert torch.equal(gr.first.topk_idx, first.topk_idx) and torch.equal(gr.candidates, cand)
+
+
+def test_round2_entry_edge_cases(ahv, golden):
+    """Degenerate sizes of the round-2 entries: refinement with k = m = 1 is plain arg-max selection, a zero cone keeps
+    every candidate on its centre, InfoNCE with no positive gives the reference's +inf loss with finite gradients, and
+    empty batches are no-ops."""
+    B, N = 2, 777
+    vs, vt = _volumes(B, 11)
+    R = ahv.so3.sample_rotations(N, seed=5, device=DEV)
+    v = _verifier(ahv, golden)
+    Rb, val, first, cand = v.refine(vs.to(DEV), vt.to(DEV), R, k=1, m=1, max_angle_deg=5.0)
+    plain = v.score(vs.to(DEV), vt.to(DEV), R, k=1, return_scores=False)
+    assert torch.equal(Rb, plain.R_best[:, 0]) and torch.equal(val, plain.topk_val[:, 0]) and torch.equal(cand[:, 0], Rb)
+    P = ahv.so3.perturb_rotations(R[:5], 9, 0.0, seed=1)
+    assert torch.allclose(P, R[:5, None].expand(-1, 9, -1, -1), atol=1e-6) and torch.equal(P[:, 0], R[:5])
+    # InfoNCE: no hypothesis within the threshold of the ground truth (modules/model.py:58-61 gives -log(0) = inf)
+    s = torch.rand(B, N, device=DEV)
+    gt = ahv.so3.sample_rotations(B, seed=99, device=DEV)
+    loss, grad = ahv.ops.infonce(s, R, gt, acc_thr_deg=1e-3)
+    assert bool(torch.isinf(loss).all()) and bool(torch.isfinite(grad).all())
+    e = torch.exp(s / 0.1)
+    assert torch.allclose(grad, e / 0.1 / e.sum(-1, keepdim=True), rtol=1e-4)
+    # empty batches
+    assert ahv.ops.resblock3d(torch.zeros(0, 32, 8, 8, 8, device=DEV), torch.zeros(16, 32, 3, 3, 3, device=DEV),
+                              torch.zeros(16, 16, 3, 3, 3, device=DEV), torch.zeros(16, 32, 1, 1, 1, device=DEV)).shape == (0, 16, 8, 8, 8)
+    assert ahv.so3.perturb_rotations(R[:0], 4, 3.0).shape == (0, 4, 3, 3)
+    with pytest.raises(ValueError):
+        v.refine(vs.to(DEV), vt.to(DEV), R, k=8, m=0)
