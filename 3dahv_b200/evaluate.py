@@ -1,7 +1,8 @@
 """The reference's evaluation loops as first-class callers of the fused path.
 
-    evaluate_category / evaluate_pairwise   test_co3d.py:93-198   (CO3D: per-category proposals, NP2 frame pairs)
-    test_category                           test_linemod.py:20-84 (LINEMOD / Objaverse: DataLoader of pair batches)
+    evaluate_category / evaluate_pairwise   test_co3d.py:93-198     (CO3D: per-category proposals, NP2 frame pairs)
+    test_category                           test_linemod.py:20-84   (LINEMOD: DataLoader of pair batches, gt similarity)
+    test_objaverse                          test_objaverse.py:14-46 (Objaverse: Trainer.test -> Estimator.test_step)
 
 Same arguments, same random draws in the same order (`random_rotations` from torch's CPU generator once per
 category / once per batch, `np.random.choice` for the key frames), same returned statistics.  What changes is
@@ -143,3 +144,32 @@ def test_category(cfg, model, dataloader, device="cuda", return_details: bool = 
     if return_details:
         return out + (pred_err.cpu().numpy(), torch.cat(gt_sims).cpu().numpy())
     return out
+
+
+@torch.no_grad()
+def test_objaverse(cfg, model, dataloader, device="cuda", out_dir: str | None = None):
+    """test_objaverse.py:14-46 without Lightning: what `pl.Trainer().test(model, dataloader)` does for this model -
+    `model.test_step(batch, i)` for every batch (modules/model.py:168-209: skip of small masks, a fresh hypothesis
+    set per step, fused verification, geodesic error appended to `step_outputs`, ground-truth distance to `gt_dis`,
+    predicted rotation to `pred_Rs`) - followed by the script's statistics.  Returns (mean error, Acc@30 %, Acc@15 %,
+    pred_Rs [n,9]); with `out_dir` also writes `objaverse_pred_Rs.txt` and appends to `result.txt` like the script."""
+    device = torch.device(device)
+    model.step_outputs.clear()
+    for i, batch in enumerate(dataloader):
+        batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        model.test_step(batch, i)
+    if not model.step_outputs:
+        raise RuntimeError("every batch was skipped (masks below SIZE_THR)")
+    pred_err = torch.cat(model.step_outputs)
+    acc_30 = 100 * (pred_err < 30).float().mean().item()
+    acc_15 = 100 * (pred_err < 15).float().mean().item()
+    err = pred_err.mean().item()
+    pred_Rs = np.concatenate([np.asarray(r).reshape(-1, 9) for r in model.pred_Rs])
+    if out_dir is not None:
+        import os
+
+        os.makedirs(out_dir, exist_ok=True)
+        np.savetxt(os.path.join(out_dir, "objaverse_pred_Rs.txt"), pred_Rs)
+        with open(os.path.join(out_dir, "result.txt"), "a") as f:
+            f.write("err: %.2f || avg_acc_30: %.2f || avg_acc_15: %.2f \n" % (err, acc_30, acc_15))
+    return err, acc_30, acc_15, pred_Rs

@@ -205,3 +205,22 @@ def test_estimator_steps_vs_oracle_idiom(ahv, oracle):
     # the fused scores themselves
     fused = model.score_rotations(vs.to(DEV), vt.to(DEV), R.to(DEV)).cpu()
     assert float(((fused - sim_ref).abs() / sim_ref.abs().clamp_min(1e-6)).max()) <= TOL
+
+
+def test_objaverse_driver(ahv, tmp_path):
+    """test_objaverse.py:14-46: Trainer.test -> test_step per batch, then error / Acc@30 / Acc@15 and the files."""
+    from modules.model import Estimator
+
+    torch.manual_seed(0)
+    cfg = _cfg(800)
+    model = Estimator(cfg, feature_extractor=_TinyBackbone()).to(DEV).eval()
+    batches = _linemod_batches(3, 2, seed=4, bad=(2,))
+    model.step_outputs.append(torch.zeros(1, device=DEV))               # stale entries are cleared like the script does
+    err, acc30, acc15, pred_Rs = ahv.evaluate.test_objaverse(cfg, model, batches, device=DEV, out_dir=str(tmp_path))
+    assert pred_Rs.shape == (4, 9) and len(model.step_outputs) == 2 and len(model.gt_dis) == 2
+    errs = torch.cat(model.step_outputs).cpu().numpy()
+    assert np.isclose(err, errs.mean(), atol=1e-4) and np.isclose(acc30, 100 * np.mean(errs < 30))
+    R = torch.from_numpy(pred_Rs).reshape(4, 3, 3).float()
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(4, 3, 3), atol=1e-5)
+    saved = np.loadtxt(tmp_path / "objaverse_pred_Rs.txt")
+    assert np.allclose(saved, pred_Rs) and "avg_acc_30" in (tmp_path / "result.txt").read_text()
