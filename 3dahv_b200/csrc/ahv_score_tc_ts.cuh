@@ -1,6 +1,6 @@
-// TS-form scoring kernel (default): view x of conv1 and conv2's A operand go register -> TMEM (tcgen05.st)
-// and are consumed in the TS form of tcgen05.mma; only the YZ operand copy lives in shared memory; a
-// pipeline stage is a hypothesis pair.  Overview, roles and precision notes: ahv_score_tc.cu.
+// The scoring kernel: view x of conv1 and conv2's A operand go register -> TMEM (tcgen05.st) and are consumed in
+// the TS form of tcgen05.mma; only the YZ operand copy lives in shared memory; a pipeline stage is a tile of two
+// hypotheses; the source volumes arrive by TMA.  Overview, roles and precision notes: ahv_score_tc.cu.
 #pragma once
 #include "ahv_tc_common.cuh"
 
@@ -8,14 +8,14 @@ namespace ahv {
 namespace tc {
 
 // ==============================================================================================
-// TS variant (fp32 volumes): view x of conv1 never touches shared memory.  Each gather lane owns one
+// View x of conv1 never touches shared memory.  Each gather lane owns one
 // accumulator row (slot, d, h) - i.e. one TMEM lane - walks the 8 voxels along w, and writes the
 // fp16 channels of every voxel (a) once into the YZ copy (views y and z, K-major core matrices,
 // 144-byte row pitch so the STS.64 are conflict-free for this lane map) and (b) with tcgen05.st
 // straight into TMEM as the A operand of view x, which the MMA warp consumes in the TS form
 // (tcgen05.mma [d], [a_tmem], b_desc).  A and D of one M=64 tile share the lane offset (0 or 16),
-// verified by experiments/ts_mma_probe.cu.  Compared with the SS kernel this removes one 16 KB
-// operand copy (stores) and one 16 KB operand read per hypothesis from the shared-memory pipe.
+// verified by experiments/ts_mma_probe.cu.  Compared with keeping a second operand copy in shared memory this
+// removes 16 KB of stores and 16 KB of tensor-core reads per hypothesis from the shared-memory pipe.
 struct MapTS {
   // YZ operand copy of one tile (two hypotheses = slots), fp16, K-major core matrices [8 w rows][8 channels]:
   //   address = chalf*yz_ch + (d>>1)*yz_dhi + slot*yz_slot + (d&1)*yz_dlo + h*yz_h + w*16   (yz_h = 144: 16 B pad
