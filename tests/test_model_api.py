@@ -158,3 +158,17 @@ def test_reference_shaped_checkpoint_loads():
         a, b = src(img, img.flip(-1)), dst(img, img.flip(-1))
     # qkv.bias carries a k-bias in torchvision that timm does not have: the stand-in zeroes it at construction
     assert torch.allclose(a[0], b[0], atol=1e-5) and torch.allclose(a[1], b[1], atol=1e-5)
+    # the call the reference's scripts make (test_co3d.py:218): Estimator.load_from_checkpoint(path, cfg=cfg)
+    import os
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "checkpoint_co3d.ckpt")
+        torch.save({"state_dict": ref_sd, "hyper_parameters": {"cfg": _cfg()}, "epoch": 3}, path)
+        torch.manual_seed(2)
+        loaded = Estimator.load_from_checkpoint(path, cfg=_cfg()).eval()
+        assert loaded.load_report["backbone_missing"] == []
+        with torch.no_grad():
+            c = loaded(img, img.flip(-1))
+        assert torch.allclose(a[0], c[0], atol=1e-5)
+        assert Estimator.load_from_checkpoint(path).num_rota == _cfg()["DATA"]["NUM_ROTA"]    # cfg from hyper_parameters
