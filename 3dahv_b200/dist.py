@@ -193,3 +193,21 @@ class ShardedVerifier:
         else:
             R_best = R[safe]
         return val, idx, R_best
+
+    @torch.no_grad()
+    def refine(self, vol_src, vol_tgt, R, k: int = 32, m: int = 64, max_angle_deg: float = 5.0, seed: int = 0):
+        """Two-pass selection (BASELINE config 4) with BOTH passes sharded: pass 1 scores this rank's slice of the
+        dense set and the ranks exchange their top-k (identical on every rank afterwards, rotations included);
+        every rank then builds the same k*m candidates per pair (`ahv_so3_perturb`) and pass 2 shards THOSE over the
+        ranks, winners exchanged inside the scoring kernel.  With a `peer` exchange the whole thing contains no NCCL
+        call.  Returns (R_best [B,3,3], score [B], (first_val, first_idx, first_R), candidates [B,k*m,3,3]) - equal
+        to `HypothesisVerifier.refine` on one GPU."""
+        from . import so3
+
+        per_pair = R.dim() == 4
+        k = min(k, R.shape[1] if per_pair else R.shape[0])
+        first_val, first_idx, first_R = self.score(vol_src, vol_tgt, R, k=k)
+        B = vol_src.shape[0]
+        cand = so3.perturb_rotations(first_R.contiguous(), m, max_angle_deg, seed).reshape(B, k * m, 3, 3).contiguous()
+        val, _, R_best = self.score(vol_src, vol_tgt, cand, k=1)
+        return R_best[:, 0], val[:, 0], (first_val, first_idx, first_R), cand

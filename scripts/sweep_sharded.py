@@ -53,6 +53,25 @@ for B, N in points:
                 ms = float(t)
                 print(json.dumps({"gpus": world, "pairs": B, "hyps": N, "vol": name, "k": k, "ms_p50": ms,
                                   "hyp_pairs_per_s": B * N / (ms * 1e-3), "sharded_equals_unsharded": ok}), flush=True)
+# BASELINE config 4 sharded: 50 000-rotation grid + top-32 x 64 refinement, both passes sharded, no NCCL call
+B4, N4, k4, m4 = 8, 50_000, 32, 64
+vs4, vt4 = vs_all[:B4].to(dev), vt_all[:B4].to(dev)
+grid4 = ahv.so3.grid_rotations(N4, device=dev)
+for _ in range(3):
+    r4 = sv.refine(vs4, vt4, grid4, k=k4, m=m4, max_angle_deg=5.0, seed=1)
+dist.barrier(); torch.cuda.synchronize()
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+for a, b in ev:
+    a.record(); r4 = sv.refine(vs4, vt4, grid4, k=k4, m=m4, max_angle_deg=5.0, seed=1); b.record()
+torch.cuda.synchronize()
+t = torch.tensor([statistics.median(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    one = v.refine(vs4, vt4, grid4, k=k4, m=m4, max_angle_deg=5.0, seed=1)
+    ok = bool(torch.equal(one[0], r4[0]) and torch.equal(one[1], r4[1]) and torch.equal(one[2].topk_idx, r4[2][1]))
+    print(json.dumps({"gpus": world, "config4_sharded_refine": True, "pairs": B4, "grid": N4, "k": k4, "m": m4, "ms_p50": float(t),
+                      "hyp_pairs_per_s": B4 * (N4 + k4 * m4) / (float(t) * 1e-3), "sharded_equals_unsharded": ok}), flush=True)
+dist.barrier()
 peer.check()
 dist.barrier()
 peer.close()

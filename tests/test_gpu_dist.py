@@ -78,6 +78,11 @@ def _worker(rank, world, port, k, out_q):
     bs = v.score(vs.bfloat16(), vt, R, k=k, return_scores=False)
     out["bf16"] = (cpu(*fv.score(vs.bfloat16(), vt, R, k=k)), cpu(bs.topk_val, bs.topk_idx, bs.R_best))
     steps += 2
+    # (6b) two-pass selection (config 4) with both passes sharded: top-k exchange, then fused exchange
+    rR, rv, (fval_, fi, fR_), cand = fv.refine(vs, vt, R, k=k, m=16, max_angle_deg=4.0, seed=3)
+    sR, sv_, sfirst, scand = v.refine(vs, vt, R, k=k, m=16, max_angle_deg=4.0, seed=3)
+    out["refine"] = (cpu(rR, rv, fi, cand), cpu(sR, sv_, sfirst.topk_idx, scand))
+    steps += 2
     # (7) host-buffer entry, sharded: host slices in, whole-set selection out
     sess = ahv.ops.HostSession(dev)
     Rh = g["R"][lo:hi]
@@ -130,7 +135,7 @@ def test_sharded_equals_single_gpu(golden):
             assert np.all(got[1][:, kk:] == -1) and np.all(np.isneginf(got[0][:, kk:]))
         for kg, got in o["graph"]:
             assert _same(got, (sval[:, :kg], sidx[:, :kg], sR[:, :kg]))
-        assert _same(*o["per_pair"]) and _same(*o["bf16"])
+        assert _same(*o["per_pair"]) and _same(*o["bf16"]) and _same(*o["refine"])
         for kh, got in o["host"]:
             assert _same(got, (sval[:, :kh], sidx[:, :kh], sR[:, :kh]))
     assert _same(res[0]["fused_topk"], res[1]["fused_topk"])
