@@ -211,3 +211,23 @@ class ShardedVerifier:
         cand = so3.perturb_rotations(first_R.contiguous(), m, max_angle_deg, seed).reshape(B, k * m, 3, 3).contiguous()
         val, _, R_best = self.score(vol_src, vol_tgt, cand, k=1)
         return R_best[:, 0], val[:, 0], (first_val, first_idx, first_R), cand
+
+    @torch.no_grad()
+    def scores(self, vol_src, vol_tgt, R):
+        """The full pred_sim [B,N] (modules/model.py:193) of a sharded set on every rank: each rank scores its slice,
+        one NCCL all-gather of B*N/P floats per rank puts the matrix together (25.6 MB per rank at
+        B=128, N=50 000, P=8).  Only needed when the caller wants every score; selection never moves them."""
+        per_pair = R.dim() == 4
+        N = R.shape[1] if per_pair else R.shape[0]
+        B = vol_src.shape[0]
+        per = -(-N // self.world)
+        lo, hi = shard_bounds(N, self.rank, self.world)
+        part = torch.zeros(B, per, device=vol_src.device, dtype=torch.float32)     # equal-sized pieces for the all-gather
+        if hi > lo:
+            Rs = (R[:, lo:hi] if per_pair else R[lo:hi]).contiguous()
+            part[:, :hi - lo] = self.verifier.score(vol_src, vol_tgt, Rs, k=1, return_scores=True).scores
+        if self.world == 1:
+            return part[:, :N]
+        pieces = [torch.empty_like(part) for _ in range(self.world)]
+        dist.all_gather(pieces, part, group=self.group)
+        return torch.cat(pieces, dim=1)[:, :N]

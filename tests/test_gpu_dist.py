@@ -83,6 +83,8 @@ def _worker(rank, world, port, k, out_q):
     sR, sv_, sfirst, scand = v.refine(vs, vt, R, k=k, m=16, max_angle_deg=4.0, seed=3)
     out["refine"] = (cpu(rR, rv, fi, cand), cpu(sR, sv_, sfirst.topk_idx, scand))
     steps += 2
+    # (6c) the full score matrix of the sharded set (NCCL all-gather of the per-rank pieces)
+    out["scores"] = (cpu(sv.scores(vs, vt, R[:2999])), cpu(v.score(vs, vt, R[:2999], k=1, return_scores=True).scores))
     # (7) host-buffer entry, sharded: host slices in, whole-set selection out
     sess = ahv.ops.HostSession(dev)
     Rh = g["R"][lo:hi]
@@ -135,7 +137,7 @@ def test_sharded_equals_single_gpu(golden):
             assert np.all(got[1][:, kk:] == -1) and np.all(np.isneginf(got[0][:, kk:]))
         for kg, got in o["graph"]:
             assert _same(got, (sval[:, :kg], sidx[:, :kg], sR[:, :kg]))
-        assert _same(*o["per_pair"]) and _same(*o["bf16"]) and _same(*o["refine"])
+        assert _same(*o["per_pair"]) and _same(*o["bf16"]) and _same(*o["refine"]) and _same(*o["scores"])
         for kh, got in o["host"]:
             assert _same(got, (sval[:, :kh], sidx[:, :kh], sR[:, :kh]))
     assert _same(res[0]["fused_topk"], res[1]["fused_topk"])
