@@ -92,3 +92,20 @@ def test_argument_validation_of_round2_entries_without_gpu(ahv):
                                    0, 1, None, 0, 0, None) == E                      # no session
     assert lib.ahv_host_session_destroy(None) == 0
     assert lib.ahv_version() == 200
+
+
+def _compile_c_example(tmp_path):
+    exe = str(tmp_path / "predict_host")
+    lib_dir = os.path.join(ROOT, "3dahv_b200")
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "predict_host.c"),
+           "-o", exe, "-L" + lib_dir, "-l:lib3dahv_b200.so", "-Wl,-rpath," + lib_dir]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_plain_c_host_compiles_against_the_header(ahv, tmp_path):
+    """include/ahv_b200.h is a C header (no C++, no torch types): a plain-C host builds and links against the library."""
+    exe = _compile_c_example(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr

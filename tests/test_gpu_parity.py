@@ -625,3 +625,33 @@ def test_peer_exchange_protocol_on_one_gpu(ahv, golden):
         torch.cuda.synchronize()
         for p in bufs:
             lib.ahv_peer_free(p)
+
+
+def test_plain_c_host_matches_the_python_binding(ahv, golden, tmp_path):
+    """examples/predict_host.c - a host with no Python and no PyTorch in it - gets the same selection through
+    ahv_predict_host_ex as the ctypes binding does."""
+    import os
+    import subprocess
+
+    from test_abi import _compile_c_example
+
+    exe = _compile_c_example(tmp_path)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    B, N, k = 3, 3000, 4
+    base = ahv.ops.base_coords().numpy()
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        f.write(np.array([B, N, k], dtype=np.int32).tobytes())
+        for a in (g["vol_src"], g["vol_tgt"], g["R"], w["W1"], w["W2"], w["b2"], base):
+            f.write(np.ascontiguousarray(a, dtype=np.float32).tobytes())
+    run = subprocess.run([exe, inp, outp], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stderr
+    raw = open(outp, "rb").read()
+    idx = np.frombuffer(raw, dtype=np.int64, count=B * k).reshape(B, k)
+    val = np.frombuffer(raw, dtype=np.float32, count=B * k, offset=B * k * 8).reshape(B, k)
+    Rb = np.frombuffer(raw, dtype=np.float32, count=B * k * 9, offset=B * k * 12).reshape(B, k, 3, 3)
+    T = torch.from_numpy
+    _, pv, pi, pR = ahv.ops.predict_host(T(g["vol_src"]), T(g["vol_tgt"]), T(g["R"]), T(w["W1"]), T(w["W2"]), T(w["b2"]), k=k,
+                                         device=_dev())
+    assert np.array_equal(idx, pi.numpy()) and np.array_equal(val, pv.numpy()) and np.array_equal(Rb, pR.numpy())
+    assert np.array_equal(Rb, g["R"][idx])
