@@ -18,11 +18,11 @@
 // per-thread accumulators: dW1 (48), dW2 (4), db2 (8), dT (8, flushed per pair), dV (32, flushed per
 // pair); they leave the CTA through global atomics (caller zero-initialises the outputs).
 //
-// The adjoint of the resampling is a GATHER, not a scatter (shared-memory atomics would cost ~130k cycles
-// per hypothesis): every thread owns two input voxels, pulls them back through R^T, walks the 4 x 4 (d, h)
-// columns around that point, intersects on each column the three |i_a - v_a| < 1 intervals in w, and for
-// the few candidates left re-uses the taps the forward gather recorded, so the weights are the forward's
-// bit for bit.  A matrix that is not a rotation falls back to scanning all 512 output voxels.
+// The adjoint of the resampling is a GATHER, not a scatter (floating-point shared-memory atomics would cost
+// ~130k cycles per hypothesis): the 512 output voxels are bucketed by the corner line of their taps (a counting
+// sort with 1 024 integer shared-memory atomics), every thread owns two input voxels and visits the 8 buckets
+// around each - exactly the output voxels that touch it, whatever the matrix R is - re-using the taps the forward
+// gather recorded, so the weights are the forward's bit for bit.
 #include "ahv_head_fp32.cuh"
 
 namespace ahv {
@@ -33,16 +33,6 @@ struct BwdSmem {
   float4 taps[kVox];       // (corner line, fx, fy, fz) of every output voxel of the current hypothesis
 };
 static_assert(sizeof(BwdSmem) <= 232448, "shared memory budget");
-
-// contribution of output voxel `vo` (tap t) to input voxel with halo line `lin`: trilinear weight or 0
-__device__ __forceinline__ float tap_weight(const float4 t, int lin) {
-  const int delta = lin - __float_as_int(t.x);  // = 100 dz + 10 dy + dx with dx,dy,dz in {0,1} iff the voxel is a tap
-  // |dx|,|dy| <= 8 < 10, so the decomposition is unique: test the 8 admissible values
-  const int dz = delta >= 100, r1 = delta - 100 * dz;
-  const int dy = r1 >= 10, dx = r1 - 10 * dy;
-  if ((unsigned)dx > 1u || delta < 0 || delta > 111) return 0.0f;
-  return (dx ? t.y : 1.0f - t.y) * (dy ? t.z : 1.0f - t.z) * (dz ? t.w : 1.0f - t.w);
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tgt_feat,
@@ -255,79 +245,74 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
     }
 
     // ---------------- dV_b += rotate^T(dX): adjoint of utils.py:113-131 as a gather ----------------
+    // Output voxel vo contributes to the 8 input voxels corner(vo) + {0,1}^3.  Turned round: input voxel v receives
+    // from the output voxels whose corner is v - delta, delta in {0,1}^3.  So the 512 output voxels are bucketed by
+    // their corner line (counting sort in shared memory, over the dH2 buffer, which is dead by now), and every
+    // thread visits the 8 buckets around each of its two input voxels - exactly the contributing voxels, no geometry
+    // test, valid for any matrix R - with the weights the forward gather recorded, bit for bit.
     {
-      // is R a rotation?  then the output voxels that can touch an input voxel sit within sqrt(3) of R^T x
-      float dev = 0.0f;
+      int* cnt = reinterpret_cast<int*>(bs.dh2);            // [1000] voxels per corner line, then running fill offset
+      int* start = cnt + kLines;                            // [1000] exclusive prefix sum
+      unsigned short* list = reinterpret_cast<unsigned short*>(start + kLines);  // [512] output voxels sorted by corner line
+      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;
+      __syncthreads();
+      int myline[2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float gij = Rr[i] * Rr[j] + Rr[3 + i] * Rr[3 + j] + Rr[6 + i] * Rr[6 + j];  // (R^T R)_ij
-          dev = fmaxf(dev, fabsf(gij - (i == j ? 1.0f : 0.0f)));
-        }
-      const bool is_rot = dev < 1e-3f;  // NaN compares false -> full scan
-      // per axis a: the w-coefficient of the sample point and its reciprocal (one division per axis and item)
-      float inv_r[3];
-      bool flat[3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        flat[a] = !(fabsf(Rr[3 * a]) > 1e-6f);
-        inv_r[a] = flat[a] ? 0.0f : 1.0f / Rr[3 * a];
+      for (int j = 0; j < 2; ++j) {
+        myline[j] = __float_as_int(bs.taps[t + 256 * j].x);
+        atomicAdd(&cnt[myline[j]], 1);
       }
+      __syncthreads();
+      {  // exclusive scan of 1000 counters: 4 per thread (250 threads), warp scan, then the 8 warp totals
+        const int i0 = 4 * t;
+        int c4[4] = {0, 0, 0, 0};
+        if (i0 < kLines) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c4[e] = cnt[i0 + e];
+        }
+        const int local = c4[0] + c4[1] + c4[2] + c4[3];
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((t & 31) >= o) incl += up;
+        }
+        int* wtot = reinterpret_cast<int*>(sm.red);          // 8 warp totals (sm.red is free outside volume staging)
+        if ((t & 31) == 31) wtot[t >> 5] = incl;
+        __syncthreads();
+        int basep = incl - local;
+        for (int w = 0; w < (t >> 5); ++w) basep += wtot[w];
+        if (i0 < kLines) {
+          start[i0] = basep;
+          start[i0 + 1] = basep + c4[0];
+          start[i0 + 2] = basep + c4[0] + c4[1];
+          start[i0 + 3] = basep + c4[0] + c4[1] + c4[2];
+        }
+      }
+      __syncthreads();
+      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;   // re-used as the fill cursor
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) list[start[myline[j]] + atomicAdd(&cnt[myline[j]], 1)] = (unsigned short)(t + 256 * j);
+      __syncthreads();
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int vi = t + 256 * j;
         const int z = vi >> 6, y = (vi >> 3) & 7, x = vi & 7;
         const int lin = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
-        auto visit = [&](int vo) {
-          const float w = tap_weight(bs.taps[vo], lin);
-          if (w != 0.0f) {
+#pragma unroll 1
+        for (int dlt = 0; dlt < 8; ++dlt) {
+          const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
+          const int cell = lin - (dz * kHalo * kHalo + dy * kHalo + dx);   // corner line of the voxels that tap v at (dx,dy,dz)
+          const int n = cnt[cell], s0 = start[cell];                      // cell >= 0: lin >= 111
+          for (int e = 0; e < n; ++e) {
+            const int vo = list[s0 + e];
+            const float4 tp = bs.taps[vo];
+            const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
             const float* src = sm.rotA + (vo >> 6) * kRotD + (vo & 63);
 #pragma unroll
             for (int c = 0; c < kC; ++c) aV[j][c] = fmaf(w, src[c * kRotC], aV[j][c]);
           }
-        };
-        if (is_rot) {
-          // input voxel centre in normalised coordinates, pulled back: out = R^T in (grid = R out, utils.py:126)
-          const float gx = (2 * x + 1) * 0.125f - 1.0f, gy = (2 * y + 1) * 0.125f - 1.0f, gz = (2 * z + 1) * 0.125f - 1.0f;
-          const float ox = unnorm(Rr[0] * gx + Rr[3] * gy + Rr[6] * gz);
-          const float oy = unnorm(Rr[1] * gx + Rr[4] * gy + Rr[7] * gz);
-          const float oz = unnorm(Rr[2] * gx + Rr[5] * gy + Rr[8] * gz);
-          (void)ox;
-          const int h0 = (int)floorf(oy) - 1, d0 = (int)floorf(oz) - 1;
-          // In index space the sample point of output voxel o' is i = R (o' - 3.5) + 3.5, and o' touches this
-          // voxel iff |i_a - v_a| < 1 on all three axes.  Along a (d, h) column that is three intervals in w:
-          // intersect them (with a margin; tap_weight() makes the exact decision) instead of testing 4 values.
-          const float vx = (float)x, vy = (float)y, vz = (float)z;
-#pragma unroll 1
-          for (int dd = 0; dd < 4; ++dd) {
-            const int d = d0 + dd;
-            if ((unsigned)d > 7u) continue;
-#pragma unroll 1
-            for (int hh = 0; hh < 4; ++hh) {
-              const int h = h0 + hh;
-              if ((unsigned)h > 7u) continue;
-              const float uh = (float)h - 3.5f, ud = (float)d - 3.5f;
-              float ulo = -3.5f, uhi = 3.5f;  // u = w - 3.5
-#pragma unroll
-              for (int a = 0; a < 3; ++a) {
-                const float ca = fmaf(Rr[3 * a + 1], uh, fmaf(Rr[3 * a + 2], ud, 3.5f - (a == 0 ? vx : (a == 1 ? vy : vz))));
-                if (!flat[a]) {
-                  const float ir = inv_r[a];
-                  const float e0 = (-1.0f - ca) * ir, e1 = (1.0f - ca) * ir;
-                  ulo = fmaxf(ulo, fminf(e0, e1));
-                  uhi = fminf(uhi, fmaxf(e0, e1));
-                } else if (fabsf(ca) >= 1.001f) {
-                  uhi = -10.0f;  // the whole column misses on this axis
-                }
-              }
-              const int wlo = max(0, (int)ceilf(ulo + 3.5f - 1e-3f)), whi = min(7, (int)floorf(uhi + 3.5f + 1e-3f));
-              for (int w = wlo; w <= whi; ++w) visit(d * 64 + h * 8 + w);
-            }
-          }
-        } else {
-#pragma unroll 1
-          for (int vo = 0; vo < kVox; ++vo) visit(vo);
         }
       }
     }
