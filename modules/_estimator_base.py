@@ -47,23 +47,26 @@ class EstimatorBase(_Base):
         def log(self, *args, **kwargs):  # Lightning's logger hook; a no-op without Lightning
             return None
 
-        @classmethod
-        def load_from_checkpoint(cls, checkpoint_path, cfg=None, map_location="cpu", **kwargs):
-            """Lightning's loader as the reference's scripts call it (`Estimator.load_from_checkpoint(path, cfg=cfg)`,
-            test_co3d.py:218, test_objaverse.py:22), for installations without Lightning: reads the checkpoint's
-            `state_dict` (and `hyper_parameters["cfg"]` when `cfg` is not given) and loads it through
-            `modules._backbone.load_reference_state_dict` - `feature_aligner.*` strictly by name, the MiDaS/timm
-            backbone keys mapped onto the SwinV2-T stand-in.  The load report is kept in `model.load_report`."""
-            from modules._backbone import load_reference_state_dict
+    @classmethod
+    def load_reference_checkpoint(cls, checkpoint_path, cfg=None, map_location="cpu", **kwargs):
+        """What the reference's scripts do with `Estimator.load_from_checkpoint(path, cfg=cfg)` (test_co3d.py:218,
+        test_objaverse.py:22) for a REFERENCE checkpoint, with or without Lightning installed: reads the checkpoint's
+        `state_dict` (and `hyper_parameters["cfg"]` when `cfg` is not given) and loads it through
+        `modules._backbone.load_reference_state_dict` - `feature_aligner.*` strictly by name, the MiDaS/timm
+        backbone keys mapped onto the SwinV2-T stand-in.  The load report is kept in `model.load_report`."""
+        from modules._backbone import load_reference_state_dict
 
-            ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
-            if cfg is None:
-                cfg = ckpt.get("hyper_parameters", {}).get("cfg")
-            if cfg is None:
-                raise ValueError("pass cfg= (the checkpoint holds no hyper_parameters['cfg'])")
-            model = cls(cfg, **kwargs)
-            model.load_report = load_reference_state_dict(model, ckpt)
-            return model
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        if cfg is None:
+            cfg = ckpt.get("hyper_parameters", {}).get("cfg")
+        if cfg is None:
+            raise ValueError("pass cfg= (the checkpoint holds no hyper_parameters['cfg'])")
+        model = cls(cfg, **kwargs)
+        model.load_report = load_reference_state_dict(model, ckpt)
+        return model
+
+    if pl is None:   # without Lightning the reference's spelling is this loader
+        load_from_checkpoint = load_reference_checkpoint
 
     def feature_extraction(self, img):
         return self.feature_extractor(img)
