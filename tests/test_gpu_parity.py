@@ -655,3 +655,23 @@ def test_plain_c_host_matches_the_python_binding(ahv, golden, tmp_path):
                                          device=_dev())
     assert np.array_equal(idx, pi.numpy()) and np.array_equal(val, pv.numpy()) and np.array_equal(Rb, pR.numpy())
     assert np.array_equal(Rb, g["R"][idx])
+
+
+def test_topk_merge_keeps_64_bit_indices(ahv):
+    """Shard lists whose global indices exceed 2^32 (a set sharded with large idx_offsets): the merge orders by
+    (score, low 32 index bits) and reports the full 64-bit index of the winning entries."""
+    dev = _dev()
+    parts, B, k = 4, 3, 5
+    gen = torch.Generator().manual_seed(0)
+    vals = torch.rand(parts, B, k, generator=gen).sort(dim=-1, descending=True).values
+    base = (1 << 33) + 12345
+    idx = base + torch.arange(parts * B * k, dtype=torch.int64).reshape(parts, B, k) * 7
+    idx[1, 0, 3:] = -1                                                    # empty slots are ignored
+    vals[1, 0, 3:] = float("-inf")
+    out_v, out_i = ahv.ops.topk_merge(vals.to(dev), idx.to(dev))
+    flat_v = vals.permute(1, 0, 2).reshape(B, -1)
+    flat_i = idx.permute(1, 0, 2).reshape(B, -1)
+    order = torch.argsort(flat_v, dim=1, descending=True, stable=True)[:, :k]
+    assert torch.equal(out_v.cpu(), torch.gather(flat_v, 1, order))
+    assert torch.equal(out_i.cpu(), torch.gather(flat_i, 1, order))
+    assert int(out_i.min()) > (1 << 32)
