@@ -117,6 +117,39 @@ AHV_API int ahv_resblock3d(const float* x, const float* conv1_w, const float* co
   return launch_resblock3d(x, conv1_w, conv2_w, down_w, out, m, (cudaStream_t)stream);
 }
 
+AHV_API int ahv_score_train(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair, const float* W1,
+                            const float* W2, const float* b2, const float* base, float* scores, void* h1_saved,
+                            float* pair_inv_scale, int B, int64_t N, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (B < 0 || N < 0 || N > 0x7fffffffLL) return AHV_EINVAL;
+  if ((int64_t)B * N > 0 && (!vol_src || !tgt_feat || !R || !W1 || !W2 || !b2 || !base || !scores || !h1_saved ||
+                             !pair_inv_scale || !workspace))
+    return AHV_EINVAL;
+  if (!aligned16(vol_src) || !aligned16(tgt_feat) || !aligned16(R) || !aligned16(W1) || !aligned16(W2) ||
+      !aligned16(h1_saved) || !aligned16(workspace))
+    return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_score_tc_train(vol_src, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, scores, h1_saved, pair_inv_scale, B, N,
+                               workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+AHV_API int ahv_score_backward_saved(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair,
+                                     const float* W1, const float* W2, const float* b2, const float* base,
+                                     const float* grad_scores, const void* h1_saved, const float* pair_inv_scale,
+                                     float* grad_vol, float* grad_tgt, float* grad_W1, float* grad_W2, float* grad_b2,
+                                     int B, int64_t N, void* stream) {
+  if (B < 0 || N < 0 || N > 0x7fffffffLL) return AHV_EINVAL;
+  if ((int64_t)B * N > 0 && (!vol_src || !tgt_feat || !R || !W1 || !W2 || !b2 || !base || !grad_scores || !h1_saved ||
+                             !pair_inv_scale || !grad_vol || !grad_tgt || !grad_W1 || !grad_W2 || !grad_b2))
+    return AHV_EINVAL;
+  if (!aligned16(h1_saved)) return AHV_EINVAL;
+  int st = check_device();
+  if (st != AHV_OK) return st;
+  return launch_score_bwd(vol_src, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, grad_scores, grad_vol, grad_tgt,
+                          grad_W1, grad_W2, grad_b2, B, N, (cudaStream_t)stream, h1_saved, pair_inv_scale);
+}
+
 AHV_API int ahv_forward_3d2d(const float* vol, const float* W1, const float* W2, const float* b2,
                      float* feat, int64_t m, void* stream) {
   if (m < 0 || (m > 0 && (!vol || !W1 || !W2 || !b2 || !feat))) return AHV_EINVAL;

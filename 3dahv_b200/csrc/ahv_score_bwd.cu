@@ -39,7 +39,8 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
                  const float* __restrict__ R, int r_per_pair, const float* __restrict__ W1,
                  const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ base,
                  const float* __restrict__ grad_scores, float* __restrict__ g_vol, float* __restrict__ g_tgt,
-                 float* __restrict__ g_W1, float* __restrict__ g_W2, float* __restrict__ g_b2, int B, int64_t N) {
+                 float* __restrict__ g_W1, float* __restrict__ g_W2, float* __restrict__ g_b2, int B, int64_t N,
+                 const __half* __restrict__ h1_saved, const float* __restrict__ pair_inv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdSmem& bs = *reinterpret_cast<BwdSmem*>(smem_raw);
   Fp32Smem& sm = bs.f;
@@ -108,9 +109,25 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
 
     // ---------------- forward recompute ----------------
     gather_hypothesis<true>(sm, Rr, bs.taps);
-    __syncthreads();
-    conv1_relu(sm);
-    __syncthreads();
+    if (h1_saved) {
+      // saved-activation form: H1 = relu(conv1(A)) of this item was kept by the training forward (fp16, in the pair's
+      // scaled units) - 4 KB read instead of 786 k FMA recomputed; A itself is still needed (dW1) and was just gathered
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(h1_saved + ((size_t)it * kP + pos) * kO + cg2 * 8));
+      const float inv = __ldg(pair_inv + b);
+      const __half2* hp = reinterpret_cast<const __half2*>(&q);
+      float* dst = sm.h1s + pos * kH1Row + cg2 * 8;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f2 = __half22float2(hp[e]);
+        dst[2 * e] = f2.x * inv;
+        dst[2 * e + 1] = f2.y * inv;
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      conv1_relu(sm);
+      __syncthreads();
+    }
     float v[8];
     conv2_bias(sm, b2r, v);
     float ss = 0.0f, ft = 0.0f;
@@ -350,7 +367,7 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
 int launch_score_bwd(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair,
                      const float* W1, const float* W2, const float* b2, const float* base,
                      const float* grad_scores, float* g_vol, float* g_tgt, float* g_W1, float* g_W2,
-                     float* g_b2, int B, int64_t N, cudaStream_t s) {
+                     float* g_b2, int B, int64_t N, cudaStream_t s, const void* h1_saved, const float* pair_inv) {
   const int64_t total = (int64_t)B * N;
   if (total == 0) return AHV_OK;
   int dev = 0, sms = 0;
@@ -360,7 +377,8 @@ int launch_score_bwd(const float* vol_src, const float* tgt_feat, const float* R
   const size_t smem = sizeof(BwdSmem);
   AHV_CUDA_OK(cudaFuncSetAttribute(score_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   score_bwd_kernel<<<grid, kThreads, smem, s>>>(vol_src, tgt_feat, R, r_per_pair, W1, W2, b2, base, grad_scores,
-                                                g_vol, g_tgt, g_W1, g_W2, g_b2, B, N);
+                                                g_vol, g_tgt, g_W1, g_W2, g_b2, B, N,
+                                                static_cast<const __half*>(h1_saved), pair_inv);
   AHV_CUDA_OK(cudaGetLastError());
   return AHV_OK;
 }

@@ -195,7 +195,7 @@ static int launch_pdl(KernelT kernel, unsigned grid, size_t smem, cudaStream_t s
 // the per-pair scales itself; when the prologue runs, the scoring kernel is launched programmatically
 // dependent on it (its setup, weight packing, volume staging and first gathers overlap the prologue; only
 // the epilogue warps wait for the target features).
-template <typename T, bool K16>
+template <typename T, bool K16, bool kSave = false>
 int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_in, const float* R,
                  int r_per_pair, const float* W1, const float* W2, const float* b2, const float* base,
                  float* scores, bool want_argmax, int B, int64_t N, const Scratch& sc, Finalize fin, cudaStream_t s) {
@@ -219,12 +219,12 @@ int launch_typed(const T* vol_src, const float* vol_tgt, const float* tgt_feat_i
   CUtensorMap vol_map;
   const int mst = make_volume_map(vol_src, B, sizeof(T) == 2, &vol_map);
   if (mst != AHV_OK) return mst;
-  AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
+  AHV_CUDA_OK(cudaFuncSetAttribute(score_tc_ts_kernel<T, K16, kSave>, cudaFuncAttributeMaxDynamicSharedMemorySize, MapTS::smem_bytes));
   // CTAs that inherit the prologue's SMs start late; only worth compensating when the prologue is smaller than this
   // grid and every CTA has tiles to spare (see the work split in the kernel)
   int late = 0;
   if (prologue && kTgtCtasPerPair * (int64_t)B <= grid / 2 && (int64_t)B * N / grid >= 8) late = kTgtCtasPerPair * B;
-  return launch_pdl(score_tc_ts_kernel<T, K16>, grid, MapTS::smem_bytes, s, prologue, vol_map, tgt, R, r_per_pair, b2, base, W1,
+  return launch_pdl(score_tc_ts_kernel<T, K16, kSave>, grid, MapTS::smem_bytes, s, prologue, vol_map, tgt, R, r_per_pair, b2, base, W1,
                     W2, scores, keys, B, N, fin, late);
 }
 
@@ -281,6 +281,20 @@ int launch_score_tc(const void* vol_src, int vol_dtype, const float* tgt_feat, c
   if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
   return dispatch(vol_src, vol_dtype, f16_gather, nullptr, tgt_feat, R, r_per_pair, W1, W2, b2, base, scores, false,
                   B, N, tc::carve(ws, B), tc::Finalize{}, s);
+}
+
+// training forward (modules/model.py:53-56 before autograd): scores + the ReLU'd conv1 output of every item and the
+// pair scales, which ahv_score_backward's saved-activation form reads instead of recomputing conv1
+int launch_score_tc_train(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair, const float* W1,
+                          const float* W2, const float* b2, const float* base, float* scores, void* h1_out,
+                          float* pair_inv_out, int B, int64_t N, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if ((int64_t)B * N == 0) return AHV_OK;
+  if (ws_bytes < tc::scratch_bytes(B)) return AHV_EWORKSPACE;
+  tc::Finalize fin;
+  fin.h1_out = static_cast<__half*>(h1_out);
+  fin.pair_inv_out = pair_inv_out;
+  return tc::launch_typed<float, false, true>(vol_src, nullptr, tgt_feat, R, r_per_pair, W1, W2, b2, base, scores, false, B, N,
+                                              tc::carve(ws, B), fin, s);
 }
 
 // the whole verification step with arg-max selection in two launches: prologue (target features, key

@@ -39,7 +39,7 @@ struct MapTS {
   static_assert(smem_bytes <= 232448, "shared memory budget");
 };
 
-template <typename T, bool K16>
+template <typename T, bool K16, bool kSave = false>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __restrict__ tgt_feat,
                    const float* __restrict__ R, int r_per_pair, const float* __restrict__ b2,
@@ -194,7 +194,10 @@ score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __r
       const float inv = stage_pair_volume<T, K16>(smem + M::off_vol, reinterpret_cast<const T*>(smem + M::off_a),
                                                   bar0 + kVolFull * 8, 0, l1max_bits, W1, true, red, gtid);
       ++vol_uses;
-      if (gtid == 0) inv_ring[fb & 7] = inv;
+      if (gtid == 0) {
+        inv_ring[fb & 7] = inv;
+        if constexpr (kSave) fin.pair_inv_out[fb] = inv;   // the same value from every CTA that stages this pair
+      }
       named_bar_sync(1, kGatherWarps * 32);
       if (threadIdx.x == 0) AHV_TL(3);
 #pragma unroll
@@ -297,7 +300,10 @@ score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __r
                                                     bar0 + (kVolFull + (vol_uses & 1)) * 8, (vol_uses >> 1) & 1, l1max_bits, W1, false,
                                                     red, gtid);
         ++vol_uses;
-        if (gtid == 0) inv_ring[it.b & 7] = inv;
+        if (gtid == 0) {
+          inv_ring[it.b & 7] = inv;
+          if constexpr (kSave) fin.pair_inv_out[it.b] = inv;
+        }
         named_bar_sync(1, kGatherWarps * 32);
         cur_b = it.b;
       }
@@ -461,7 +467,7 @@ score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __r
     __syncwarp();
   } else {
     // =========================== EPILOGUE ===========================
-    epilogue_role(work, warp - kEpiWarp0, lane, tmem, bar0, M::tmem_a2, partial, tgt_feat, b2, inv_ring,
+    epilogue_role<kSave>(work, warp - kEpiWarp0, lane, tmem, bar0, M::tmem_a2, partial, tgt_feat, b2, inv_ring,
                         scores, best_keys, N, B, R, r_per_pair, fin);
   }
 

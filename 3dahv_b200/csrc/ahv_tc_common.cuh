@@ -52,6 +52,11 @@ struct Finalize {
   float* R_best = nullptr;
   int64_t idx_offset = 0;
   unsigned* counter = nullptr;  // zero at kernel start (cleared with the keys), reset by the last CTA
+  // training forward (kSave instantiation only): conv1's ReLU'd output of every item, fp16 in the pair's scaled units
+  // [B*N][64 positions][32 channels], and 1/scale per pair - the fused backward reads them instead of recomputing
+  // conv1 (4 KB per item; the reference's autograd saves ~420 KB per hypothesis)
+  __half* h1_out = nullptr;
+  float* pair_inv_out = nullptr;
   // hypothesis set sharded over `peers.world` GPUs: the winners are exchanged through peer
   // memory by this kernel itself (no NCCL call, no merge kernel); see ahv_peer.cuh for the buffer
   peer::Args peers;
@@ -310,6 +315,7 @@ __device__ AHV_STAGE_INLINE float stage_pair_volume(unsigned char* vsm, const T*
 //   phase B (one tile later, after conv2): tcgen05.ld D2 -> undo the pair scale, + bias -> L2 norm with
 //            F.normalize's eps (:122) -> dot with the target features (registers) -> mean over the 64
 //            positions (modules/model.py:193) -> score, and the running arg-max key (:195).
+template <bool kSave = false>
 __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane, uint32_t tmem, uint32_t bar0,
                                               uint32_t tmem_a2, float* partial,
                                               const float* __restrict__ tgt_feat, const float* __restrict__ b2,
@@ -389,6 +395,13 @@ __device__ __forceinline__ void epilogue_role(const Work& work, int s, int lane,
       wq[e] = *reinterpret_cast<const uint32_t*>(&hh);
     }
     tmem_st16(tmem + ((uint32_t)(32 * s) << 16) + tmem_a2 + gb * 16, wq);  // 16 TMEM columns of conv2's A operand
+    if constexpr (kSave) {  // training forward: keep this row of H1 (64 B) for the backward pass
+      if (slot < it.cnt) {
+        uint4* dst = reinterpret_cast<uint4*>(fin.h1_out + (((size_t)it.b * N + it.n0 + slot) * kP + pos) * kO);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = make_uint4(wq[4 * e], wq[4 * e + 1], wq[4 * e + 2], wq[4 * e + 3]);
+      }
+    }
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();

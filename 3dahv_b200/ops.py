@@ -125,10 +125,39 @@ def rotate_volume_backward(grad_out: torch.Tensor, R: torch.Tensor, per_rotation
     return out
 
 
+def score_train(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor,
+                b2: torch.Tensor, workspace: torch.Tensor | None = None):
+    """ahv_score_train: the training forward - scores [B,N] from the tensor-core kernel, plus what the backward pass
+    wants back: conv1's ReLU'd output of every item (fp16 [B*N,64,32], 4 KB per item) and 1/scale per pair [B]."""
+    vs, tf, R = _dev(vol_src, "vol_src"), _dev(tgt_feat, "tgt_feat"), _dev(R, "R")
+    W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
+    B = vs.shape[0]
+    per_pair = R.dim() == 4
+    N = R.shape[1] if per_pair else R.shape[0]
+    if tuple(vs.shape) != (B, 16, 8, 8, 8) or tuple(tf.shape) != (B, 32, 64) or (per_pair and R.shape[0] != B):
+        raise ValueError("vol_src [B,16,8,8,8], tgt_feat [B,32,64], R [N,3,3] or [B,N,3,3] expected")
+    dev = vs.device
+    scores = torch.empty(B, N, device=dev, dtype=torch.float32)
+    h1 = torch.empty(B * N, 64, 32, device=dev, dtype=torch.float16)
+    pair_inv = torch.empty(B, device=dev, dtype=torch.float32)
+    need = workspace_bytes(B, N, 1)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    base = base_coords(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ahv_score_train(vs.data_ptr(), tf.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(), W2.data_ptr(),
+                                              b2.data_ptr(), base.data_ptr(), scores.data_ptr(), h1.data_ptr(), pair_inv.data_ptr(),
+                                              B, N, workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                              _stream(vs)), "ahv_score_train")
+    return scores, h1, pair_inv
+
+
 def score_backward(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor,
-                   b2: torch.Tensor, grad_scores: torch.Tensor):
+                   b2: torch.Tensor, grad_scores: torch.Tensor, h1_saved: torch.Tensor | None = None,
+                   pair_inv: torch.Tensor | None = None):
     """Fused gradient of the verification scores (modules/model.py:53-56 under autograd): returns
-    (grad_vol_src [B,16,8,8,8], grad_tgt_feat [B,32,64], grad_W1 [32,384], grad_W2 [32,32], grad_b2 [32])."""
+    (grad_vol_src [B,16,8,8,8], grad_tgt_feat [B,32,64], grad_W1 [32,384], grad_W2 [32,32], grad_b2 [32]).
+    With `h1_saved` / `pair_inv` from `score_train` the kernel reads conv1's output instead of recomputing it."""
     vs, tg, R, gs = _dev(vol_src, "vol_src"), _dev(tgt_feat, "tgt_feat"), _dev(R, "R"), _dev(grad_scores, "grad_scores")
     W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
     B = vs.shape[0]
@@ -143,10 +172,21 @@ def score_backward(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tenso
     g_vol, g_tgt, g_w1, g_w2, g_b2 = z(B, 16, 8, 8, 8), z(B, 32, 64), z(32, 384), z(32, 32), z(32)
     base = base_coords(dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().ahv_score_backward(vs.data_ptr(), tg.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(),
-                                                 W2.data_ptr(), b2.data_ptr(), base.data_ptr(), gs.data_ptr(),
-                                                 g_vol.data_ptr(), g_tgt.data_ptr(), g_w1.data_ptr(), g_w2.data_ptr(),
-                                                 g_b2.data_ptr(), B, N, _stream(vs)), "ahv_score_backward")
+        if h1_saved is not None:
+            h1 = _dev(h1_saved, "h1_saved", torch.float16)
+            pi = _dev(pair_inv, "pair_inv")
+            if h1.numel() != B * N * 64 * 32 or pi.numel() != B:
+                raise ValueError("h1_saved [B*N,64,32] fp16 and pair_inv [B] expected")
+            _lib.check(_lib.lib().ahv_score_backward_saved(vs.data_ptr(), tg.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(),
+                                                           W2.data_ptr(), b2.data_ptr(), base.data_ptr(), gs.data_ptr(),
+                                                           h1.data_ptr(), pi.data_ptr(), g_vol.data_ptr(), g_tgt.data_ptr(),
+                                                           g_w1.data_ptr(), g_w2.data_ptr(), g_b2.data_ptr(), B, N, _stream(vs)),
+                       "ahv_score_backward_saved")
+        else:
+            _lib.check(_lib.lib().ahv_score_backward(vs.data_ptr(), tg.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(),
+                                                     W2.data_ptr(), b2.data_ptr(), base.data_ptr(), gs.data_ptr(),
+                                                     g_vol.data_ptr(), g_tgt.data_ptr(), g_w1.data_ptr(), g_w2.data_ptr(),
+                                                     g_b2.data_ptr(), B, N, _stream(vs)), "ahv_score_backward")
     return g_vol, g_tgt, g_w1, g_w2, g_b2
 
 

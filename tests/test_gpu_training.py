@@ -230,3 +230,35 @@ def test_fused_infonce_kernel_vs_eager_formulation(ahv):
     # inference-style call: no gradient buffer is produced
     loss, grad = ahv.ops.infonce(s0, Rsh, gt, 15.0, want_grad=False)
     assert grad is None and torch.allclose(loss, lb.detach(), rtol=2e-5, atol=1e-6)
+
+
+def test_saved_activation_backward_matches_recomputation(ahv, golden):
+    """The training forward can keep conv1's ReLU'd output (fp16, 4 KB per item) so that the backward kernel reads it
+    instead of recomputing conv1 (opt-in).  Per-pair and shared rotation sets, ranges that cross pair boundaries, an
+    outlier volume (pair scale != 1).  Gradients that do not pass through the ReLU mask agree to fp16-operand accuracy
+    (2e-3 of the maximum).  vol_src and W1 do pass through it, and the ~0.05 % of pre-activations within fp16-operand
+    error of zero take the mask of the forward that was actually run: a flipped element moves the gradient of the
+    voxels it feeds by a few per cent of the maximum (measured 2.6 %), so those two are gated at 8 % worst element and
+    5 % in the L2 norm."""
+    dev = torch.device("cuda", 0)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    T = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    gen = torch.Generator().manual_seed(4)
+    for B, N, per_pair, scale in ((3, 700, False, 1.0), (2, 333, True, 1.0), (3, 64, False, 300.0)):
+        vs0, vt0 = T(g["vol_src"][:B]) * scale, T(g["vol_tgt"][:B])
+        R = T(g["R"][: B * N]).reshape(B, N, 3, 3).contiguous() if per_pair else T(g["R"][:N])
+        gs = torch.randn(B, N, generator=gen).to(dev)
+        grads = []
+        for save in (True, False):
+            leaves = [t.clone().requires_grad_(True) for t in (vs0, vt0, T(w["W1"]), T(w["W2"]), T(w["b2"]))]
+            s = ahv.training.verification_scores(*leaves[:2], R, *leaves[2:], math=ahv.MATH_TC, save_activations=save)
+            (s * gs).sum().backward()
+            grads.append((s.detach(), [l.grad.clone() for l in leaves]))
+        assert torch.equal(grads[0][0], grads[1][0])                       # same forward kernel arithmetic
+        for name, a, b in zip(("vol_src", "vol_tgt", "W1", "W2", "b2"), grads[0][1], grads[1][1]):
+            scale_g = float(b.abs().max())
+            worst, l2 = float((a - b).abs().max()) / scale_g, float((a - b).norm() / b.norm())
+            if name in ("vol_src", "W1"):
+                assert worst <= 8e-2 and l2 <= 5e-2, (B, N, per_pair, name, worst, l2)
+            else:
+                assert worst <= 2e-3, (B, N, per_pair, name, worst)
