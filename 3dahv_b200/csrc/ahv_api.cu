@@ -138,14 +138,18 @@ AHV_API int ahv_score_backward_saved(const float* vol_src, const float* tgt_feat
                                      const float* W1, const float* W2, const float* b2, const float* base,
                                      const float* grad_scores, const void* h1_saved, const float* pair_inv_scale,
                                      float* grad_vol, float* grad_tgt, float* grad_W1, float* grad_W2, float* grad_b2,
-                                     int B, int64_t N, void* stream) {
+                                     int B, int64_t N, int math_mode, void* stream) {
   if (B < 0 || N < 0 || N > 0x7fffffffLL) return AHV_EINVAL;
+  if (math_mode != AHV_MATH_TC && math_mode != AHV_MATH_FP32) return AHV_EINVAL;
   if ((int64_t)B * N > 0 && (!vol_src || !tgt_feat || !R || !W1 || !W2 || !b2 || !base || !grad_scores || !h1_saved ||
                              !pair_inv_scale || !grad_vol || !grad_tgt || !grad_W1 || !grad_W2 || !grad_b2))
     return AHV_EINVAL;
   if (!aligned16(h1_saved)) return AHV_EINVAL;
   int st = check_device();
   if (st != AHV_OK) return st;
+  if (math_mode == AHV_MATH_TC)
+    return launch_score_bwd_tc(vol_src, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, grad_scores, h1_saved,
+                               pair_inv_scale, grad_vol, grad_tgt, grad_W1, grad_W2, grad_b2, B, N, (cudaStream_t)stream);
   return launch_score_bwd(vol_src, tgt_feat, R, r_per_pair != 0, W1, W2, b2, base, grad_scores, grad_vol, grad_tgt,
                           grad_W1, grad_W2, grad_b2, B, N, (cudaStream_t)stream, h1_saved, pair_inv_scale);
 }

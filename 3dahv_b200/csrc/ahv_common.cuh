@@ -99,6 +99,10 @@ int launch_score_bwd(const float* vol_src, const float* tgt_feat, const float* R
                      const float* grad_scores, float* g_vol, float* g_tgt, float* g_W1, float* g_W2,
                      float* g_b2, int B, int64_t N, cudaStream_t s, const void* h1_saved = nullptr,
                      const float* pair_inv = nullptr);
+int launch_score_bwd_tc(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair,
+                        const float* W1, const float* W2, const float* b2, const float* base,
+                        const float* grad_scores, const void* h1_saved, const float* pair_inv, float* g_vol,
+                        float* g_tgt, float* g_W1, float* g_W2, float* g_b2, int B, int64_t N, cudaStream_t s);
 int launch_score_tc_train(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair, const float* W1,
                           const float* W2, const float* b2, const float* base, float* scores, void* h1_out,
                           float* pair_inv_out, int B, int64_t N, void* ws, size_t ws_bytes, cudaStream_t s);

@@ -1,0 +1,557 @@
+// Fused backward of the verification scores with the two large contractions on tcgen05 (training variant,
+// SURVEY.md §8a-8 / §8f-3; the reference: autograd through modules/model.py:43-63).
+//
+// Same chain as ahv_score_bwd.cu (which stays the exact fp32 form) for a training step that kept conv1's ReLU'd
+// output H1 in the forward (ahv_score_train).  Per (pair, hypothesis) item:
+//
+//   X = rotate(V_b, R_n)                       fp32 gather in shared memory (taps recorded for the adjoint)
+//   H1 <- saved (fp16, pair-scaled) ; H2 = H1 W2^T + b2 ; F = H2/|H2| ; dH2, dT, db2, dW2, dH1   fp32 CUDA cores
+//   dA   [64 pos x 384]   = dH1 [64 x 32] . W1 [32 x 384]        tcgen05.mma  M=64 N=192 (x2)  K=32
+//   dW1^T[384    x 32 ]   = A^T [384 x 64] . dH1 [64 x 32]       tcgen05.mma  M=128 (x3 views) N=32 K=64
+//   dX = fold(dA) (three tri-plane views onto the rotated volume) ; dV_b += rotate^T(dX)   (bucketed gather)
+//
+// These two contractions are 1.57 MFLOP of the ~1.8 MFLOP per item and were 36 % of the fp32 kernel's time.
+//
+// Operands (fp16, fp32 accumulation in TMEM), all K-major SWIZZLE_NONE core-matrix layouts
+// (element (row r, k) at (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2):
+//   dH1  as A of dA   [pos][o]   : SBO 512, LBO 128     written by the thread that owns (pos, 8 channels): one 16 B store
+//   W1^T as B of dA   [n'][o]    : SBO 512, LBO 128     packed once per CTA; rows PERMUTED n' = g*96 + view*32 + cc*8 + kk
+//                                                       (channel c = 4g + cc) so that every fold thread owns 32 columns
+//                                                       of every view
+//   A^T  as A of dW1  [m][pos]   : SBO 1024, LBO 128    m = view*128 + c*8 + kk; view y is the rotated volume as it lies
+//                                                       ([c][d][h][w]), view x its (h,w) transpose, view z its (d,h) one
+//   dH1  as B of dW1  [o][pos]   : SBO 1040, LBO 128    (pitch 1040: the eight 2-byte stores of a warp hit distinct banks)
+// Scales: A^T carries the pair's power-of-two scale of the forward (pair_inv_scale); dH1 a per-item power of two
+// chosen from max |dH1| (2^13 <= max < 2^14), both undone in fp32 when the accumulators are read.
+// dA lands in TMEM as two M=64 accumulators side by side in the lanes (lanes 0-15 / 16-31 of every 32-lane quadrant),
+// so all 32 lanes of a warp fold; dW1^T is read every item into per-thread fp32 accumulators (48 per thread),
+// which keeps the accumulation across items in fp32 and lets the scale differ per item.
+//
+// Gradients are those of the function the tensor-core forward evaluated (its ReLU mask), with fp16 operand rounding:
+// 4e-4 of the maximum for gradients that do not pass the mask, a few per cent at the voxels a flipped mask element
+// feeds (see training.verification_scores).
+#include "ahv_head_fp32.cuh"
+#include "ahv_tc_ptx.cuh"
+
+namespace ahv {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kAtView = 16384;     // bytes of one view of A^T: 128 rows x 64 positions fp16
+constexpr int kDh1bPitch = 1040;   // SBO of the dW1 B operand
+constexpr int kTmemCols = 512;     // dA: columns 0..191 (both lane halves); dW1^T: columns 192..287
+constexpr int kColW = 192;
+
+struct __align__(128) BwdTcSmem {
+  float vol[kLines * kC];          // halo'd source volume, channel innermost (as the fp32 scorer)
+  float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded), later dX
+  float h1s[kP * kH1Row];          // H1 [pos][32] fp32
+  float w2s[kO * kH1Row];
+  float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> counting-sort arrays of the adjoint gather
+  float4 taps[kVox];
+  unsigned char at[3 * kAtView];   // A^T operand
+  unsigned char w1t[kK * kO * 2];  // W1^T operand (permuted rows)
+  unsigned char dh1a[kP * kO * 2];
+  unsigned char dh1b[4 * kDh1bPitch];
+  float base[8];
+  float red[8];
+  float Rcur[12];
+  unsigned long long bar;
+  uint32_t tmem_slot;
+};
+static_assert(sizeof(BwdTcSmem) <= 232448, "shared memory budget");
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// trilinear gather of one hypothesis into rotA, 4 lanes per output voxel (as gather_hypothesis of the fp32 scorer,
+// without the transposed copy); lane j==0 of every voxel records the tap for the adjoint
+__device__ __forceinline__ void gather_rotated(BwdTcSmem& sm, const float* R) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 3, q = lane >> 2;
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int s = it * 8 + warp;
+    const int d = s >> 3, h = s & 7, w = q;
+    const Tap t = make_tap(R, sm.base[w], sm.base[h], sm.base[d]);
+    if (j == 0) sm.taps[d * 64 + h * 8 + w] = make_float4(__int_as_float(t.line), t.fx, t.fy, t.fz);
+    const int swap = (t.line ^ q) & 1;  // parity order: the two x-taps of a lane pair never share a bank half
+    const float wx_first = swap ? t.fx : 1.0f - t.fx;
+    const float wx_second = swap ? 1.0f - t.fx : t.fx;
+    const float* p0 = sm.vol + (t.line + swap) * kC + j * 4;
+    const float* p1 = sm.vol + (t.line + 1 - swap) * kC + j * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float wyz = (dy ? t.fy : 1.0f - t.fy) * (dz ? t.fz : 1.0f - t.fz);
+        const int off = (dz * kHalo * kHalo + dy * kHalo) * kC;
+        const float4 a = *reinterpret_cast<const float4*>(p0 + off);
+        const float4 b = *reinterpret_cast<const float4*>(p1 + off);
+        const float wa = wyz * wx_first, wb = wyz * wx_second;
+        acc.x = fmaf(wa, a.x, acc.x); acc.y = fmaf(wa, a.y, acc.y);
+        acc.z = fmaf(wa, a.z, acc.z); acc.w = fmaf(wa, a.w, acc.w);
+        acc.x = fmaf(wb, b.x, acc.x); acc.y = fmaf(wb, b.y, acc.y);
+        acc.z = fmaf(wb, b.z, acc.z); acc.w = fmaf(wb, b.w, acc.w);
+      }
+    float* dst = sm.rotA + (j * 4) * kRotC + d * kRotD + h * 8 + w;
+    dst[0] = acc.x; dst[kRotC] = acc.y; dst[2 * kRotC] = acc.z; dst[3 * kRotC] = acc.w;
+  }
+}
+
+// rotated volume (fp32) -> the three views of the A^T operand (fp16, pair scale `sb`)
+__device__ __forceinline__ void pack_views(BwdTcSmem& sm, float sb) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // view y: [c][d][h][w] as it lies; lanes run over (d, h): contiguous 16 B stores
+    const int task = t + 256 * i, c = task >> 6, d = (task >> 3) & 7, h = task & 7;
+    const float* src = sm.rotA + c * kRotC + d * kRotD + h * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    *reinterpret_cast<uint4*>(sm.at + kAtView + c * 1024 + d * 128 + h * 16) =
+        make_uint4(pack_h2(a.x * sb, a.y * sb), pack_h2(a.z * sb, a.w * sb), pack_h2(b.x * sb, b.y * sb), pack_h2(b.z * sb, b.w * sb));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // view z: [c][h][d][w]; lanes run over (h, d)
+    const int task = t + 256 * i, c = task >> 6, h = (task >> 3) & 7, d = task & 7;
+    const float* src = sm.rotA + c * kRotC + d * kRotD + h * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    *reinterpret_cast<uint4*>(sm.at + 2 * kAtView + c * 1024 + h * 128 + d * 16) =
+        make_uint4(pack_h2(a.x * sb, a.y * sb), pack_h2(a.z * sb, a.w * sb), pack_h2(b.x * sb, b.y * sb), pack_h2(b.z * sb, b.w * sb));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // view x: [c][d][w][h]; lanes run over (d, w), eight h gathered per thread
+    const int task = t + 256 * i, c = task >> 6, d = (task >> 3) & 7, w = task & 7;
+    const float* src = sm.rotA + c * kRotC + d * kRotD + w;
+    *reinterpret_cast<uint4*>(sm.at + c * 1024 + d * 128 + w * 16) =
+        make_uint4(pack_h2(src[0] * sb, src[8] * sb), pack_h2(src[16] * sb, src[24] * sb), pack_h2(src[32] * sb, src[40] * sb),
+                   pack_h2(src[48] * sb, src[56] * sb));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__ tgt_feat,
+                    const float* __restrict__ R, int r_per_pair, const float* __restrict__ W1,
+                    const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ base,
+                    const float* __restrict__ grad_scores, const __half* __restrict__ h1_saved,
+                    const float* __restrict__ pair_inv, float* __restrict__ g_vol, float* __restrict__ g_tgt,
+                    float* __restrict__ g_W1, float* __restrict__ g_W2, float* __restrict__ g_b2, int B, int64_t N) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BwdTcSmem& sm = *reinterpret_cast<BwdTcSmem*>(smem_raw);
+  const int64_t total = (int64_t)B * N;
+  const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+  if (lo >= hi) return;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t bar_s = smem_u32(&sm.bar);
+
+  // ---- set-up: W2 (fp32), W1^T operand (fp16, permuted rows), base coordinates, barrier, TMEM ----
+  for (int i = t; i < kO * kO; i += kThreads) {
+    const int o = i / kO, c = i % kO;
+    sm.w2s[((o % 8) * 4 + o / 8) * kH1Row + c] = W2[i];
+  }
+  for (int i = t; i < kO * kK; i += kThreads) {
+    const int o = i / kK, k = i - o * kK;  // coalesced read of W1[o][k]
+    const int view = k >> 7, c = (k >> 3) & 15, kk = k & 7;
+    const int grp = (c >> 2) * 12 + view * 4 + (c & 3);  // n' / 8
+    *reinterpret_cast<__half*>(sm.w1t + grp * 512 + (o >> 3) * 128 + kk * 16 + (o & 7) * 2) = __float2half_rn(__ldg(W1 + i));
+  }
+  if (t < 8) sm.base[t] = base ? base[t] : 0.0f;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(bar_s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&sm.tmem_slot), kTmemCols);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+  const uint32_t at_s = smem_u32(sm.at), w1t_s = smem_u32(sm.w1t), dh1a_s = smem_u32(sm.dh1a), dh1b_s = smem_u32(sm.dh1b);
+  constexpr uint32_t idA = instr_desc(64, kColW), idW = instr_desc(128, 32);
+
+  // conv2 / normalise mapping: thread = (position, 8 channels cg2*8 ..)
+  const int pos = t >> 2, cg2 = t & 3;
+  // accumulator read-out mapping: TMEM quadrant of this warp, column half
+  const int qd = warp & 3, hf = warp >> 2;
+  const uint32_t tq = tmem + ((uint32_t)(32 * qd) << 16);
+  // fold mapping: lanes 0-15 / 16-31 hold the two M=64 accumulators: position 16 qd + lane%16, channel group g
+  const int fpos = 16 * qd + (lane & 15), fp = fpos >> 3, fq = fpos & 7, fg = (lane >> 4) * 2 + hf;
+
+  float b2r[8], tg[8];
+#pragma unroll
+  for (int oo = 0; oo < 8; ++oo) b2r[oo] = b2[cg2 * 8 + oo];
+  float aW1[3][16];  // dW1[o = 16 hf + oo][k = view*128 + 32 qd + lane]
+  float aW2[4];      // dW2[o = t >> 3][i = (t & 7) * 4 ..]
+  float ab2[8];      // db2[cg2*8 + oo] (this thread's position only)
+  float aT[8];       // dT_b[cg2*8 + oo][pos]
+  float aV[2][kC];   // dV_b[c][voxel t + 256 j]
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int oo = 0; oo < 16; ++oo) aW1[v][oo] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) aW2[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ab2[i] = aT[i] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int c = 0; c < kC; ++c) aV[j][c] = 0.0f;
+
+  auto flush_pair = [&](int b) {  // dT and dV of pair b leave the CTA
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo) {
+      if (aT[oo] != 0.0f) atomicAdd(g_tgt + ((size_t)b * kO + cg2 * 8 + oo) * kP + pos, aT[oo]);
+      aT[oo] = 0.0f;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < kC; ++c) {
+        if (aV[j][c] != 0.0f) atomicAdd(g_vol + ((size_t)b * kC + c) * kVox + t + 256 * j, aV[j][c]);
+        aV[j][c] = 0.0f;
+      }
+  };
+
+  int cur_b = -1;
+  float pinv = 1.0f;
+  uint32_t phase = 0;
+  for (int64_t it = lo; it < hi; ++it) {
+    const int b = (int)(it / N);
+    const int64_t n = it - (int64_t)b * N;
+    if (b != cur_b) {
+      if (cur_b >= 0) flush_pair(cur_b);
+      __syncthreads();
+      stage_volume<float>(sm.vol, vol_src + (size_t)b * kC * kVox);
+#pragma unroll
+      for (int oo = 0; oo < 8; ++oo) tg[oo] = tgt_feat[((size_t)b * kO + cg2 * 8 + oo) * kP + pos];
+      pinv = __ldg(pair_inv + b);
+      cur_b = b;
+    }
+    if (t < 9) sm.Rcur[t] = R[(r_per_pair ? (size_t)it : (size_t)n) * 9 + t];
+    // H1 of this item as the forward kept it (fp16, pair-scaled): in flight during the gather
+    const uint4 hq = __ldg(reinterpret_cast<const uint4*>(h1_saved + ((size_t)it * kP + pos) * kO + cg2 * 8));
+    const float g64 = grad_scores[it] * (1.0f / 64.0f);  // d mean over the 64 positions
+    __syncthreads();
+    float Rr[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Rr[e] = sm.Rcur[e];
+
+    // ---------------- X = rotate(V_b, R), H1 ----------------
+    gather_rotated(sm, Rr);
+    {
+      const __half2* hp = reinterpret_cast<const __half2*>(&hq);
+      float* dst = sm.h1s + pos * kH1Row + cg2 * 8;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f2 = __half22float2(hp[e]);
+        dst[2 * e] = f2.x * pinv;
+        dst[2 * e + 1] = f2.y * pinv;
+      }
+    }
+    __syncthreads();
+
+    // ---------------- A^T operand; conv2, normalise, dH2 ----------------
+    pack_views(sm, 1.0f / pinv);
+    float v[8];
+    {
+      float h[kO];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 x = *reinterpret_cast<const float4*>(sm.h1s + pos * kH1Row + 4 * i);
+        h[4 * i] = x.x; h[4 * i + 1] = x.y; h[4 * i + 2] = x.z; h[4 * i + 3] = x.w;
+      }
+#pragma unroll
+      for (int oo = 0; oo < 8; ++oo) {
+        const float* wr = sm.w2s + (oo * 4 + cg2) * kH1Row;
+        float a = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(wr + 4 * i);
+          a = fmaf(w.x, h[4 * i], a); a = fmaf(w.y, h[4 * i + 1], a);
+          a = fmaf(w.z, h[4 * i + 2], a); a = fmaf(w.w, h[4 * i + 3], a);
+        }
+        v[oo] = a + b2r[oo];
+      }
+    }
+    float ss = 0.0f, ft = 0.0f;
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo) { ss = fmaf(v[oo], v[oo], ss); ft = fmaf(v[oo], tg[oo], ft); }
+    ss = quad_sum(ss);
+    ft = quad_sum(ft);
+    {
+      // F = v / max(|v|, eps) (modules/modules.py:122).  d<F,T>/dv = (T - F <F,T>) / |v| above the clamp, T / eps below
+      const float nraw = sqrtf(ss), nr = fmaxf(nraw, 1e-12f), inv = 1.0f / nr;
+      const float fdot = ft * inv;
+      const bool clamped = nraw < 1e-12f;
+#pragma unroll
+      for (int oo = 0; oo < 8; ++oo) {
+        const float F = v[oo] * inv;
+        const float d2 = g64 * inv * (clamped ? tg[oo] : tg[oo] - F * fdot);
+        aT[oo] = fmaf(g64, F, aT[oo]);
+        ab2[oo] += d2;
+        v[oo] = d2;
+      }
+      float* dst = sm.dh2 + pos * kH1Row + cg2 * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+
+    // ---------------- dW2 += dH2^T H1 ; dH1 = (dH2 W2) * [H1 > 0] ----------------
+    {
+      const int o = t >> 3, i0 = (t & 7) * 4;
+#pragma unroll 8
+      for (int p = 0; p < kP; ++p) {
+        const float d = sm.dh2[p * kH1Row + o];
+        const float4 h = *reinterpret_cast<const float4*>(sm.h1s + p * kH1Row + i0);
+        aW2[0] = fmaf(d, h.x, aW2[0]); aW2[1] = fmaf(d, h.y, aW2[1]);
+        aW2[2] = fmaf(d, h.z, aW2[2]); aW2[3] = fmaf(d, h.w, aW2[3]);
+      }
+    }
+    float dh1[8];
+    {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dh1[j] = 0.0f;
+#pragma unroll 4
+      for (int o = 0; o < kO; ++o) {
+        const float d = sm.dh2[pos * kH1Row + o];
+        const float* wr = sm.w2s + ((o % 8) * 4 + o / 8) * kH1Row + cg2 * 8;  // W2[o][cg2*8 ..]
+        const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+        dh1[0] = fmaf(d, w0.x, dh1[0]); dh1[1] = fmaf(d, w0.y, dh1[1]);
+        dh1[2] = fmaf(d, w0.z, dh1[2]); dh1[3] = fmaf(d, w0.w, dh1[3]);
+        dh1[4] = fmaf(d, w1.x, dh1[4]); dh1[5] = fmaf(d, w1.y, dh1[5]);
+        dh1[6] = fmaf(d, w1.z, dh1[6]); dh1[7] = fmaf(d, w1.w, dh1[7]);
+      }
+      const float* hp = sm.h1s + pos * kH1Row + cg2 * 8;  // ReLU mask (modules/modules.py:68)
+      float mx = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dh1[j] = hp[j] > 0.0f ? dh1[j] : 0.0f;
+        mx = fmaxf(mx, fabsf(dh1[j]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) sm.red[warp] = mx;
+    }
+    __syncthreads();
+
+    // ---------------- dH1 -> fp16 operands under the item's power-of-two scale ----------------
+    float invS;
+    {
+      float m = sm.red[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, sm.red[w]);
+      int e = ((__float_as_int(m) >> 23) & 0xff) - 127;  // floor(log2 max|dH1|)
+      e = m > 0.0f ? min(max(e, -100), 100) : 13;
+      const float S = __int_as_float((127 + 13 - e) << 23);  // 2^13 <= max * S < 2^14
+      invS = __int_as_float((127 - 13 + e) << 23);
+      *reinterpret_cast<uint4*>(sm.dh1a + (pos >> 3) * 512 + cg2 * 128 + (pos & 7) * 16) =
+          make_uint4(pack_h2(dh1[0] * S, dh1[1] * S), pack_h2(dh1[2] * S, dh1[3] * S), pack_h2(dh1[4] * S, dh1[5] * S),
+                     pack_h2(dh1[6] * S, dh1[7] * S));
+      unsigned char* bb = sm.dh1b + cg2 * kDh1bPitch + (pos >> 3) * 128 + (pos & 7) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<__half*>(bb + j * 16) = __float2half_rn(dh1[j] * S);
+    }
+    fence_proxy_async();  // A^T, dH1 operands: generic-proxy stores -> async proxy
+    __syncthreads();
+
+    // ---------------- the two contractions on the tensor core ----------------
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half)  // dA: rows = positions, columns = 192 of the permuted W1^T rows
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          umma_f16(tmem + ((uint32_t)(16 * half) << 16), smem_desc(dh1a_s + j * 256, 128, 512),
+                   smem_desc(w1t_s + half * (kColW / 8) * 512 + j * 256, 128, 512), idA, j);
+#pragma unroll
+      for (int view = 0; view < 3; ++view)  // dW1^T: rows = (c, kk) of the view, K = the 64 positions
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_f16(tmem + kColW + view * 32, smem_desc(at_s + view * kAtView + j * 256, 128, 1024),
+                   smem_desc(dh1b_s + j * 256, 128, kDh1bPitch), idW, j);
+      umma_commit(bar_s);
+      __syncwarp();
+    }
+
+    // ---------------- meanwhile: bucket the 512 output voxels by the corner line of their taps ----------------
+    int* cnt = reinterpret_cast<int*>(sm.dh2);            // [1000] voxels per corner line, then running fill offset
+    int* start = cnt + kLines;                            // [1000] exclusive prefix sum
+    unsigned short* list = reinterpret_cast<unsigned short*>(start + kLines);  // [512] output voxels sorted by line
+    {
+      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;
+      __syncthreads();
+      int myline[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        myline[j] = __float_as_int(sm.taps[t + 256 * j].x);
+        atomicAdd(&cnt[myline[j]], 1);
+      }
+      __syncthreads();
+      {  // exclusive scan of 1000 counters: 4 per thread (250 threads), warp scan, then the 8 warp totals
+        const int i0 = 4 * t;
+        int c4[4] = {0, 0, 0, 0};
+        if (i0 < kLines) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c4[e] = cnt[i0 + e];
+        }
+        const int local = c4[0] + c4[1] + c4[2] + c4[3];
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        int* wtot = reinterpret_cast<int*>(sm.red);
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        int basep = incl - local;
+        for (int w = 0; w < warp; ++w) basep += wtot[w];
+        if (i0 < kLines) {
+          start[i0] = basep;
+          start[i0 + 1] = basep + c4[0];
+          start[i0 + 2] = basep + c4[0] + c4[1];
+          start[i0 + 3] = basep + c4[0] + c4[1] + c4[2];
+        }
+      }
+      __syncthreads();
+      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;   // re-used as the fill cursor
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) list[start[myline[j]] + atomicAdd(&cnt[myline[j]], 1)] = (unsigned short)(t + 256 * j);
+    }
+
+    // ---------------- accumulators: dW1^T -> registers, dA -> dX (fold of the three views) ----------------
+    mbar_wait(bar_s, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      const float sc = invS * pinv;  // undo the item's dH1 scale and the pair's volume scale
+      uint32_t r[16];
+#pragma unroll
+      for (int view = 0; view < 3; ++view) {
+        tmem_ld16(tq + kColW + view * 32 + hf * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int oo = 0; oo < 16; ++oo) aW1[view][oo] = fmaf(__uint_as_float(r[oo]), sc, aW1[view][oo]);
+      }
+    }
+    {
+      uint32_t r[32];
+      // view x: dX[c, d=p, h=q, w=kk] = ...   (every element of dX written exactly once: no zeroing needed)
+      tmem_ld32(tq + hf * 96, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        float* dst = sm.rotA + (4 * fg + cc) * kRotC + fp * kRotD + fq * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(r[cc * 8]) * invS, __uint_as_float(r[cc * 8 + 1]) * invS,
+                                                      __uint_as_float(r[cc * 8 + 2]) * invS, __uint_as_float(r[cc * 8 + 3]) * invS);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(__uint_as_float(r[cc * 8 + 4]) * invS, __uint_as_float(r[cc * 8 + 5]) * invS,
+                                                          __uint_as_float(r[cc * 8 + 6]) * invS, __uint_as_float(r[cc * 8 + 7]) * invS);
+      }
+      tmem_ld32(tq + hf * 96 + 32, r);  // view y, in flight across the barrier
+      tmem_ld_wait();
+      __syncthreads();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {  // dX[c, d=p, h=kk, w=q] += ...
+        float* dst = sm.rotA + (4 * fg + cc) * kRotC + fp * kRotD + fq;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) dst[kk * 8] = fmaf(__uint_as_float(r[cc * 8 + kk]), invS, dst[kk * 8]);
+      }
+      tmem_ld32(tq + hf * 96 + 64, r);  // view z
+      tmem_ld_wait();
+      tc_fence_before();                // the next item's MMAs overwrite these accumulators
+      __syncthreads();
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {  // dX[c, d=kk, h=p, w=q] += ...
+        float* dst = sm.rotA + (4 * fg + cc) * kRotC + fp * 8 + fq;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) dst[kk * kRotD] = fmaf(__uint_as_float(r[cc * 8 + kk]), invS, dst[kk * kRotD]);
+      }
+    }
+    __syncthreads();
+
+    // ---------------- dV_b += rotate^T(dX): adjoint of utils.py:113-131 as a gather over the buckets ----------------
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int vi = t + 256 * j;
+      const int z = vi >> 6, y = (vi >> 3) & 7, x = vi & 7;
+      const int lin = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
+#pragma unroll 1
+      for (int dlt = 0; dlt < 8; ++dlt) {
+        const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
+        const int cell = lin - (dz * kHalo * kHalo + dy * kHalo + dx);   // corner line of the voxels that tap v at (dx,dy,dz)
+        const int nn = cnt[cell], s0 = start[cell];                      // cell >= 0: lin >= 111
+        for (int e = 0; e < nn; ++e) {
+          const int vo = list[s0 + e];
+          const float4 tp = sm.taps[vo];
+          const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
+          const float* src = sm.rotA + (vo >> 6) * kRotD + (vo & 63);
+#pragma unroll
+          for (int c = 0; c < kC; ++c) aV[j][c] = fmaf(w, src[c * kRotC], aV[j][c]);
+        }
+      }
+    }
+    __syncthreads();  // rotA (dX), taps and the buckets are re-used by the next hypothesis
+  }
+  flush_pair(cur_b);
+  // weight gradients: one atomic per accumulator and CTA
+#pragma unroll
+  for (int view = 0; view < 3; ++view)
+#pragma unroll
+    for (int oo = 0; oo < 16; ++oo) atomicAdd(g_W1 + (16 * hf + oo) * kK + view * 128 + 32 * qd + lane, aW1[view][oo]);
+  {
+    const int o = t >> 3, i0 = (t & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(g_W2 + o * kO + i0 + i, aW2[i]);
+    // db2: sum over the 64 positions inside the CTA first (threads with equal cg2 = t & 3)
+    __syncthreads();
+    float* red = sm.h1s;  // [4 cg2][8 oo][64 pos]
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo) red[(cg2 * 8 + oo) * kP + pos] = ab2[oo];
+    __syncthreads();
+    if (t < kO) {
+      float s = 0.0f;
+      for (int p = 0; p < kP; ++p) s += red[t * kP + p];
+      atomicAdd(g_b2 + t, s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int launch_score_bwd_tc(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair,
+                        const float* W1, const float* W2, const float* b2, const float* base,
+                        const float* grad_scores, const void* h1_saved, const float* pair_inv, float* g_vol,
+                        float* g_tgt, float* g_W1, float* g_W2, float* g_b2, int B, int64_t N, cudaStream_t s) {
+  const int64_t total = (int64_t)B * N;
+  if (total == 0) return AHV_OK;
+  if (!h1_saved || !pair_inv) return AHV_EINVAL;
+  int dev = 0, sms = 0;
+  AHV_CUDA_OK(cudaGetDevice(&dev));
+  AHV_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = (unsigned)(total < sms ? total : sms);
+  const size_t smem = sizeof(BwdTcSmem);
+  AHV_CUDA_OK(cudaFuncSetAttribute(score_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_bwd_tc_kernel<<<grid, kThreads, smem, s>>>(vol_src, tgt_feat, R, r_per_pair, W1, W2, b2, base, grad_scores,
+                                                   static_cast<const __half*>(h1_saved), pair_inv, g_vol, g_tgt,
+                                                   g_W1, g_W2, g_b2, B, N);
+  AHV_CUDA_OK(cudaGetLastError());
+  return AHV_OK;
+}
+
+}  // namespace ahv

@@ -154,10 +154,12 @@ def score_train(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tensor, 
 
 def score_backward(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor,
                    b2: torch.Tensor, grad_scores: torch.Tensor, h1_saved: torch.Tensor | None = None,
-                   pair_inv: torch.Tensor | None = None):
+                   pair_inv: torch.Tensor | None = None, math: int = MATH_TC):
     """Fused gradient of the verification scores (modules/model.py:53-56 under autograd): returns
     (grad_vol_src [B,16,8,8,8], grad_tgt_feat [B,32,64], grad_W1 [32,384], grad_W2 [32,32], grad_b2 [32]).
-    With `h1_saved` / `pair_inv` from `score_train` the kernel reads conv1's output instead of recomputing it."""
+    With `h1_saved` / `pair_inv` from `score_train` the kernel reads conv1's output instead of recomputing it, and
+    `math` picks how it contracts dA = dH1 W1 and dW1 = dH1^T A: MATH_TC on tcgen05, MATH_FP32 in FFMA.  Without them
+    it is the exact fp32 kernel whatever `math` says."""
     vs, tg, R, gs = _dev(vol_src, "vol_src"), _dev(tgt_feat, "tgt_feat"), _dev(R, "R"), _dev(grad_scores, "grad_scores")
     W1, W2, b2 = _dev(W1.reshape(32, 384), "W1"), _dev(W2.reshape(32, 32), "W2"), _dev(b2, "b2")
     B = vs.shape[0]
@@ -180,7 +182,7 @@ def score_backward(vol_src: torch.Tensor, tgt_feat: torch.Tensor, R: torch.Tenso
             _lib.check(_lib.lib().ahv_score_backward_saved(vs.data_ptr(), tg.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(),
                                                            W2.data_ptr(), b2.data_ptr(), base.data_ptr(), gs.data_ptr(),
                                                            h1.data_ptr(), pi.data_ptr(), g_vol.data_ptr(), g_tgt.data_ptr(),
-                                                           g_w1.data_ptr(), g_w2.data_ptr(), g_b2.data_ptr(), B, N, _stream(vs)),
+                                                           g_w1.data_ptr(), g_w2.data_ptr(), g_b2.data_ptr(), B, N, int(math), _stream(vs)),
                        "ahv_score_backward_saved")
         else:
             _lib.check(_lib.lib().ahv_score_backward(vs.data_ptr(), tg.data_ptr(), R.data_ptr(), int(per_pair), W1.data_ptr(),

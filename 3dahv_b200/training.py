@@ -69,7 +69,7 @@ class _VerifyScores(torch.autograd.Function):
     """scores[b,n] of modules/model.py:53-56; forward fused, backward chunked recomputation."""
 
     @staticmethod
-    def forward(ctx, vol_src, vol_tgt, R, W1, W2, b2, math, chunk, fused_backward, save_activations):
+    def forward(ctx, vol_src, vol_tgt, R, W1, W2, b2, math, chunk, fused_backward, save_activations, tc_backward=True):
         tgt = ops.forward_3d2d(vol_tgt.detach().float(), W1.detach(), W2.detach(), b2.detach())
         h1 = pair_inv = None
         needs_grad = any(t.requires_grad for t in (vol_src, vol_tgt, W1, W2, b2))
@@ -82,6 +82,7 @@ class _VerifyScores(torch.autograd.Function):
         ctx.save_for_backward(vol_src, vol_tgt, R, W1, W2, b2, tgt, h1, pair_inv)
         ctx.chunk = chunk
         ctx.fused_backward = fused_backward
+        ctx.bwd_math = MATH_TC if tc_backward else MATH_FP32
         return scores
 
     @staticmethod
@@ -93,13 +94,13 @@ class _VerifyScores(torch.autograd.Function):
         if ctx.fused_backward:
             g_vs, g_tgt, g_w1, g_w2, g_b = ops.score_backward(vol_src.detach().float(), tgt_saved, R, W1.detach().float(),
                                                               W2.detach().float(), b2.detach().float(),
-                                                              grad_scores.contiguous().float(), h1, pair_inv)
+                                                              grad_scores.contiguous().float(), h1, pair_inv, ctx.bwd_math)
             with torch.enable_grad():   # target side: B volumes through the differentiable head
                 vt = vol_tgt.detach().float().requires_grad_(True)
                 w1, w2, bb = (t.detach().float().requires_grad_(True) for t in (W1, W2, b2))
                 gt = torch.autograd.grad(head_torch(vt, w1, w2, bb), [vt, w1, w2, bb], grad_outputs=g_tgt)
             return (g_vs, gt[0], None, (g_w1 + gt[1].reshape(32, 384)).reshape(W1.shape),
-                    (g_w2 + gt[2].reshape(32, 32)).reshape(W2.shape), g_b + gt[3], None, None, None, None)
+                    (g_w2 + gt[2].reshape(32, 32)).reshape(W2.shape), g_b + gt[3], None, None, None, None, None)
         with torch.enable_grad():
             vs = vol_src.detach().float().requires_grad_(True)
             vt = vol_tgt.detach().float().requires_grad_(True)
@@ -123,11 +124,11 @@ class _VerifyScores(torch.autograd.Function):
             gt = torch.autograd.grad(tgt, [vt, w1, w2, bb], grad_outputs=g_tgt, allow_unused=True)
             g_vt = gt[0]
             g_w1, g_w2, g_b = g_w1 + gt[1], g_w2 + gt[2], g_b + gt[3]
-        return g_vs, g_vt, None, g_w1.reshape(W1.shape), g_w2.reshape(W2.shape), g_b, None, None, None, None
+        return g_vs, g_vt, None, g_w1.reshape(W1.shape), g_w2.reshape(W2.shape), g_b, None, None, None, None, None
 
 
 def verification_scores(vol_src, vol_tgt, R, W1, W2, b2, math: int = MATH_TC, chunk: int = 1024,
-                        fused_backward: bool = True, save_activations: bool = False) -> torch.Tensor:
+                        fused_backward: bool = True, save_activations: bool = False, tc_backward: bool = True) -> torch.Tensor:
     """Differentiable pred_sim [B,N] (modules/model.py:53-56 / :193).  R [N,3,3] or [B,N,3,3].
     `save_activations` (opt-in; tensor-core forward + fused backward only): the forward keeps conv1's ReLU'd output of
     every (pair, hypothesis) - 4 KB per item in fp16, against the ~420 KB per hypothesis the reference's autograd keeps -
@@ -137,8 +138,11 @@ def verification_scores(vol_src, vol_tgt, R, W1, W2, b2, math: int = MATH_TC, ch
     of ReLU's kink than in an fp32 evaluation.  Gradients that do not pass through the mask (vol_tgt, W2, b2) agree
     with the default to 4e-4 of their maximum; vol_src / W1 to a few per cent at the voxels such an element feeds
     (measured 2.6 % of the maximum; tests/test_gpu_training.py).  The default recomputes and matches the reference's
-    fp32 autograd to 1e-4."""
-    return _VerifyScores.apply(vol_src, vol_tgt, R.contiguous(), W1, W2, b2, math, chunk, fused_backward, save_activations)
+    fp32 autograd to 1e-4.  With saved activations `tc_backward` (default) also moves the backward's two large
+    contractions, dA = dH1 W1 and dW1 = dH1^T A, to tcgen05 with fp16 operands under power-of-two scales
+    (csrc/ahv_score_bwd_tc.cu); False keeps them in fp32 FFMA."""
+    return _VerifyScores.apply(vol_src, vol_tgt, R.contiguous(), W1, W2, b2, math, chunk, fused_backward, save_activations,
+                               tc_backward)
 
 
 class _InfoNCE(torch.autograd.Function):

@@ -127,7 +127,9 @@ AHV_API int ahv_resblock3d(const float* x, const float* conv1_w, const float* co
  * ahv_score_train = ahv_score with AHV_MATH_TC, fp32 volumes, k = 0, that also keeps conv1's ReLU'd output of every
  * (pair, hypothesis) - h1_saved [B*N][64][32] fp16 in the pair's scaled units - and 1/scale per pair
  * (pair_inv_scale [B]); ahv_score_backward_saved = ahv_score_backward reading them instead of recomputing conv1
- * (786 k of the backward's 2.4 M FMA per item).  Workspace: ahv_workspace_bytes(B, N, 1). */
+ * (786 k of the backward's 2.4 M FMA per item).  math_mode AHV_MATH_FP32: the remaining contractions in fp32 FFMA;
+ * AHV_MATH_TC: dA = dH1 W1 and dW1 = dH1^T A on tcgen05 (fp16 operands under power-of-two scales, fp32 accumulation in
+ * TMEM; csrc/ahv_score_bwd_tc.cu).  Workspace: ahv_workspace_bytes(B, N, 1). */
 AHV_API int ahv_score_train(const float* vol_src, const float* tgt_feat, const float* R, int r_per_pair, const float* W1,
                             const float* W2, const float* b2, const float* base, float* scores, void* h1_saved,
                             float* pair_inv_scale, int B, int64_t N, void* workspace, size_t workspace_bytes,
@@ -136,7 +138,7 @@ AHV_API int ahv_score_backward_saved(const float* vol_src, const float* tgt_feat
                                      const float* W1, const float* W2, const float* b2, const float* base,
                                      const float* grad_scores, const void* h1_saved, const float* pair_inv_scale,
                                      float* grad_vol, float* grad_tgt, float* grad_W1, float* grad_W2, float* grad_b2,
-                                     int B, int64_t N, void* stream);
+                                     int B, int64_t N, int math_mode, void* stream);
 
 /* infoNCE_loss given the scores (training variant, modules/model.py:43-63 / model_co3d.py:41-61), one launch:
  * positives of pair b = hypotheses whose rotation lies within acc_thr_deg of gt_R[b] (:46-49);

@@ -10,6 +10,7 @@ B, N = int(os.environ.get("AHV_B", "12")), int(os.environ.get("AHV_N", "9000"))
 chunk = int(os.environ.get("AHV_CHUNK", "1024"))
 fused = os.environ.get("AHV_FUSED_BWD", "1") != "0"
 save = os.environ.get("AHV_SAVE", "0") != "0"
+tc_bwd = os.environ.get("AHV_TC_BWD", "1") != "0"
 W1, W2, b2, vs, vt, _ = bench.synthetic_inputs(torch, B, 16)
 W1, W2, b2 = (t.to(dev).requires_grad_(True) for t in (W1, W2, b2))
 vs, vt = vs.to(dev).requires_grad_(True), vt.to(dev).requires_grad_(True)
@@ -17,7 +18,7 @@ gt = ahv.so3.sample_rotations(B, seed=1, device=dev)
 Rs = torch.cat([gt[:, None], ahv.so3.sample_rotations(B * (N - 1), seed=2, device=dev).reshape(B, N - 1, 3, 3)], 1).contiguous()
 
 def step():
-    s = ahv.training.verification_scores(vs, vt, Rs, W1, W2, b2, chunk=chunk, fused_backward=fused, save_activations=save)
+    s = ahv.training.verification_scores(vs, vt, Rs, W1, W2, b2, chunk=chunk, fused_backward=fused, save_activations=save, tc_backward=tc_bwd)
     loss = ahv.training.infonce_loss(s, Rs, gt, acc_thr_deg=15.0).mean()
     loss.backward()
     return loss
@@ -32,5 +33,5 @@ for a, b in ev:
 torch.cuda.synchronize()
 ms = sorted(a.elapsed_time(b) for a, b in ev)[n // 2]
 print(json.dumps({"what": "training step: fused scores forward + InfoNCE + backward to volumes and head weights",
-                  "pairs": B, "hyps_per_pair": N, "saved_activations": save and fused, "backward": "fused kernel (ahv_score_backward)" if fused else f"chunked recomputation (chunk {chunk})",
+                  "pairs": B, "hyps_per_pair": N, "saved_activations": save and fused, "tcgen05_backward": save and fused and tc_bwd, "backward": "fused kernel (ahv_score_backward)" if fused else f"chunked recomputation (chunk {chunk})",
                   "ms_per_step_p50": ms, "hyp_pairs_per_s_fwd_bwd": B * N / (ms * 1e-3), "loss": float(loss.detach())}))

@@ -234,12 +234,14 @@ def test_fused_infonce_kernel_vs_eager_formulation(ahv):
 
 def test_saved_activation_backward_matches_recomputation(ahv, golden):
     """The training forward can keep conv1's ReLU'd output (fp16, 4 KB per item) so that the backward kernel reads it
-    instead of recomputing conv1 (opt-in).  Per-pair and shared rotation sets, ranges that cross pair boundaries, an
-    outlier volume (pair scale != 1).  Gradients that do not pass through the ReLU mask agree to fp16-operand accuracy
-    (2e-3 of the maximum).  vol_src and W1 do pass through it, and the ~0.05 % of pre-activations within fp16-operand
-    error of zero take the mask of the forward that was actually run: a flipped element moves the gradient of the
-    voxels it feeds by a few per cent of the maximum (measured 2.6 %), so those two are gated at 8 % worst element and
-    5 % in the L2 norm."""
+    instead of recomputing conv1 (opt-in), and then contract dA / dW1 on tcgen05 (`tc_backward`) or in FFMA.  Per-pair
+    and shared rotation sets, ranges that cross pair boundaries, an outlier volume (pair scale != 1).  Gradients that
+    do not pass through the ReLU mask agree with the recomputing form to fp16-operand accuracy (2e-3 of the maximum).
+    vol_src and W1 do pass through it, and the ~0.05 % of pre-activations within fp16-operand error of zero take the
+    mask of the forward that was actually run: a flipped element moves the gradient of the voxels it feeds by a few
+    per cent of the maximum (measured 2.6 %), so against the recomputing form those two are only gated at 8 % worst
+    element and 5 % in the L2 norm - their exact check is the next test; the two saved-activation forms share the
+    mask and agree with each other to fp16-operand accuracy everywhere."""
     dev = torch.device("cuda", 0)
     g, w = golden["shared_n3000_b3"], golden["weights"]
     T = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
@@ -248,17 +250,70 @@ def test_saved_activation_backward_matches_recomputation(ahv, golden):
         vs0, vt0 = T(g["vol_src"][:B]) * scale, T(g["vol_tgt"][:B])
         R = T(g["R"][: B * N]).reshape(B, N, 3, 3).contiguous() if per_pair else T(g["R"][:N])
         gs = torch.randn(B, N, generator=gen).to(dev)
-        grads = []
-        for save in (True, False):
+        grads = {}
+        for mode in ("recompute", "saved_fp32", "saved_tc"):
             leaves = [t.clone().requires_grad_(True) for t in (vs0, vt0, T(w["W1"]), T(w["W2"]), T(w["b2"]))]
-            s = ahv.training.verification_scores(*leaves[:2], R, *leaves[2:], math=ahv.MATH_TC, save_activations=save)
+            s = ahv.training.verification_scores(*leaves[:2], R, *leaves[2:], math=ahv.MATH_TC,
+                                                 save_activations=mode != "recompute", tc_backward=mode == "saved_tc")
             (s * gs).sum().backward()
-            grads.append((s.detach(), [l.grad.clone() for l in leaves]))
-        assert torch.equal(grads[0][0], grads[1][0])                       # same forward kernel arithmetic
-        for name, a, b in zip(("vol_src", "vol_tgt", "W1", "W2", "b2"), grads[0][1], grads[1][1]):
-            scale_g = float(b.abs().max())
-            worst, l2 = float((a - b).abs().max()) / scale_g, float((a - b).norm() / b.norm())
-            if name in ("vol_src", "W1"):
-                assert worst <= 8e-2 and l2 <= 5e-2, (B, N, per_pair, name, worst, l2)
-            else:
-                assert worst <= 2e-3, (B, N, per_pair, name, worst)
+            grads[mode] = (s.detach(), [l.grad.clone() for l in leaves])
+        names = ("vol_src", "vol_tgt", "W1", "W2", "b2")
+        for mode in ("saved_fp32", "saved_tc"):
+            assert torch.equal(grads[mode][0], grads["recompute"][0])          # same forward kernel arithmetic
+            for name, a, b in zip(names, grads[mode][1], grads["recompute"][1]):
+                scale_g = float(b.abs().max())
+                worst, l2 = float((a - b).abs().max()) / scale_g, float((a - b).norm() / b.norm())
+                if name in ("vol_src", "W1"):
+                    assert worst <= 8e-2 and l2 <= 5e-2, (B, N, per_pair, mode, name, worst, l2)
+                else:
+                    assert worst <= 2e-3, (B, N, per_pair, mode, name, worst)
+        for name, a, b in zip(names, grads["saved_tc"][1], grads["saved_fp32"][1]):   # same mask: operand rounding only
+            worst = float((a - b).abs().max()) / float(b.abs().max())
+            assert worst <= 2e-3, (B, N, per_pair, "tc vs fp32 contractions", name, worst)
+
+
+@pytest.mark.parametrize("per_pair", [False, True])
+def test_saved_activation_backward_is_the_gradient_of_the_function_that_ran(ahv, golden, oracle, per_pair):
+    """Exact check of the saved-activation backward (both contraction forms) against fp64 autograd through the oracle's
+    restatement of the chain (utils.py:113-131, modules/modules.py:112-124, modules/model.py:53-56) in which conv1's
+    output takes the VALUE the forward kept and the ReLU MASK of that value - the function the training forward
+    evaluated.  Upstream gradients span six decades (the per-item power-of-two operand scale), the second volume
+    carries an outlier voxel (pair scale).  fp32 contractions: 2e-5 of each gradient's maximum; tcgen05 contractions
+    (fp16 operands): 1e-3."""
+    import torch.nn.functional as F
+
+    dev = torch.device("cuda", 0)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    T = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    B, N = 2, 150
+    vs = T(g["vol_src"][:B]).clone()
+    vs[1, 3, 2, 5, 1] = 4.0e3
+    R = T(g["R"][: B * N]).reshape(B, N, 3, 3).contiguous() if per_pair else T(g["R"][:N])
+    W1, W2, b2 = T(w["W1"]), T(w["W2"]), T(w["b2"])
+    tgt = ahv.ops.forward_3d2d(T(g["vol_tgt"][:B]), W1, W2, b2)
+    gen = torch.Generator().manual_seed(9)
+    gs = (torch.randn(B, N, generator=gen) * torch.logspace(-6, 0, N)[torch.randperm(N, generator=gen)][None]).to(dev)
+    scores, h1, pinv = ahv.ops.score_train(vs, tgt, R, W1, W2, b2)
+
+    leaves = [t.double().requires_grad_(True) for t in (vs, tgt, W1, W2, b2)]
+    v64, t64, w1, w2, bb = leaves
+    ref_scores = []
+    for b in range(B):
+        Rb = (R[b] if per_pair else R).double()
+        rot = oracle.rotate_volume_torch(v64[b][None].expand(N, -1, -1, -1, -1), Rb)
+        tri = torch.cat([rot.permute(0, 1, 4, 2, 3).reshape(N, 128, 8, 8), rot.permute(0, 1, 3, 2, 4).reshape(N, 128, 8, 8),
+                         rot.reshape(N, 128, 8, 8)], dim=1)
+        pre = F.conv2d(tri, w1.reshape(32, 384, 1, 1))
+        kept = (h1.reshape(B, N, 64, 32)[b].double() * pinv[b].double()).permute(0, 2, 1).reshape(N, 32, 8, 8)
+        mask = (kept > 0).double()
+        hid = pre * mask + (kept - pre * mask).detach()      # value = what the forward kept, gradient = through its mask
+        f = F.normalize(F.conv2d(hid, w2.reshape(32, 32, 1, 1), bb), p=2, dim=1).flatten(2)
+        ref_scores.append((f * t64[b][None]).sum(dim=1).mean(dim=-1))
+    ref_scores = torch.stack(ref_scores)
+    assert float((ref_scores.detach().float() - scores).abs().max()) <= 1e-3        # the kept H1 reproduces the forward's scores
+    ref = torch.autograd.grad(ref_scores, leaves, grad_outputs=gs.double())
+    for math, tol in ((ahv.MATH_FP32, 2e-5), (ahv.MATH_TC, 1e-3)):
+        got = ahv.ops.score_backward(vs, tgt, R, W1, W2, b2, gs, h1, pinv, math)
+        for name, a, r in zip(("vol_src", "tgt_feat", "W1", "W2", "b2"), got, ref):
+            err = float((a.double() - r.reshape(a.shape)).abs().max()) / float(r.abs().max())
+            assert err <= tol, (per_pair, "tcgen05" if math == ahv.MATH_TC else "fp32", name, err)
