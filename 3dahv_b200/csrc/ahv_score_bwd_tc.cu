@@ -43,10 +43,15 @@ constexpr int kAtView = 16384;     // bytes of one view of A^T: 128 rows x 64 po
 constexpr int kDh1bPitch = 1040;   // SBO of the dW1 B operand
 constexpr int kTmemCols = 512;     // dA: columns 0..191 (both lane halves); dW1^T: columns 192..287
 constexpr int kColW = 192;
+// dX (gradient w.r.t. the rotated volume) lives over the A^T operand once its MMAs are done, voxel-major with the 16
+// channels innermost: element (d, h, w, c) at d*kDxD + h*kDxH + w*kDxW + c floats.  The pitches are 4*odd mod 32, so a
+// quarter-warp that runs over h (fold of view x) or over w (views y, z) hits eight distinct 16-byte bank groups.
+constexpr int kDxW = 20, kDxH = 164, kDxD = 1312;
+static_assert(8 * kDxD * 4 <= 3 * kAtView, "dX fits over the A^T operand");
 
 struct __align__(128) BwdTcSmem {
   float vol[kLines * kC];          // halo'd source volume, channel innermost (as the fp32 scorer)
-  float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded), later dX
+  float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded)
   float h1s[kP * kH1Row];          // H1 [pos][32] fp32
   float w2s[kO * kH1Row];
   float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> counting-sort arrays of the adjoint gather
@@ -444,37 +449,45 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
         for (int oo = 0; oo < 16; ++oo) aW1[view][oo] = fmaf(__uint_as_float(r[oo]), sc, aW1[view][oo]);
       }
     }
+    float* dX = reinterpret_cast<float*>(sm.at);  // the A^T operand is dead: its MMAs have completed
     {
       uint32_t r[32];
-      // view x: dX[c, d=p, h=q, w=kk] = ...   (every element of dX written exactly once: no zeroing needed)
+      // view x: dX[d=p, h=q, w=kk, c] = ...   (every element of dX written exactly once: no zeroing needed)
       tmem_ld32(tq + hf * 96, r);
       tmem_ld_wait();
+      {
+        float* dst = dX + fp * kDxD + fq * kDxH + 4 * fg;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        float* dst = sm.rotA + (4 * fg + cc) * kRotC + fp * kRotD + fq * 8;
-        *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(r[cc * 8]) * invS, __uint_as_float(r[cc * 8 + 1]) * invS,
-                                                      __uint_as_float(r[cc * 8 + 2]) * invS, __uint_as_float(r[cc * 8 + 3]) * invS);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(__uint_as_float(r[cc * 8 + 4]) * invS, __uint_as_float(r[cc * 8 + 5]) * invS,
-                                                          __uint_as_float(r[cc * 8 + 6]) * invS, __uint_as_float(r[cc * 8 + 7]) * invS);
+        for (int kk = 0; kk < 8; ++kk)
+          *reinterpret_cast<float4*>(dst + kk * kDxW) = make_float4(__uint_as_float(r[kk]) * invS, __uint_as_float(r[8 + kk]) * invS,
+                                                                   __uint_as_float(r[16 + kk]) * invS, __uint_as_float(r[24 + kk]) * invS);
       }
       tmem_ld32(tq + hf * 96 + 32, r);  // view y, in flight across the barrier
       tmem_ld_wait();
       __syncthreads();
+      {  // dX[d=p, h=kk, w=q, c] += ...
+        float* dst = dX + fp * kDxD + fq * kDxW + 4 * fg;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {  // dX[c, d=p, h=kk, w=q] += ...
-        float* dst = sm.rotA + (4 * fg + cc) * kRotC + fp * kRotD + fq;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) dst[kk * 8] = fmaf(__uint_as_float(r[cc * 8 + kk]), invS, dst[kk * 8]);
+        for (int kk = 0; kk < 8; ++kk) {
+          float4 x = *reinterpret_cast<float4*>(dst + kk * kDxH);
+          x.x = fmaf(__uint_as_float(r[kk]), invS, x.x); x.y = fmaf(__uint_as_float(r[8 + kk]), invS, x.y);
+          x.z = fmaf(__uint_as_float(r[16 + kk]), invS, x.z); x.w = fmaf(__uint_as_float(r[24 + kk]), invS, x.w);
+          *reinterpret_cast<float4*>(dst + kk * kDxH) = x;
+        }
       }
       tmem_ld32(tq + hf * 96 + 64, r);  // view z
       tmem_ld_wait();
       tc_fence_before();                // the next item's MMAs overwrite these accumulators
       __syncthreads();
+      {  // dX[d=kk, h=p, w=q, c] += ...
+        float* dst = dX + fp * kDxH + fq * kDxW + 4 * fg;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {  // dX[c, d=kk, h=p, w=q] += ...
-        float* dst = sm.rotA + (4 * fg + cc) * kRotC + fp * 8 + fq;
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) dst[kk * kRotD] = fmaf(__uint_as_float(r[cc * 8 + kk]), invS, dst[kk * kRotD]);
+        for (int kk = 0; kk < 8; ++kk) {
+          float4 x = *reinterpret_cast<float4*>(dst + kk * kDxD);
+          x.x = fmaf(__uint_as_float(r[kk]), invS, x.x); x.y = fmaf(__uint_as_float(r[8 + kk]), invS, x.y);
+          x.z = fmaf(__uint_as_float(r[16 + kk]), invS, x.z); x.w = fmaf(__uint_as_float(r[24 + kk]), invS, x.w);
+          *reinterpret_cast<float4*>(dst + kk * kDxD) = x;
+        }
       }
     }
     __syncthreads();
@@ -494,13 +507,17 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
           const int vo = list[s0 + e];
           const float4 tp = sm.taps[vo];
           const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
-          const float* src = sm.rotA + (vo >> 6) * kRotD + (vo & 63);
+          const float* src = dX + (vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW;
 #pragma unroll
-          for (int c = 0; c < kC; ++c) aV[j][c] = fmaf(w, src[c * kRotC], aV[j][c]);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
+            aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
+            aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
+          }
         }
       }
     }
-    __syncthreads();  // rotA (dX), taps and the buckets are re-used by the next hypothesis
+    __syncthreads();  // dX (the operand buffer), taps and the buckets are re-used by the next hypothesis
   }
   flush_pair(cur_b);
   // weight gradients: one atomic per accumulator and CTA
