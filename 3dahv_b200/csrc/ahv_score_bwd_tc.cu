@@ -8,7 +8,7 @@
 //   H1 <- saved (fp16, pair-scaled) ; H2 = H1 W2^T + b2 ; F = H2/|H2| ; dH2, dT, db2, dW2, dH1   fp32 CUDA cores
 //   dA   [64 pos x 384]   = dH1 [64 x 32] . W1 [32 x 384]        tcgen05.mma  M=64 N=192 (x2)  K=32
 //   dW1^T[384    x 32 ]   = A^T [384 x 64] . dH1 [64 x 32]       tcgen05.mma  M=128 (x3 views) N=32 K=64
-//   dX = fold(dA) (three tri-plane views onto the rotated volume) ; dV_b += rotate^T(dX)   (bucketed gather)
+//   dX = fold(dA) (three tri-plane views onto the rotated volume) ; dV_b += rotate^T(dX)   (gather over a work list)
 //
 // These two contractions are 1.57 MFLOP of the ~1.8 MFLOP per item and were 36 % of the fp32 kernel's time.
 //
@@ -18,7 +18,7 @@
 //   W1^T as B of dA   [n'][o]    : SBO 512, LBO 128     packed once per CTA; rows PERMUTED n' = g*96 + view*32 + cc*8 + kk
 //                                                       (channel c = 4g + cc) so that every fold thread owns 32 columns
 //                                                       of every view
-//   A^T  as A of dW1  [m][pos]   : SBO 1024, LBO 128    m = view*128 + c*8 + kk; view y is the rotated volume as it lies
+//   A^T  as A of dW1  [m][pos]   : SBO 1024, LBO 128    (view z: 1152 / 144) m = view*128 + c*8 + kk; view y is the rotated volume as it lies
 //                                                       ([c][d][h][w]), view x its (h,w) transpose, view z its (d,h) one
 //   dH1  as B of dW1  [o][pos]   : SBO 1040, LBO 128    (pitch 1040: the eight 2-byte stores of a warp hit distinct banks)
 // Scales: A^T carries the pair's power-of-two scale of the forward (pair_inv_scale); dH1 a per-item power of two
@@ -33,6 +33,17 @@
 #include "ahv_head_fp32.cuh"
 #include "ahv_tc_ptx.cuh"
 
+// -DAHV_BWD_PHASES: thread 0 of CTA 0 accumulates clock64() per phase and prints the shares (diagnostics builds only)
+#ifdef AHV_BWD_PHASES
+#include <cstdio>
+#define AHV_PH(i)                                                           \
+  do {                                                                      \
+    if (threadIdx.x == 0) { const long long c_ = clock64(); ph_[i] += c_ - last_; last_ = c_; } \
+  } while (0)
+#else
+#define AHV_PH(i) do {} while (0)
+#endif
+
 namespace ahv {
 
 using namespace tc;
@@ -40,6 +51,8 @@ using namespace tc;
 namespace {
 
 constexpr int kAtView = 16384;     // bytes of one view of A^T: 128 rows x 64 positions fp16
+constexpr int kAtZLbo = 144, kAtZSbo = 8 * kAtZLbo;   // view z: K-chunk pitch 144 B (its stores run over h: distinct banks)
+constexpr int kAtBytes = 2 * kAtView + 16 * kAtZSbo;
 constexpr int kDh1bPitch = 1040;   // SBO of the dW1 B operand
 constexpr int kTmemCols = 512;     // dA: columns 0..191 (both lane halves); dW1^T: columns 192..287
 constexpr int kColW = 192;
@@ -47,16 +60,16 @@ constexpr int kColW = 192;
 // channels innermost: element (d, h, w, c) at d*kDxD + h*kDxH + w*kDxW + c floats.  The pitches are 4*odd mod 32, so a
 // quarter-warp that runs over h (fold of view x) or over w (views y, z) hits eight distinct 16-byte bank groups.
 constexpr int kDxW = 20, kDxH = 164, kDxD = 1312;
-static_assert(8 * kDxD * 4 <= 3 * kAtView, "dX fits over the A^T operand");
+static_assert(8 * kDxD * 4 <= kAtBytes, "dX fits over the A^T operand");
 
 struct __align__(128) BwdTcSmem {
   float vol[kLines * kC];          // halo'd source volume, channel innermost (as the fp32 scorer)
-  float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded)
+  float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded); dead after the operands -> work-list entries
   float h1s[kP * kH1Row];          // H1 [pos][32] fp32
   float w2s[kO * kH1Row];
-  float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> counting-sort arrays of the adjoint gather
+  float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> counters of the adjoint's work list
   float4 taps[kVox];
-  unsigned char at[3 * kAtView];   // A^T operand
+  unsigned char at[kAtBytes];      // A^T operand
   unsigned char w1t[kK * kO * 2];  // W1^T operand (permuted rows)
   unsigned char dh1a[kP * kO * 2];
   unsigned char dh1b[4 * kDh1bPitch];
@@ -67,6 +80,7 @@ struct __align__(128) BwdTcSmem {
   uint32_t tmem_slot;
 };
 static_assert(sizeof(BwdTcSmem) <= 232448, "shared memory budget");
+static_assert(kVox * 8 * 8 <= kC * kRotC * 4 && 2 * kVox * 4 <= kP * kH1Row * 4, "work list fits the dead buffers");
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -109,24 +123,24 @@ __device__ __forceinline__ void gather_rotated(BwdTcSmem& sm, const float* R) {
   }
 }
 
+// output voxel (z*64 + y*8 + x) a thread lists for the adjoint: lane bits -> x2 x1 y2 y1 z2, warp bits and j -> the rest
+__device__ __forceinline__ int out_voxel(int t, int j) {
+  const int x = ((t & 3) << 1) | ((t >> 5) & 1), y = (((t >> 2) & 3) << 1) | ((t >> 6) & 1);
+  const int z = (((t >> 4) & 1) << 2) | (((t >> 7) & 1) << 1) | j;
+  return z * 64 + y * 8 + x;
+}
+
 // rotated volume (fp32) -> the three views of the A^T operand (fp16, pair scale `sb`)
 __device__ __forceinline__ void pack_views(BwdTcSmem& sm, float sb) {
   const int t = threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {  // view y: [c][d][h][w] as it lies; lanes run over (d, h): contiguous 16 B stores
+  for (int i = 0; i < 4; ++i) {  // views y and z: one conversion, two conflict-free 16 B stores; lanes run over (d, h)
     const int task = t + 256 * i, c = task >> 6, d = (task >> 3) & 7, h = task & 7;
     const float* src = sm.rotA + c * kRotC + d * kRotD + h * 8;
     const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-    *reinterpret_cast<uint4*>(sm.at + kAtView + c * 1024 + d * 128 + h * 16) =
-        make_uint4(pack_h2(a.x * sb, a.y * sb), pack_h2(a.z * sb, a.w * sb), pack_h2(b.x * sb, b.y * sb), pack_h2(b.z * sb, b.w * sb));
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {  // view z: [c][h][d][w]; lanes run over (h, d)
-    const int task = t + 256 * i, c = task >> 6, h = (task >> 3) & 7, d = task & 7;
-    const float* src = sm.rotA + c * kRotC + d * kRotD + h * 8;
-    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-    *reinterpret_cast<uint4*>(sm.at + 2 * kAtView + c * 1024 + h * 128 + d * 16) =
-        make_uint4(pack_h2(a.x * sb, a.y * sb), pack_h2(a.z * sb, a.w * sb), pack_h2(b.x * sb, b.y * sb), pack_h2(b.z * sb, b.w * sb));
+    const uint4 pk = make_uint4(pack_h2(a.x * sb, a.y * sb), pack_h2(a.z * sb, a.w * sb), pack_h2(b.x * sb, b.y * sb), pack_h2(b.z * sb, b.w * sb));
+    *reinterpret_cast<uint4*>(sm.at + kAtView + c * 1024 + d * 128 + h * 16) = pk;           // [c][d][h][w] as it lies
+    *reinterpret_cast<uint4*>(sm.at + 2 * kAtView + c * kAtZSbo + h * kAtZLbo + d * 16) = pk;  // [c][h][d][w], h pitch 144 B
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {  // view x: [c][d][w][h]; lanes run over (d, w), eight h gathered per thread
@@ -228,6 +242,11 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   int cur_b = -1;
   float pinv = 1.0f;
   uint32_t phase = 0;
+  float r_next = 0.0f;
+  if (t < 9) r_next = __ldg(R + (r_per_pair ? (size_t)lo : (size_t)(lo % N)) * 9 + t);
+#ifdef AHV_BWD_PHASES
+  long long ph_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, last_ = clock64();
+#endif
   for (int64_t it = lo; it < hi; ++it) {
     const int b = (int)(it / N);
     const int64_t n = it - (int64_t)b * N;
@@ -240,7 +259,10 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       pinv = __ldg(pair_inv + b);
       cur_b = b;
     }
-    if (t < 9) sm.Rcur[t] = R[(r_per_pair ? (size_t)it : (size_t)n) * 9 + t];
+    if (t < 9) {   // this item's rotation was fetched one item ago; fetch the next one's
+      sm.Rcur[t] = r_next;
+      if (it + 1 < hi) r_next = __ldg(R + (r_per_pair ? (size_t)(it + 1) : (size_t)((it + 1) % N)) * 9 + t);
+    }
     // H1 of this item as the forward kept it (fp16, pair-scaled): in flight during the gather
     const uint4 hq = __ldg(reinterpret_cast<const uint4*>(h1_saved + ((size_t)it * kP + pos) * kO + cg2 * 8));
     const float g64 = grad_scores[it] * (1.0f / 64.0f);  // d mean over the 64 positions
@@ -248,6 +270,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     float Rr[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) Rr[e] = sm.Rcur[e];
+    AHV_PH(0);
 
     // ---------------- X = rotate(V_b, R), H1 ----------------
     gather_rotated(sm, Rr);
@@ -262,9 +285,11 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       }
     }
     __syncthreads();
+    AHV_PH(1);
 
     // ---------------- A^T operand; conv2, normalise, dH2 ----------------
     pack_views(sm, 1.0f / pinv);
+    AHV_PH(2);
     float v[8];
     {
       float h[kO];
@@ -309,6 +334,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
+    AHV_PH(3);
 
     // ---------------- dW2 += dH2^T H1 ; dH1 = (dH2 W2) * [H1 > 0] ----------------
     {
@@ -347,6 +373,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       if (lane == 0) sm.red[warp] = mx;
     }
     __syncthreads();
+    AHV_PH(4);
 
     // ---------------- dH1 -> fp16 operands under the item's power-of-two scale ----------------
     float invS;
@@ -367,6 +394,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     }
     fence_proxy_async();  // A^T, dH1 operands: generic-proxy stores -> async proxy
     __syncthreads();
+    AHV_PH(5);
 
     // ---------------- the two contractions on the tensor core ----------------
     if (warp == 0) {
@@ -381,34 +409,57 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       for (int view = 0; view < 3; ++view)  // dW1^T: rows = (c, kk) of the view, K = the 64 positions
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          umma_f16(tmem + kColW + view * 32, smem_desc(at_s + view * kAtView + j * 256, 128, 1024),
+          umma_f16(tmem + kColW + view * 32,
+                   view < 2 ? smem_desc(at_s + view * kAtView + j * 256, 128, 1024)
+                            : smem_desc(at_s + 2 * kAtView + j * 2 * kAtZLbo, kAtZLbo, kAtZSbo),
                    smem_desc(dh1b_s + j * 256, 128, kDh1bPitch), idW, j);
       umma_commit(bar_s);
       __syncwarp();
     }
 
-    // ---------------- meanwhile: bucket the 512 output voxels by the corner line of their taps ----------------
-    int* cnt = reinterpret_cast<int*>(sm.dh2);            // [1000] voxels per corner line, then running fill offset
-    int* start = cnt + kLines;                            // [1000] exclusive prefix sum
-    unsigned short* list = reinterpret_cast<unsigned short*>(start + kLines);  // [512] output voxels sorted by line
+    // ---------------- meanwhile: the adjoint's work list ----------------
+    // Output voxel vo feeds the 8 input voxels of its tap with weight w.  Turned round: every INPUT voxel gets the list
+    // of its (vo, w) contributions (counting sort over the <= 4096 contributions that land inside the volume; the
+    // rotated-volume buffer is dead since the operands were packed and holds the entries), so the adjoint below is one
+    // flat loop per input voxel - valid for any matrix R.
+    int* cnt = reinterpret_cast<int*>(sm.dh2);       // [512] contributions per input voxel
+    int* start = cnt + kVox;                         // [512] exclusive prefix sum
+    uint2* ent = reinterpret_cast<uint2*>(sm.rotA);  // [<= 4096] (offset of dX[vo], weight), grouped by input voxel
     {
-      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;
+      cnt[t] = 0;
+      cnt[t + 256] = 0;
       __syncthreads();
-      int myline[2];
+      // The thread's two output voxels are chosen two apart in x and y and four in z across the lanes of a warp, so
+      // that the taps of one warp's voxels rarely meet in the same counter (adjacent voxels share half their taps and
+      // would serialise the atomics).
+      int tgt0[2];
+      uint32_t inside[2], rank[2][4];
+      float fx[2], fy[2], fz[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        myline[j] = __float_as_int(sm.taps[t + 256 * j].x);
-        atomicAdd(&cnt[myline[j]], 1);
+        const int vo = out_voxel(t, j);
+        const float4 tp = sm.taps[vo];
+        const int line = __float_as_int(tp.x);   // ((z0+1)*10 + (y0+1))*10 + (x0+1), corner in [-1, 7]^3
+        const int zl = line / (kHalo * kHalo), rl = line - zl * (kHalo * kHalo), yl = rl / kHalo, xl = rl - yl * kHalo;
+        const int x0 = xl - 1, y0 = yl - 1, z0 = zl - 1;
+        fx[j] = tp.y; fy[j] = tp.z; fz[j] = tp.w;
+        tgt0[j] = z0 * 64 + y0 * 8 + x0;
+        uint32_t m = 0;
+        rank[j][0] = rank[j][1] = rank[j][2] = rank[j][3] = 0;
+#pragma unroll
+        for (int dlt = 0; dlt < 8; ++dlt) {
+          const int x = x0 + (dlt & 1), y = y0 + ((dlt >> 1) & 1), z = z0 + (dlt >> 2);
+          if ((unsigned)x < 8u && (unsigned)y < 8u && (unsigned)z < 8u) {
+            m |= 1u << dlt;   // the atomic's return value is this contribution's place in its list (<= 511: 16 bits)
+            rank[j][dlt >> 1] |= (uint32_t)atomicAdd(&cnt[tgt0[j] + (dlt >> 2) * 64 + ((dlt >> 1) & 1) * 8 + (dlt & 1)], 1) << (16 * (dlt & 1));
+          }
+        }
+        inside[j] = m;
       }
       __syncthreads();
-      {  // exclusive scan of 1000 counters: 4 per thread (250 threads), warp scan, then the 8 warp totals
-        const int i0 = 4 * t;
-        int c4[4] = {0, 0, 0, 0};
-        if (i0 < kLines) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) c4[e] = cnt[i0 + e];
-        }
-        const int local = c4[0] + c4[1] + c4[2] + c4[3];
+      {  // exclusive scan of the 512 counters: 2 per thread, warp scan, then the 8 warp totals
+        const int c0 = cnt[2 * t], c1 = cnt[2 * t + 1];
+        const int local = c0 + c1;
         int incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -420,22 +471,29 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
         __syncthreads();
         int basep = incl - local;
         for (int w = 0; w < warp; ++w) basep += wtot[w];
-        if (i0 < kLines) {
-          start[i0] = basep;
-          start[i0 + 1] = basep + c4[0];
-          start[i0 + 2] = basep + c4[0] + c4[1];
-          start[i0 + 3] = basep + c4[0] + c4[1] + c4[2];
-        }
+        start[2 * t] = basep;
+        start[2 * t + 1] = basep + c0;
       }
       __syncthreads();
-      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;   // re-used as the fill cursor
-      __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 2; ++j) list[start[myline[j]] + atomicAdd(&cnt[myline[j]], 1)] = (unsigned short)(t + 256 * j);
+      for (int j = 0; j < 2; ++j) {
+        const int vo = out_voxel(t, j);
+        const uint32_t off = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW);
+#pragma unroll
+        for (int dlt = 0; dlt < 8; ++dlt)
+          if ((inside[j] >> dlt) & 1u) {
+            const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
+            const float w = (dx ? fx[j] : 1.0f - fx[j]) * (dy ? fy[j] : 1.0f - fy[j]) * (dz ? fz[j] : 1.0f - fz[j]);
+            const int v = tgt0[j] + dz * 64 + dy * 8 + dx;
+            ent[start[v] + ((rank[j][dlt >> 1] >> (16 * (dlt & 1))) & 0xffffu)] = make_uint2(off, __float_as_uint(w));
+          }
+      }
     }
 
+    AHV_PH(6);
     // ---------------- accumulators: dW1^T -> registers, dA -> dX (fold of the three views) ----------------
     mbar_wait(bar_s, phase);
+    AHV_PH(7);
     phase ^= 1;
     tc_fence_after();
     {
@@ -491,34 +549,40 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       }
     }
     __syncthreads();
+    AHV_PH(8);
 
-    // ---------------- dV_b += rotate^T(dX): adjoint of utils.py:113-131 as a gather over the buckets ----------------
+    // ---------------- dV_b += rotate^T(dX): adjoint of utils.py:113-131, one flat list per input voxel ----------------
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int vi = t + 256 * j;
-      const int z = vi >> 6, y = (vi >> 3) & 7, x = vi & 7;
-      const int lin = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
-#pragma unroll 1
-      for (int dlt = 0; dlt < 8; ++dlt) {
-        const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
-        const int cell = lin - (dz * kHalo * kHalo + dy * kHalo + dx);   // corner line of the voxels that tap v at (dx,dy,dz)
-        const int nn = cnt[cell], s0 = start[cell];                      // cell >= 0: lin >= 111
-        for (int e = 0; e < nn; ++e) {
-          const int vo = list[s0 + e];
-          const float4 tp = sm.taps[vo];
-          const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
-          const float* src = dX + (vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW;
+      const int nn = cnt[vi];
+      const uint2* e = ent + start[vi];
+#pragma unroll 2
+      for (int i = 0; i < nn; ++i) {
+        const uint2 en = e[i];
+        const float w = __uint_as_float(en.y);
+        const float* src = dX + en.x;
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
-            aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
-            aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
-          }
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
+          aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
+          aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
         }
       }
     }
-    __syncthreads();  // dX (the operand buffer), taps and the buckets are re-used by the next hypothesis
+    __syncthreads();  // dX (the operand buffer), taps and the work list are re-used by the next hypothesis
+    AHV_PH(9);
   }
+#ifdef AHV_BWD_PHASES
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long tot = 0;
+    for (int i = 0; i < 10; ++i) tot += ph_[i];
+    printf("bwd_tc phases, cycles per item (CTA 0, %lld items): loop+R %lld | gather+H1 %lld | pack views %lld | conv2+dH2 %lld | dW2+dH1 %lld | "
+           "operands %lld | MMA issue+sort %lld | MMA wait %lld | dW1 read+fold %lld | adjoint %lld | total %lld\n",
+           (long long)(hi - lo), ph_[0] / (hi - lo), ph_[1] / (hi - lo), ph_[2] / (hi - lo), ph_[3] / (hi - lo), ph_[4] / (hi - lo),
+           ph_[5] / (hi - lo), ph_[6] / (hi - lo), ph_[7] / (hi - lo), ph_[8] / (hi - lo), ph_[9] / (hi - lo), tot / (hi - lo));
+  }
+#endif
   flush_pair(cur_b);
   // weight gradients: one atomic per accumulator and CTA
 #pragma unroll

@@ -5,6 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 ahv = importlib.import_module("3dahv_b200")
+if os.environ.get("AHV_VARIANT_LIB"):   # scripts-only: time an experiment / diagnostics build (the product reads no environment)
+    ahv._lib.LIB_PATH = os.path.abspath(os.environ["AHV_VARIANT_LIB"])
 dev = torch.device("cuda", 0)
 B, N = int(os.environ.get("AHV_B", "12")), int(os.environ.get("AHV_N", "9000"))
 chunk = int(os.environ.get("AHV_CHUNK", "1024"))
