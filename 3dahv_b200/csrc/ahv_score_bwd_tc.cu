@@ -56,6 +56,7 @@ constexpr int kAtBytes = 2 * kAtView + 16 * kAtZSbo;
 constexpr int kDh1bPitch = 1040;   // SBO of the dW1 B operand
 constexpr int kTmemCols = 512;     // dA: columns 0..191 (both lane halves); dW1^T: columns 192..287
 constexpr int kColW = 192;
+constexpr int kColH2 = 288, kColDh1 = 304;   // conv2 and dH1 accumulators: 16 columns each, both lane halves
 // dX (gradient w.r.t. the rotated volume) lives over the A^T operand once its MMAs are done, voxel-major with the 16
 // channels innermost: element (d, h, w, c) at d*kDxD + h*kDxH + w*kDxW + c floats.  The pitches are 4*odd mod 32, so a
 // quarter-warp that runs over h (fold of view x) or over w (views y, z) hits eight distinct 16-byte bank groups.
@@ -66,17 +67,21 @@ struct __align__(128) BwdTcSmem {
   float vol[kLines * kC];          // halo'd source volume, channel innermost (as the fp32 scorer)
   float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded); dead after the operands -> work-list entries
   float h1s[kP * kH1Row];          // H1 [pos][32] fp32
-  float w2s[kO * kH1Row];
   float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> counters of the adjoint's work list
   float4 taps[kVox];
   unsigned char at[kAtBytes];      // A^T operand
   unsigned char w1t[kK * kO * 2];  // W1^T operand (permuted rows)
   unsigned char dh1a[kP * kO * 2];
+  unsigned char h1a[kP * kO * 2];  // H1 as the forward kept it: A of conv2
+  unsigned char dh2a[kP * kO * 2]; // dH2 (row-scaled): A of dH1
+  unsigned char w2b[kO * kO * 2];  // W2 as B of conv2 [o][i]
+  unsigned char w2tb[kO * kO * 2]; // W2^T as B of dH1 [i][o]
+  float2 part[kP * 4];             // per (position, channel block): partial |H2|^2 and <H2, T>
   unsigned char dh1b[4 * kDh1bPitch];
   float base[8];
   float red[8];
   float Rcur[12];
-  unsigned long long bar;
+  unsigned long long bar[3];       // contractions | conv2 | dH1
   uint32_t tmem_slot;
 };
 static_assert(sizeof(BwdTcSmem) <= 232448, "shared memory budget");
@@ -165,12 +170,14 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
   if (lo >= hi) return;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const uint32_t bar_s = smem_u32(&sm.bar);
+  const uint32_t bar_s = smem_u32(&sm.bar[0]);
 
   // ---- set-up: W2 (fp32), W1^T operand (fp16, permuted rows), base coordinates, barrier, TMEM ----
   for (int i = t; i < kO * kO; i += kThreads) {
     const int o = i / kO, c = i % kO;
-    sm.w2s[((o % 8) * 4 + o / 8) * kH1Row + c] = W2[i];
+    const __half w = __float2half_rn(__ldg(W2 + i));
+    *reinterpret_cast<__half*>(sm.w2b + (o >> 3) * 512 + (c >> 3) * 128 + (o & 7) * 16 + (c & 7) * 2) = w;   // rows o, K = i
+    *reinterpret_cast<__half*>(sm.w2tb + (c >> 3) * 512 + (o >> 3) * 128 + (c & 7) * 16 + (o & 7) * 2) = w;  // rows i, K = o
   }
   for (int i = t; i < kO * kK; i += kThreads) {
     const int o = i / kK, k = i - o * kK;  // coalesced read of W1[o][k]
@@ -182,6 +189,8 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(bar_s, 1);
+      mbar_init(bar_s + 8, 1);
+      mbar_init(bar_s + 16, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -193,12 +202,14 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
   const uint32_t at_s = smem_u32(sm.at), w1t_s = smem_u32(sm.w1t), dh1a_s = smem_u32(sm.dh1a), dh1b_s = smem_u32(sm.dh1b);
-  constexpr uint32_t idA = instr_desc(64, kColW), idW = instr_desc(128, 32);
+  const uint32_t h1a_s = smem_u32(sm.h1a), dh2a_s = smem_u32(sm.dh2a), w2b_s = smem_u32(sm.w2b), w2tb_s = smem_u32(sm.w2tb);
+  constexpr uint32_t idA = instr_desc(64, kColW), idW = instr_desc(128, 32), idC = instr_desc(64, 16);
 
-  // conv2 / normalise mapping: thread = (position, 8 channels cg2*8 ..)
-  const int pos = t >> 2, cg2 = t & 3;
   // accumulator read-out mapping: TMEM quadrant of this warp, column half
   const int qd = warp & 3, hf = warp >> 2;
+  // head mapping: thread = (position, 8 channels cg2*8 ..) as the M=64 accumulators present them: the two lane halves
+  // of a quadrant hold two 16-column accumulators of the same 16 rows, warps w and w+4 split each into 8 + 8 columns
+  const int pos = 16 * qd + (lane & 15), cg2 = (lane >> 4) * 2 + hf;
   const uint32_t tq = tmem + ((uint32_t)(32 * qd) << 16);
   // fold mapping: lanes 0-15 / 16-31 hold the two M=64 accumulators: position 16 qd + lane%16, channel group g
   const int fpos = 16 * qd + (lane & 15), fp = fpos >> 3, fq = fpos & 7, fg = (lane >> 4) * 2 + hf;
@@ -266,15 +277,17 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     // H1 of this item as the forward kept it (fp16, pair-scaled): in flight during the gather
     const uint4 hq = __ldg(reinterpret_cast<const uint4*>(h1_saved + ((size_t)it * kP + pos) * kO + cg2 * 8));
     const float g64 = grad_scores[it] * (1.0f / 64.0f);  // d mean over the 64 positions
+    float inv_s2 = 1.0f;
     __syncthreads();
     float Rr[9];
 #pragma unroll
     for (int e = 0; e < 9; ++e) Rr[e] = sm.Rcur[e];
     AHV_PH(0);
 
-    // ---------------- X = rotate(V_b, R), H1 ----------------
+    // ---------------- X = rotate(V_b, R); H1 as conv2's operand and in fp32 ----------------
     gather_rotated(sm, Rr);
     {
+      *reinterpret_cast<uint4*>(sm.h1a + (pos >> 3) * 512 + cg2 * 128 + (pos & 7) * 16) = hq;
       const __half2* hp = reinterpret_cast<const __half2*>(&hq);
       float* dst = sm.h1s + pos * kH1Row + cg2 * 8;
 #pragma unroll
@@ -284,38 +297,44 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
         dst[2 * e + 1] = f2.y * pinv;
       }
     }
+    fence_proxy_async();
     __syncthreads();
     AHV_PH(1);
 
-    // ---------------- A^T operand; conv2, normalise, dH2 ----------------
+    // ---------------- conv2 on the tensor core (the forward's own arithmetic), A^T operand meanwhile ----------------
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half)  // output channels 16 half .. +15 -> lanes 16 half .. of every quadrant
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          umma_f16(tmem + kColH2 + ((uint32_t)(16 * half) << 16), smem_desc(h1a_s + j * 256, 128, 512),
+                   smem_desc(w2b_s + half * 1024 + j * 256, 128, 512), idC, j);
+      umma_commit(bar_s + 8);
+      __syncwarp();
+    }
     pack_views(sm, 1.0f / pinv);
     AHV_PH(2);
+    mbar_wait(bar_s + 8, phase);
+    tc_fence_after();
     float v[8];
     {
-      float h[kO];
+      uint32_t r8[8];
+      tmem_ld8(tq + kColH2 + hf * 8, r8);
+      tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 x = *reinterpret_cast<const float4*>(sm.h1s + pos * kH1Row + 4 * i);
-        h[4 * i] = x.x; h[4 * i + 1] = x.y; h[4 * i + 2] = x.z; h[4 * i + 3] = x.w;
-      }
-#pragma unroll
-      for (int oo = 0; oo < 8; ++oo) {
-        const float* wr = sm.w2s + (oo * 4 + cg2) * kH1Row;
-        float a = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 w = *reinterpret_cast<const float4*>(wr + 4 * i);
-          a = fmaf(w.x, h[4 * i], a); a = fmaf(w.y, h[4 * i + 1], a);
-          a = fmaf(w.z, h[4 * i + 2], a); a = fmaf(w.w, h[4 * i + 3], a);
-        }
-        v[oo] = a + b2r[oo];
-      }
+      for (int oo = 0; oo < 8; ++oo) v[oo] = fmaf(__uint_as_float(r8[oo]), pinv, b2r[oo]);  // undo the pair scale, add bias
     }
     float ss = 0.0f, ft = 0.0f;
 #pragma unroll
     for (int oo = 0; oo < 8; ++oo) { ss = fmaf(v[oo], v[oo], ss); ft = fmaf(v[oo], tg[oo], ft); }
-    ss = quad_sum(ss);
-    ft = quad_sum(ft);
+    sm.part[pos * 4 + cg2] = make_float2(ss, ft);
+    __syncthreads();
+    {
+      const float4 p01 = *reinterpret_cast<const float4*>(&sm.part[pos * 4]), p23 = *reinterpret_cast<const float4*>(&sm.part[pos * 4 + 2]);
+      ss = (p01.x + p01.z) + (p23.x + p23.z);   // fixed order: the four threads of a position agree bit for bit
+      ft = (p01.y + p01.w) + (p23.y + p23.w);
+    }
     {
       // F = v / max(|v|, eps) (modules/modules.py:122).  d<F,T>/dv = (T - F <F,T>) / |v| above the clamp, T / eps below
       const float nraw = sqrtf(ss), nr = fmaxf(nraw, 1e-12f), inv = 1.0f / nr;
@@ -332,11 +351,34 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       float* dst = sm.dh2 + pos * kH1Row + cg2 * 8;
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      // dH2 as the A operand of dH1 = dH2 W2, scaled per ROW (the thread that reads the row back undoes it): every
+      // |dH2| of this position is below 2 |g/64| / |v|, which the power of two maps into [2^13, 2^14)
+      const float bnd = 2.0f * fabsf(g64) * inv;
+      int e = ((__float_as_int(bnd) >> 23) & 0xff) - 127;
+      e = bnd > 0.0f ? min(max(e, -100), 100) : 13;
+      const float S2 = __int_as_float((127 + 13 - e) << 23);
+      inv_s2 = __int_as_float((127 - 13 + e) << 23);
+      *reinterpret_cast<uint4*>(sm.dh2a + (pos >> 3) * 512 + cg2 * 128 + (pos & 7) * 16) =
+          make_uint4(pack_h2(v[0] * S2, v[1] * S2), pack_h2(v[2] * S2, v[3] * S2), pack_h2(v[4] * S2, v[5] * S2),
+                     pack_h2(v[6] * S2, v[7] * S2));
     }
+    fence_proxy_async();
+    tc_fence_before();  // conv2's accumulator has been read
     __syncthreads();
     AHV_PH(3);
 
-    // ---------------- dW2 += dH2^T H1 ; dH1 = (dH2 W2) * [H1 > 0] ----------------
+    // ---------------- dH1 = (dH2 W2) * [H1 > 0] on the tensor core; dW2 += dH2^T H1 meanwhile (fp32) ----------------
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          umma_f16(tmem + kColDh1 + ((uint32_t)(16 * half) << 16), smem_desc(dh2a_s + j * 256, 128, 512),
+                   smem_desc(w2tb_s + half * 1024 + j * 256, 128, 512), idC, j);
+      umma_commit(bar_s + 16);
+      __syncwarp();
+    }
     {
       const int o = t >> 3, i0 = (t & 7) * 4;
 #pragma unroll 8
@@ -349,29 +391,23 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     }
     float dh1[8];
     {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dh1[j] = 0.0f;
-#pragma unroll 4
-      for (int o = 0; o < kO; ++o) {
-        const float d = sm.dh2[pos * kH1Row + o];
-        const float* wr = sm.w2s + ((o % 8) * 4 + o / 8) * kH1Row + cg2 * 8;  // W2[o][cg2*8 ..]
-        const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
-        dh1[0] = fmaf(d, w0.x, dh1[0]); dh1[1] = fmaf(d, w0.y, dh1[1]);
-        dh1[2] = fmaf(d, w0.z, dh1[2]); dh1[3] = fmaf(d, w0.w, dh1[3]);
-        dh1[4] = fmaf(d, w1.x, dh1[4]); dh1[5] = fmaf(d, w1.y, dh1[5]);
-        dh1[6] = fmaf(d, w1.z, dh1[6]); dh1[7] = fmaf(d, w1.w, dh1[7]);
-      }
+      mbar_wait(bar_s + 16, phase);
+      tc_fence_after();
+      uint32_t r8[8];
+      tmem_ld8(tq + kColDh1 + hf * 8, r8);
+      tmem_ld_wait();
       const float* hp = sm.h1s + pos * kH1Row + cg2 * 8;  // ReLU mask (modules/modules.py:68)
       float mx = 0.0f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dh1[j] = hp[j] > 0.0f ? dh1[j] : 0.0f;
+        dh1[j] = hp[j] > 0.0f ? __uint_as_float(r8[j]) * inv_s2 : 0.0f;
         mx = fmaxf(mx, fabsf(dh1[j]));
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (lane == 0) sm.red[warp] = mx;
     }
+    tc_fence_before();
     __syncthreads();
     AHV_PH(4);
 
