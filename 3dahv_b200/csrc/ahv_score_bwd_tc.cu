@@ -1,35 +1,46 @@
-// Fused backward of the verification scores with the two large contractions on tcgen05 (training variant,
+// Fused backward of the verification scores with its contractions on tcgen05 (training variant,
 // SURVEY.md §8a-8 / §8f-3; the reference: autograd through modules/model.py:43-63).
 //
 // Same chain as ahv_score_bwd.cu (which stays the exact fp32 form) for a training step that kept conv1's ReLU'd
-// output H1 in the forward (ahv_score_train).  Per (pair, hypothesis) item:
+// output H1 in the forward (ahv_score_train).  One CTA = 256 threads per SM, a contiguous range of (pair, hypothesis)
+// items; per item:
 //
-//   X = rotate(V_b, R_n)                       fp32 gather in shared memory (taps recorded for the adjoint)
-//   H1 <- saved (fp16, pair-scaled) ; H2 = H1 W2^T + b2 ; F = H2/|H2| ; dH2, dT, db2, dW2, dH1   fp32 CUDA cores
-//   dA   [64 pos x 384]   = dH1 [64 x 32] . W1 [32 x 384]        tcgen05.mma  M=64 N=192 (x2)  K=32
-//   dW1^T[384    x 32 ]   = A^T [384 x 64] . dH1 [64 x 32]       tcgen05.mma  M=128 (x3 views) N=32 K=64
+//   X = rotate(V_b, R_n)                         fp32 gather in shared memory (taps recorded for the adjoint)
+//   H2 = H1 W2^T + b2   [64 pos x 32]            tcgen05.mma  M=64 N=16 (x2)  K=32   H1 = the fp16 rows the forward kept
+//   F = H2/|H2| ; dH2 ; dT += (g/64) F ; db2     fp32, thread = (position, 8 channels) as the accumulator presents them
+//   dH1 = (dH2 W2) * [H1 > 0]                    tcgen05.mma  M=64 N=16 (x2)  K=32   dH2 scaled per row (position)
+//   dW2 += dH2^T H1                              fp32 FFMA, in the shadow of the dH1 MMAs
+//   dA   [64 pos x 384]  = dH1 [64 x 32] . W1    tcgen05.mma  M=64 N=192 (x2) K=32
+//   dW1^T[384    x 32 ]  = A^T [384 x 64] . dH1  tcgen05.mma  M=128 (x3 views) N=32 K=64
 //   dX = fold(dA) (three tri-plane views onto the rotated volume) ; dV_b += rotate^T(dX)   (gather over a work list)
 //
-// These two contractions are 1.57 MFLOP of the ~1.8 MFLOP per item and were 36 % of the fp32 kernel's time.
+// 1.7 of the ~1.8 MFLOP per item are tensor-core work; the fp32 kernel spent 62 % of its time on them.
 //
 // Operands (fp16, fp32 accumulation in TMEM), all K-major SWIZZLE_NONE core-matrix layouts
 // (element (row r, k) at (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2):
-//   dH1  as A of dA   [pos][o]   : SBO 512, LBO 128     written by the thread that owns (pos, 8 channels): one 16 B store
-//   W1^T as B of dA   [n'][o]    : SBO 512, LBO 128     packed once per CTA; rows PERMUTED n' = g*96 + view*32 + cc*8 + kk
-//                                                       (channel c = 4g + cc) so that every fold thread owns 32 columns
-//                                                       of every view
-//   A^T  as A of dW1  [m][pos]   : SBO 1024, LBO 128    (view z: 1152 / 144) m = view*128 + c*8 + kk; view y is the rotated volume as it lies
-//                                                       ([c][d][h][w]), view x its (h,w) transpose, view z its (d,h) one
-//   dH1  as B of dW1  [o][pos]   : SBO 1040, LBO 128    (pitch 1040: the eight 2-byte stores of a warp hit distinct banks)
-// Scales: A^T carries the pair's power-of-two scale of the forward (pair_inv_scale); dH1 a per-item power of two
-// chosen from max |dH1| (2^13 <= max < 2^14), both undone in fp32 when the accumulators are read.
-// dA lands in TMEM as two M=64 accumulators side by side in the lanes (lanes 0-15 / 16-31 of every 32-lane quadrant),
-// so all 32 lanes of a warp fold; dW1^T is read every item into per-thread fp32 accumulators (48 per thread),
-// which keeps the accumulation across items in fp32 and lets the scale differ per item.
+//   H1, dH2, dH1 as A [pos][ch] : SBO 512, LBO 128     written by the thread that owns (pos, 8 channels): one 16 B store
+//   W2 / W2^T     as B [32][32] : SBO 512, LBO 128     packed once per CTA
+//   W1^T as B of dA   [n'][o]   : SBO 512, LBO 128     packed once per CTA; rows PERMUTED n' = g*96 + view*32 + cc*8 + kk
+//                                                      (channel c = 4g + cc) so that every fold thread owns 32 columns
+//                                                      of every view
+//   A^T  as A of dW1  [m][pos]  : SBO 1024, LBO 128    (view z: 1152 / 144) m = view*128 + c*8 + kk; view y is the rotated
+//                                                      volume as it lies ([c][d][h][w]), view x its (h,w) transpose, view z
+//                                                      its (d,h) one
+//   dH1  as B of dW1  [o][pos]  : SBO 1040, LBO 128    (pitch 1040: the eight 2-byte stores of a warp hit distinct banks)
+// Scales (powers of two, undone in fp32 when the accumulators are read): H1 and A^T carry the pair's scale of the
+// forward (pair_inv_scale); dH2 a per-position scale from the bound 2 |g/64| / |H2|; dH1 a per-item scale from
+// max |dH1| (2^13 <= max < 2^14).
+// The M=64 accumulators come in pairs side by side in the lanes (lanes 0-15 / 16-31 of every 32-lane quadrant hold two
+// column blocks of the same 16 rows), so all 32 lanes of a warp read; dW1^T is read every item into per-thread fp32
+// accumulators (48 per thread), which keeps the accumulation across items in fp32 and lets the scale differ per item.
+// dX lies voxel-major, channels innermost, over the dead A^T operand; the adjoint walks, per input voxel, a row of up
+// to 16 (offset, weight) contributions built in one pass of shared-memory atomics (exact fallback for matrices that are
+// not rotations and crowd more contributions onto a voxel).
 //
 // Gradients are those of the function the tensor-core forward evaluated (its ReLU mask), with fp16 operand rounding:
-// 4e-4 of the maximum for gradients that do not pass the mask, a few per cent at the voxels a flipped mask element
-// feeds (see training.verification_scores).
+// checked to 1e-3 of each gradient's maximum against fp64 autograd of that function (tests/test_gpu_training.py).
+#include <cstddef>
+
 #include "ahv_head_fp32.cuh"
 #include "ahv_tc_ptx.cuh"
 
@@ -66,8 +77,8 @@ static_assert(8 * kDxD * 4 <= kAtBytes, "dX fits over the A^T operand");
 struct __align__(128) BwdTcSmem {
   float vol[kLines * kC];          // halo'd source volume, channel innermost (as the fp32 scorer)
   float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded); dead after the operands -> work-list entries
+  float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> tail of the work list, its counters  (must follow rotA)
   float h1s[kP * kH1Row];          // H1 [pos][32] fp32
-  float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> counters of the adjoint's work list
   float4 taps[kVox];
   unsigned char at[kAtBytes];      // A^T operand
   unsigned char w1t[kK * kO * 2];  // W1^T operand (permuted rows)
@@ -83,9 +94,15 @@ struct __align__(128) BwdTcSmem {
   float Rcur[12];
   unsigned long long bar[3];       // contractions | conv2 | dH1
   uint32_t tmem_slot;
+  int overflow;                    // some input voxel has more than kListCap contributions (degenerate R): exact path
 };
 static_assert(sizeof(BwdTcSmem) <= 232448, "shared memory budget");
-static_assert(kVox * 8 * 8 <= kC * kRotC * 4 && 2 * kVox * 4 <= kP * kH1Row * 4, "work list fits the dead buffers");
+// adjoint work list: per input voxel a row of kListCap 4-byte entries (dX offset / 4 | weight as unorm16 << 16), row pitch
+// 20 words so that eight consecutive rows start in distinct 16-byte bank groups.  It covers the rotated-volume buffer and
+// the first 4 KB of the dH2 buffer behind it; the counters follow.
+constexpr int kListCap = 16, kListPitch = 20, kListTail = (kVox * kListPitch * 4 - kC * kRotC * 4) / 4;   // floats of dh2 it takes
+static_assert(kListTail >= 0 && (kListTail + 2 * kVox) <= kP * kH1Row && kVox * 8 * 8 <= kC * kRotC * 4, "work list fits the dead buffers");
+static_assert(offsetof(BwdTcSmem, dh2) == offsetof(BwdTcSmem, rotA) + kC * kRotC * 4, "dh2 follows rotA");
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -455,75 +472,45 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
 
     // ---------------- meanwhile: the adjoint's work list ----------------
     // Output voxel vo feeds the 8 input voxels of its tap with weight w.  Turned round: every INPUT voxel gets the list
-    // of its (vo, w) contributions (counting sort over the <= 4096 contributions that land inside the volume; the
-    // rotated-volume buffer is dead since the operands were packed and holds the entries), so the adjoint below is one
-    // flat loop per input voxel - valid for any matrix R.
-    int* cnt = reinterpret_cast<int*>(sm.dh2);       // [512] contributions per input voxel
-    int* start = cnt + kVox;                         // [512] exclusive prefix sum
-    uint2* ent = reinterpret_cast<uint2*>(sm.rotA);  // [<= 4096] (offset of dX[vo], weight), grouped by input voxel
+    // of its (vo, w) contributions, so that the adjoint below is one flat loop per input voxel.  A rigid rotation puts
+    // about 8 (at most ~12) contributions on a voxel: the list is a fixed row of kListCap entries per voxel, filled in
+    // ONE pass (the counter's atomic returns the place in the row).  A matrix that is not a rotation can exceed the
+    // row: then the item takes the exact path below (counting sort with prefix sums) - valid for any matrix R.
+    int* cnt = reinterpret_cast<int*>(sm.dh2 + kListTail);   // [512] contributions per input voxel
+    int* start = cnt + kVox;                                 // [512] exclusive prefix sum (exact path)
+    uint32_t* ent16 = reinterpret_cast<uint32_t*>(sm.rotA);  // [512][kListPitch]
+    uint2* ent = reinterpret_cast<uint2*>(sm.rotA);          // exact path: [<= 4096] (offset of dX[vo], weight)
     {
       cnt[t] = 0;
       cnt[t + 256] = 0;
+      if (t == 0) sm.overflow = 0;
       __syncthreads();
       // The thread's two output voxels are chosen two apart in x and y and four in z across the lanes of a warp, so
       // that the taps of one warp's voxels rarely meet in the same counter (adjacent voxels share half their taps and
       // would serialise the atomics).
-      int tgt0[2];
-      uint32_t inside[2], rank[2][4];
-      float fx[2], fy[2], fz[2];
+      bool over = false;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int vo = out_voxel(t, j);
+        const uint32_t off4 = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW) >> 2;
         const float4 tp = sm.taps[vo];
         const int line = __float_as_int(tp.x);   // ((z0+1)*10 + (y0+1))*10 + (x0+1), corner in [-1, 7]^3
         const int zl = line / (kHalo * kHalo), rl = line - zl * (kHalo * kHalo), yl = rl / kHalo, xl = rl - yl * kHalo;
         const int x0 = xl - 1, y0 = yl - 1, z0 = zl - 1;
-        fx[j] = tp.y; fy[j] = tp.z; fz[j] = tp.w;
-        tgt0[j] = z0 * 64 + y0 * 8 + x0;
-        uint32_t m = 0;
-        rank[j][0] = rank[j][1] = rank[j][2] = rank[j][3] = 0;
+        const int tgt0 = z0 * 64 + y0 * 8 + x0;
 #pragma unroll
         for (int dlt = 0; dlt < 8; ++dlt) {
-          const int x = x0 + (dlt & 1), y = y0 + ((dlt >> 1) & 1), z = z0 + (dlt >> 2);
-          if ((unsigned)x < 8u && (unsigned)y < 8u && (unsigned)z < 8u) {
-            m |= 1u << dlt;   // the atomic's return value is this contribution's place in its list (<= 511: 16 bits)
-            rank[j][dlt >> 1] |= (uint32_t)atomicAdd(&cnt[tgt0[j] + (dlt >> 2) * 64 + ((dlt >> 1) & 1) * 8 + (dlt & 1)], 1) << (16 * (dlt & 1));
+          const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
+          if ((unsigned)(x0 + dx) < 8u && (unsigned)(y0 + dy) < 8u && (unsigned)(z0 + dz) < 8u) {
+            const int v = tgt0 + dz * 64 + dy * 8 + dx;
+            const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
+            const int r = atomicAdd(&cnt[v], 1);
+            if (r < kListCap) ent16[v * kListPitch + r] = off4 | (__float2uint_rn(w * 65535.0f) << 16);
+            else over = true;
           }
         }
-        inside[j] = m;
       }
-      __syncthreads();
-      {  // exclusive scan of the 512 counters: 2 per thread, warp scan, then the 8 warp totals
-        const int c0 = cnt[2 * t], c1 = cnt[2 * t + 1];
-        const int local = c0 + c1;
-        int incl = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += up;
-        }
-        int* wtot = reinterpret_cast<int*>(sm.red);
-        if (lane == 31) wtot[warp] = incl;
-        __syncthreads();
-        int basep = incl - local;
-        for (int w = 0; w < warp; ++w) basep += wtot[w];
-        start[2 * t] = basep;
-        start[2 * t + 1] = basep + c0;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int vo = out_voxel(t, j);
-        const uint32_t off = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW);
-#pragma unroll
-        for (int dlt = 0; dlt < 8; ++dlt)
-          if ((inside[j] >> dlt) & 1u) {
-            const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
-            const float w = (dx ? fx[j] : 1.0f - fx[j]) * (dy ? fy[j] : 1.0f - fy[j]) * (dz ? fz[j] : 1.0f - fz[j]);
-            const int v = tgt0[j] + dz * 64 + dy * 8 + dx;
-            ent[start[v] + ((rank[j][dlt >> 1] >> (16 * (dlt & 1))) & 0xffffu)] = make_uint2(off, __float_as_uint(w));
-          }
-      }
+      if (over) sm.overflow = 1;
     }
 
     AHV_PH(6);
@@ -588,21 +575,122 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     AHV_PH(8);
 
     // ---------------- dV_b += rotate^T(dX): adjoint of utils.py:113-131, one flat list per input voxel ----------------
+    if (sm.overflow == 0) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int vi = t + 256 * j;
-      const int nn = cnt[vi];
-      const uint2* e = ent + start[vi];
+      for (int j = 0; j < 2; ++j) {
+        const int vi = t + 256 * j;
+        const int nn = cnt[vi];
+        int nmax = nn;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        uint32_t en[kListCap];
+        {
+          const uint4* row = reinterpret_cast<const uint4*>(ent16 + vi * kListPitch);
+#pragma unroll
+          for (int q = 0; q < kListCap / 4; ++q) {
+            const uint4 x = row[q];
+            en[4 * q] = x.x; en[4 * q + 1] = x.y; en[4 * q + 2] = x.z; en[4 * q + 3] = x.w;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kListCap; ++i) {
+          if (i >= nmax) break;   // warp-uniform
+          if (i < nn) {
+            const float w = (float)(en[i] >> 16) * (1.0f / 65535.0f);
+            const float* src = dX + ((en[i] & 0xffffu) << 2);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
+              aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
+              aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
+            }
+          }
+        }
+      }
+    } else {
+      // exact path (some voxel has more than kListCap contributions): counting sort with prefix sums, 8-byte entries
+      __syncthreads();
+      {
+        cnt[t] = 0;
+        cnt[t + 256] = 0;
+        __syncthreads();
+        // The thread's two output voxels are chosen two apart in x and y and four in z across the lanes of a warp, so
+        // that the taps of one warp's voxels rarely meet in the same counter (adjacent voxels share half their taps and
+        // would serialise the atomics).
+        int tgt0[2];
+        uint32_t inside[2], rank[2][4];
+        float fx[2], fy[2], fz[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int vo = out_voxel(t, j);
+          const float4 tp = sm.taps[vo];
+          const int line = __float_as_int(tp.x);   // ((z0+1)*10 + (y0+1))*10 + (x0+1), corner in [-1, 7]^3
+          const int zl = line / (kHalo * kHalo), rl = line - zl * (kHalo * kHalo), yl = rl / kHalo, xl = rl - yl * kHalo;
+          const int x0 = xl - 1, y0 = yl - 1, z0 = zl - 1;
+          fx[j] = tp.y; fy[j] = tp.z; fz[j] = tp.w;
+          tgt0[j] = z0 * 64 + y0 * 8 + x0;
+          uint32_t m = 0;
+          rank[j][0] = rank[j][1] = rank[j][2] = rank[j][3] = 0;
+#pragma unroll
+          for (int dlt = 0; dlt < 8; ++dlt) {
+            const int x = x0 + (dlt & 1), y = y0 + ((dlt >> 1) & 1), z = z0 + (dlt >> 2);
+            if ((unsigned)x < 8u && (unsigned)y < 8u && (unsigned)z < 8u) {
+              m |= 1u << dlt;   // the atomic's return value is this contribution's place in its list (<= 511: 16 bits)
+              rank[j][dlt >> 1] |= (uint32_t)atomicAdd(&cnt[tgt0[j] + (dlt >> 2) * 64 + ((dlt >> 1) & 1) * 8 + (dlt & 1)], 1) << (16 * (dlt & 1));
+            }
+          }
+          inside[j] = m;
+        }
+        __syncthreads();
+        {  // exclusive scan of the 512 counters: 2 per thread, warp scan, then the 8 warp totals
+          const int c0 = cnt[2 * t], c1 = cnt[2 * t + 1];
+          const int local = c0 + c1;
+          int incl = local;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+          }
+          int* wtot = reinterpret_cast<int*>(sm.red);
+          if (lane == 31) wtot[warp] = incl;
+          __syncthreads();
+          int basep = incl - local;
+          for (int w = 0; w < warp; ++w) basep += wtot[w];
+          start[2 * t] = basep;
+          start[2 * t + 1] = basep + c0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int vo = out_voxel(t, j);
+          const uint32_t off = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW);
+#pragma unroll
+          for (int dlt = 0; dlt < 8; ++dlt)
+            if ((inside[j] >> dlt) & 1u) {
+              const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
+              const float w = (dx ? fx[j] : 1.0f - fx[j]) * (dy ? fy[j] : 1.0f - fy[j]) * (dz ? fz[j] : 1.0f - fz[j]);
+              const int v = tgt0[j] + dz * 64 + dy * 8 + dx;
+              ent[start[v] + ((rank[j][dlt >> 1] >> (16 * (dlt & 1))) & 0xffffu)] = make_uint2(off, __float_as_uint(w));
+            }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int vi = t + 256 * j;
+        const int nn = cnt[vi];
+        const uint2* e = ent + start[vi];
 #pragma unroll 2
-      for (int i = 0; i < nn; ++i) {
-        const uint2 en = e[i];
-        const float w = __uint_as_float(en.y);
-        const float* src = dX + en.x;
+        for (int i = 0; i < nn; ++i) {
+          const uint2 en = e[i];
+          const float w = __uint_as_float(en.y);
+          const float* src = dX + en.x;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
-          aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
-          aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
+            aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
+            aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
+          }
         }
       }
     }
@@ -613,6 +701,8 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     long long tot = 0;
     for (int i = 0; i < 10; ++i) tot += ph_[i];
+    printf("sort detail: issue+zero+count %lld | scan %lld | fill = rest\n", ph_[10] / (hi - lo), ph_[11] / (hi - lo));
+    ph_[6] += ph_[10] + ph_[11];
     printf("bwd_tc phases, cycles per item (CTA 0, %lld items): loop+R %lld | gather+H1 %lld | pack views %lld | conv2+dH2 %lld | dW2+dH1 %lld | "
            "operands %lld | MMA issue+sort %lld | MMA wait %lld | dW1 read+fold %lld | adjoint %lld | total %lld\n",
            (long long)(hi - lo), ph_[0] / (hi - lo), ph_[1] / (hi - lo), ph_[2] / (hi - lo), ph_[3] / (hi - lo), ph_[4] / (hi - lo),

@@ -272,14 +272,16 @@ def test_saved_activation_backward_matches_recomputation(ahv, golden):
             assert worst <= 2e-3, (B, N, per_pair, "tc vs fp32 contractions", name, worst)
 
 
-@pytest.mark.parametrize("per_pair", [False, True])
-def test_saved_activation_backward_is_the_gradient_of_the_function_that_ran(ahv, golden, oracle, per_pair):
+@pytest.mark.parametrize("per_pair,shrink", [(False, 1.0), (True, 1.0), (False, 0.35)])
+def test_saved_activation_backward_is_the_gradient_of_the_function_that_ran(ahv, golden, oracle, per_pair, shrink):
     """Exact check of the saved-activation backward (both contraction forms) against fp64 autograd through the oracle's
     restatement of the chain (utils.py:113-131, modules/modules.py:112-124, modules/model.py:53-56) in which conv1's
     output takes the VALUE the forward kept and the ReLU MASK of that value - the function the training forward
     evaluated.  Upstream gradients span six decades (the per-item power-of-two operand scale), the second volume
-    carries an outlier voxel (pair scale).  fp32 contractions: 2e-5 of each gradient's maximum; tcgen05 contractions
-    (fp16 operands): 1e-3."""
+    carries an outlier voxel (pair scale).  `shrink` < 1 multiplies the matrices by 0.35: no longer rotations, the
+    samples crowd into the middle of the volume and one input voxel collects dozens of contributions (the adjoint's
+    exact path; utils.py:113-131 accepts any matrix).  fp32 contractions: 2e-5 of each gradient's maximum; tcgen05
+    contractions (fp16 operands): 1e-3."""
     import torch.nn.functional as F
 
     dev = torch.device("cuda", 0)
@@ -288,7 +290,8 @@ def test_saved_activation_backward_is_the_gradient_of_the_function_that_ran(ahv,
     B, N = 2, 150
     vs = T(g["vol_src"][:B]).clone()
     vs[1, 3, 2, 5, 1] = 4.0e3
-    R = T(g["R"][: B * N]).reshape(B, N, 3, 3).contiguous() if per_pair else T(g["R"][:N])
+    R = (T(g["R"][: B * N]).reshape(B, N, 3, 3) if per_pair else T(g["R"][:N])) * shrink
+    R = R.contiguous()
     W1, W2, b2 = T(w["W1"]), T(w["W2"]), T(w["b2"])
     tgt = ahv.ops.forward_3d2d(T(g["vol_tgt"][:B]), W1, W2, b2)
     gen = torch.Generator().manual_seed(9)
@@ -316,4 +319,4 @@ def test_saved_activation_backward_is_the_gradient_of_the_function_that_ran(ahv,
         got = ahv.ops.score_backward(vs, tgt, R, W1, W2, b2, gs, h1, pinv, math)
         for name, a, r in zip(("vol_src", "tgt_feat", "W1", "W2", "b2"), got, ref):
             err = float((a.double() - r.reshape(a.shape)).abs().max()) / float(r.abs().max())
-            assert err <= tol, (per_pair, "tcgen05" if math == ahv.MATH_TC else "fp32", name, err)
+            assert err <= tol, (per_pair, shrink, "tcgen05" if math == ahv.MATH_TC else "fp32", name, err)
