@@ -42,6 +42,10 @@ class EstimatorBase(_Base):
         self.feature_aligner = Feature_Aligner(in_channel=768, mid_channel=256, out_channel=32, n_heads=4, depth=4)
         self.step_outputs = []
         self._verifier = None
+        # training: keep conv1's output in the forward and run the backward's contractions on tcgen05 (2.7x faster
+        # step; gradients of the function the tensor-core forward evaluated - 3dahv_b200.training.verification_scores).
+        # Off by default: the default backward matches the reference's fp32 autograd to 1e-4.
+        self.fast_backward = bool(cfg.get("TRAIN", {}).get("FAST_BACKWARD", False)) if isinstance(cfg, dict) else False
 
     if pl is None:
         def log(self, *args, **kwargs):  # Lightning's logger hook; a no-op without Lightning
@@ -98,13 +102,14 @@ class EstimatorBase(_Base):
 
     def infoNCE_loss(self, img_feat_1, img_feat_2, sampled_R, gt_delta_R):
         """modules/model.py:43-63 — per-pair hypothesis sets [B,N,3,3] with the ground truth at index 0.
-        Differentiable: the scores come from the fused kernel, their backward pass recomputes chunk by
-        chunk (3dahv_b200.training); gradients reach the volumes (hence the lifting and the backbone)
-        and the verification head.  Returns the per-sample loss [B]."""
+        Differentiable: the scores come from the fused kernel, their backward pass is the fused backward kernel
+        (3dahv_b200.training; `self.fast_backward` / cfg["TRAIN"]["FAST_BACKWARD"] selects the saved-activation
+        tensor-core form); gradients reach the volumes (hence the lifting and the backbone) and the verification
+        head.  Returns the per-sample loss [B]."""
         head = self.feature_aligner.feature_embedding_2d
         tr = _ahv().training
         scores = tr.verification_scores(img_feat_1, img_feat_2, sampled_R.contiguous(), head[0].weight, head[2].weight,
-                                        head[2].bias)
+                                        head[2].bias, save_activations=self.fast_backward)
         return tr.infonce_loss(scores, sampled_R, gt_delta_R, self.cfg["DATA"]["ACC_THR"])
 
     def _sample_training_rotations(self, gt_R):

@@ -143,3 +143,14 @@ def test_training_step_backpropagates_to_backbone_and_head(ahv):
     loss.backward()
     assert torch.isfinite(loss) and c.feature_aligner.feature_embedding_2d[0].weight.grad.abs().sum() > 0
     assert len(c.configure_optimizers()[0][0].param_groups) == 2
+    # cfg["TRAIN"]["FAST_BACKWARD"]: same step through the saved-activation tensor-core backward - same loss (the forward
+    # arithmetic is the same kernel's), head gradients within the mode's stated accuracy
+    grads_exact = [p.grad.clone() for p in (head[0].weight, head[2].weight, head[2].bias)]
+    m.fast_backward = True
+    opt.zero_grad()
+    torch.manual_seed(1)
+    loss1 = m.training_step(batch, 0)
+    loss1.backward()
+    assert torch.allclose(loss1.detach(), loss0.detach(), rtol=1e-5, atol=1e-6)
+    for p, g0 in zip((head[0].weight, head[2].weight, head[2].bias), grads_exact):
+        assert float((p.grad - g0).norm() / g0.norm()) <= 5e-2
