@@ -425,7 +425,7 @@ def run_ours(args):
                 raise   # ranks out of lockstep cannot continue safely
 
     # ------------------------------------------------ informational sections on rank 0 (no exchange below this line)
-    other, latency, eager = {}, {}, None
+    other, latency, eager, training = {}, {}, None, {}
     smem_peak_gbs = None
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     if rank == 0:
@@ -445,6 +445,35 @@ def run_ours(args):
                 other["fp32_volumes_tc_f16gather"] = _rate(vs, ahv.MATH_TC_F16GATHER)
             except Exception as e:  # noqa: BLE001
                 other["error"] = repr(e)
+
+        # training variant: scores + InfoNCE forward/backward on the reference's training shape
+        # (12 pairs x 9 000 per-pair hypotheses, ground truth first), p50 of 7 steps after 2 warm-ups, three backward forms
+        if not strong_headline and world == 1:
+            try:
+                Bt, Nt = 12, 9000
+                tW1, tW2, tb2, tvs, tvt, _ = synthetic_inputs(torch, Bt, 16)
+                leaves = [x.to(dev).requires_grad_(True) for x in (tvs, tvt, tW1, tW2, tb2)]
+                gt_t = ahv.so3.sample_rotations(Bt, 1, 0, dev)
+                Rs_t = torch.cat([gt_t[:, None], ahv.so3.sample_rotations(Bt * (Nt - 1), 2, 0, dev).reshape(Bt, Nt - 1, 3, 3)], 1).contiguous()
+                for name, kw in (("exact_fp32_backward", {}), ("saved_h1_fp32_backward", {"save_activations": True, "tc_backward": False}),
+                                 ("saved_h1_tcgen05_backward", {"save_activations": True})):
+                    ms = []
+                    for i in range(9):
+                        for x in leaves:
+                            x.grad = None
+                        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        ea.record()
+                        sc = ahv.training.verification_scores(leaves[0], leaves[1], Rs_t, *leaves[2:], **kw)
+                        ahv.training.infonce_loss(sc, Rs_t, gt_t, acc_thr_deg=15.0).mean().backward()
+                        eb.record()
+                        torch.cuda.synchronize()
+                        if i >= 2:
+                            ms.append(ea.elapsed_time(eb))
+                    training[name] = {"ms_per_step_p50": sorted(ms)[len(ms) // 2]}
+                training["shape"] = f"{Bt} pairs x {Nt} per-pair hypotheses; scores + InfoNCE + gradients to volumes and head weights"
+                del leaves, Rs_t, sc
+            except Exception as e:  # noqa: BLE001
+                training["error"] = repr(e)
 
         # measured shared-memory read peak (no such figure in MEASURED_PEAKS.json)
         import ctypes
@@ -511,6 +540,7 @@ def run_ours(args):
             "clocks": clocks,
             "latency_p50_per_pair": latency,
             "other_modes_hyp_pairs_per_s": other,
+            "training_step": training,
             "e2e": {"value": units_per_step * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "api": ("ahv_predict_host_ex (C ABI, pinned host buffers, caller-owned session)" +

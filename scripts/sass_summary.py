@@ -32,7 +32,7 @@ arch = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=Tru
 print("# ELF images:", ", ".join(sorted(set(re.findall(r"sm_\d+a?", arch)))))
 for k, c in kernels.items():
     name = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip()
-    name = re.sub(r"\(.*", "", name)
+    name = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", ""))
     print(f"\n{name}  [{c['TOTAL']} instructions]")
     items = [(op, n) for op, n in sorted(c.items()) if op != "TOTAL"]
     print("  " + "  ".join(f"{op}={n}" for op, n in items))
