@@ -67,7 +67,10 @@ constexpr int kAtBytes = 2 * kAtView + 16 * kAtZSbo;
 constexpr int kDh1bPitch = 1040;   // SBO of the dW1 B operand
 constexpr int kTmemCols = 512;     // dA: columns 0..191 (both lane halves); dW1^T: columns 192..287
 constexpr int kColW = 192;
-constexpr int kColH2 = 288, kColDh1 = 304;   // conv2 and dH1 accumulators: 16 columns each, both lane halves
+// rotated volume [c][d][h][w]: channel pitch 584 = 8 mod 32, so the gather's four lanes of a voxel (channels j, j+4, j+8, j+12)
+// and its eight voxels along w store to 32 distinct banks
+constexpr int kRc = kS * kRotD + 8;
+constexpr int kColH2 = 288, kColDh1 = 304, kColW2 = 320;   // conv2, dH1, dW2 accumulators: 16 columns each, both lane halves
 // dX (gradient w.r.t. the rotated volume) lives over the A^T operand once its MMAs are done, voxel-major with the 16
 // channels innermost: element (d, h, w, c) at d*kDxD + h*kDxH + w*kDxW + c floats.  The pitches are 4*odd mod 32, so a
 // quarter-warp that runs over h (fold of view x) or over w (views y, z) hits eight distinct 16-byte bank groups.
@@ -76,9 +79,8 @@ static_assert(8 * kDxD * 4 <= kAtBytes, "dX fits over the A^T operand");
 
 struct __align__(128) BwdTcSmem {
   float vol[kLines * kC];          // halo'd source volume, channel innermost (as the fp32 scorer)
-  float rotA[kC * kRotC];          // rotated volume X [c][d][h][w] (padded); dead after the operands -> work-list entries
-  float dh2[kP * kH1Row];          // dL/dH2; dead after dH1 -> tail of the work list, its counters  (must follow rotA)
-  float h1s[kP * kH1Row];          // H1 [pos][32] fp32
+  float rotA[kC * kRc];          // rotated volume X [c][d][h][w] (padded); dead after the operands -> work-list entries
+  float dh2[kP * kH1Row];          // scratch behind rotA: tail of the work list, its counters; db2 reduction at the end
   float4 taps[kVox];
   unsigned char at[kAtBytes];      // A^T operand
   unsigned char w1t[kK * kO * 2];  // W1^T operand (permuted rows)
@@ -89,6 +91,8 @@ struct __align__(128) BwdTcSmem {
   unsigned char w2tb[kO * kO * 2]; // W2^T as B of dH1 [i][o]
   float2 part[kP * 4];             // per (position, channel block): partial |H2|^2 and <H2, T>
   unsigned char dh1b[4 * kDh1bPitch];
+  unsigned char h1t[4 * kDh1bPitch];   // H1^T  [i][pos]: B of dW2
+  unsigned char dh2t[8 * kDh1bPitch];  // dH2^T [o][pos]: A of dW2 (M=64: the upper 32 rows are never written, their products never read)
   float base[8];
   float red[8];
   float Rcur[12];
@@ -100,13 +104,25 @@ static_assert(sizeof(BwdTcSmem) <= 232448, "shared memory budget");
 // adjoint work list: per input voxel a row of kListCap 4-byte entries (dX offset / 4 | weight as unorm16 << 16), row pitch
 // 20 words so that eight consecutive rows start in distinct 16-byte bank groups.  It covers the rotated-volume buffer and
 // the first 4 KB of the dH2 buffer behind it; the counters follow.
-constexpr int kListCap = 16, kListPitch = 20, kListTail = (kVox * kListPitch * 4 - kC * kRotC * 4) / 4;   // floats of dh2 it takes
-static_assert(kListTail >= 0 && (kListTail + 2 * kVox) <= kP * kH1Row && kVox * 8 * 8 <= kC * kRotC * 4, "work list fits the dead buffers");
-static_assert(offsetof(BwdTcSmem, dh2) == offsetof(BwdTcSmem, rotA) + kC * kRotC * 4, "dh2 follows rotA");
+constexpr int kListCap = 16, kListPitch = 20, kListTail = (kVox * kListPitch * 4 - kC * kRc * 4) / 4;   // floats of dh2 it takes
+static_assert(kListTail >= 0 && (kListTail + 2 * kVox) <= kP * kH1Row && kVox * 8 * 8 <= kC * kRc * 4, "work list fits the dead buffers");
+static_assert(offsetof(BwdTcSmem, dh2) == offsetof(BwdTcSmem, rotA) + kC * kRc * 4, "dh2 follows rotA");
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// vol_g [16][512] NCDHW -> halo'd lines, the 16 channels of a line in the order 0 4 8 12 | 1 5 9 13 | 2 6 10 14 | 3 7 11 15
+__device__ __forceinline__ void stage_volume_interleaved(float* __restrict__ vol, const float* __restrict__ vol_g) {
+  for (int i = threadIdx.x; i < kLines * kC; i += kThreads) vol[i] = 0.0f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < kC * kVox; i += kThreads) {
+    const int c = i >> 9, v = i & 511;
+    const int z = v >> 6, y = (v >> 3) & 7, x = v & 7;
+    const int line = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
+    vol[line * kC + (c & 3) * 4 + (c >> 2)] = __ldg(vol_g + i);
+  }
 }
 
 // trilinear gather of one hypothesis into rotA, 4 lanes per output voxel (as gather_hypothesis of the fp32 scorer,
@@ -140,8 +156,8 @@ __device__ __forceinline__ void gather_rotated(BwdTcSmem& sm, const float* R) {
         acc.x = fmaf(wb, b.x, acc.x); acc.y = fmaf(wb, b.y, acc.y);
         acc.z = fmaf(wb, b.z, acc.z); acc.w = fmaf(wb, b.w, acc.w);
       }
-    float* dst = sm.rotA + (j * 4) * kRotC + d * kRotD + h * 8 + w;
-    dst[0] = acc.x; dst[kRotC] = acc.y; dst[2 * kRotC] = acc.z; dst[3 * kRotC] = acc.w;
+    float* dst = sm.rotA + j * kRc + d * kRotD + h * 8 + w;   // the staged volume interleaves the channels: lane j holds j, j+4, j+8, j+12
+    dst[0] = acc.x; dst[4 * kRc] = acc.y; dst[8 * kRc] = acc.z; dst[12 * kRc] = acc.w;
   }
 }
 
@@ -158,7 +174,7 @@ __device__ __forceinline__ void pack_views(BwdTcSmem& sm, float sb) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {  // views y and z: one conversion, two conflict-free 16 B stores; lanes run over (d, h)
     const int task = t + 256 * i, c = task >> 6, d = (task >> 3) & 7, h = task & 7;
-    const float* src = sm.rotA + c * kRotC + d * kRotD + h * 8;
+    const float* src = sm.rotA + c * kRc + d * kRotD + h * 8;
     const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
     const uint4 pk = make_uint4(pack_h2(a.x * sb, a.y * sb), pack_h2(a.z * sb, a.w * sb), pack_h2(b.x * sb, b.y * sb), pack_h2(b.z * sb, b.w * sb));
     *reinterpret_cast<uint4*>(sm.at + kAtView + c * 1024 + d * 128 + h * 16) = pk;           // [c][d][h][w] as it lies
@@ -167,7 +183,7 @@ __device__ __forceinline__ void pack_views(BwdTcSmem& sm, float sb) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {  // view x: [c][d][w][h]; lanes run over (d, w), eight h gathered per thread
     const int task = t + 256 * i, c = task >> 6, d = (task >> 3) & 7, w = task & 7;
-    const float* src = sm.rotA + c * kRotC + d * kRotD + w;
+    const float* src = sm.rotA + c * kRc + d * kRotD + w;
     *reinterpret_cast<uint4*>(sm.at + c * 1024 + d * 128 + w * 16) =
         make_uint4(pack_h2(src[0] * sb, src[8] * sb), pack_h2(src[16] * sb, src[24] * sb), pack_h2(src[32] * sb, src[40] * sb),
                    pack_h2(src[48] * sb, src[56] * sb));
@@ -219,6 +235,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
   const uint32_t at_s = smem_u32(sm.at), w1t_s = smem_u32(sm.w1t), dh1a_s = smem_u32(sm.dh1a), dh1b_s = smem_u32(sm.dh1b);
+  const uint32_t h1t_s = smem_u32(sm.h1t), dh2t_s = smem_u32(sm.dh2t);
   const uint32_t h1a_s = smem_u32(sm.h1a), dh2a_s = smem_u32(sm.dh2a), w2b_s = smem_u32(sm.w2b), w2tb_s = smem_u32(sm.w2tb);
   constexpr uint32_t idA = instr_desc(64, kColW), idW = instr_desc(128, 32), idC = instr_desc(64, 16);
 
@@ -235,7 +252,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
 #pragma unroll
   for (int oo = 0; oo < 8; ++oo) b2r[oo] = b2[cg2 * 8 + oo];
   float aW1[3][16];  // dW1[o = 16 hf + oo][k = view*128 + 32 qd + lane]
-  float aW2[4];      // dW2[o = t >> 3][i = (t & 7) * 4 ..]
+  float aW2[8];      // dW2[o = 16 qd + lane % 16][i = 16 (lane / 16) + 8 hf ..]  (quadrants 0 and 1 only)
   float ab2[8];      // db2[cg2*8 + oo] (this thread's position only)
   float aT[8];       // dT_b[cg2*8 + oo][pos]
   float aV[2][kC];   // dV_b[c][voxel t + 256 j]
@@ -244,7 +261,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
 #pragma unroll
     for (int oo = 0; oo < 16; ++oo) aW1[v][oo] = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) aW2[i] = 0.0f;
+  for (int i = 0; i < 8; ++i) aW2[i] = 0.0f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) ab2[i] = aT[i] = 0.0f;
 #pragma unroll
@@ -267,6 +284,41 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       }
   };
 
+  // ---- the adjoint's work list ----
+  // Output voxel vo feeds the 8 input voxels of its tap with weight w.  Turned round: every INPUT voxel gets the list
+  // of its (vo, w) contributions, so that the adjoint is one flat loop per input voxel.  A rigid rotation puts about 8
+  // (at most ~12) contributions on a voxel: the list is a fixed row of kListCap entries per voxel, filled in ONE pass
+  // (the counter's atomic returns the place in the row) while the tensor core works.  A matrix that is not a rotation
+  // can exceed the row: then the item takes the exact path (counting sort with prefix sums) - valid for any matrix R.
+  int* cnt = reinterpret_cast<int*>(sm.dh2 + kListTail);   // [512] contributions per input voxel
+  int* start = cnt + kVox;                                 // [512] exclusive prefix sum (exact path)
+  uint32_t* ent16 = reinterpret_cast<uint32_t*>(sm.rotA);  // [512][kListPitch]
+  uint2* ent = reinterpret_cast<uint2*>(sm.rotA);          // exact path: [<= 4096] (offset of dX[vo], weight)
+  // The thread's two output voxels (one per pass) are chosen two apart in x and y and four in z across the lanes of a
+  // warp, so that the taps of one warp's voxels rarely meet in the same counter.
+  auto list_pass = [&](int j) {
+    const int vo = out_voxel(t, j);
+    const uint32_t off4 = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW) >> 2;
+    const float4 tp = sm.taps[vo];
+    const int line = __float_as_int(tp.x);   // ((z0+1)*10 + (y0+1))*10 + (x0+1), corner in [-1, 7]^3
+    const int zl = line / (kHalo * kHalo), rl = line - zl * (kHalo * kHalo), yl = rl / kHalo, xl = rl - yl * kHalo;
+    const int x0 = xl - 1, y0 = yl - 1, z0 = zl - 1;
+    const int tgt0 = z0 * 64 + y0 * 8 + x0;
+    bool over = false;
+#pragma unroll
+    for (int dlt = 0; dlt < 8; ++dlt) {
+      const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
+      if ((unsigned)(x0 + dx) < 8u && (unsigned)(y0 + dy) < 8u && (unsigned)(z0 + dz) < 8u) {
+        const int v = tgt0 + dz * 64 + dy * 8 + dx;
+        const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
+        const int r = atomicAdd(&cnt[v], 1);
+        if (r < kListCap) ent16[v * kListPitch + r] = off4 | (__float2uint_rn(w * 65535.0f) << 16);
+        else over = true;
+      }
+    }
+    if (over) sm.overflow = 1;
+  };
+
   int cur_b = -1;
   float pinv = 1.0f;
   uint32_t phase = 0;
@@ -281,12 +333,15 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     if (b != cur_b) {
       if (cur_b >= 0) flush_pair(cur_b);
       __syncthreads();
-      stage_volume<float>(sm.vol, vol_src + (size_t)b * kC * kVox);
+      stage_volume_interleaved(sm.vol, vol_src + (size_t)b * kC * kVox);
 #pragma unroll
       for (int oo = 0; oo < 8; ++oo) tg[oo] = tgt_feat[((size_t)b * kO + cg2 * 8 + oo) * kP + pos];
       pinv = __ldg(pair_inv + b);
       cur_b = b;
     }
+    cnt[t] = 0;   // the work list's counters (the previous item's adjoint is behind a barrier)
+    cnt[t + 256] = 0;
+    if (t == 0) sm.overflow = 0;
     if (t < 9) {   // this item's rotation was fetched one item ago; fetch the next one's
       sm.Rcur[t] = r_next;
       if (it + 1 < hi) r_next = __ldg(R + (r_per_pair ? (size_t)(it + 1) : (size_t)((it + 1) % N)) * 9 + t);
@@ -301,18 +356,14 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     for (int e = 0; e < 9; ++e) Rr[e] = sm.Rcur[e];
     AHV_PH(0);
 
-    // ---------------- X = rotate(V_b, R); H1 as conv2's operand and in fp32 ----------------
+    // ---------------- X = rotate(V_b, R); H1 as the operand of conv2 and of dW2 ----------------
     gather_rotated(sm, Rr);
     {
       *reinterpret_cast<uint4*>(sm.h1a + (pos >> 3) * 512 + cg2 * 128 + (pos & 7) * 16) = hq;
-      const __half2* hp = reinterpret_cast<const __half2*>(&hq);
-      float* dst = sm.h1s + pos * kH1Row + cg2 * 8;
+      const __half* hp = reinterpret_cast<const __half*>(&hq);   // and transposed, as the B operand of dW2
+      unsigned char* bb = sm.h1t + cg2 * kDh1bPitch + (pos >> 3) * 128 + (pos & 7) * 2;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f2 = __half22float2(hp[e]);
-        dst[2 * e] = f2.x * pinv;
-        dst[2 * e + 1] = f2.y * pinv;
-      }
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<__half*>(bb + j * 16) = hp[j];
     }
     fence_proxy_async();
     __syncthreads();
@@ -365,26 +416,37 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
         ab2[oo] += d2;
         v[oo] = d2;
       }
-      float* dst = sm.dh2 + pos * kH1Row + cg2 * 8;
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-      // dH2 as the A operand of dH1 = dH2 W2, scaled per ROW (the thread that reads the row back undoes it): every
-      // |dH2| of this position is below 2 |g/64| / |v|, which the power of two maps into [2^13, 2^14)
-      const float bnd = 2.0f * fabsf(g64) * inv;
+      // dH2 as fp16 operands - rows = positions for dH1 = dH2 W2, rows = channels for dW2 = dH2^T H1 - under ONE power of
+      // two per item (dW2 contracts over the positions): every |dH2| is below 2 |g/64| / min_p |H2_p|, which the scale maps
+      // into [2^13, 2^14).  The smallest |H2_p|^2 comes from the partial sums every thread can see (fixed order: all
+      // warps derive the same scale).
+      float ssmin;
+      {
+        const float4 a01 = *reinterpret_cast<const float4*>(&sm.part[lane * 4]), a23 = *reinterpret_cast<const float4*>(&sm.part[lane * 4 + 2]);
+        const float4 b01 = *reinterpret_cast<const float4*>(&sm.part[(lane + 32) * 4]), b23 = *reinterpret_cast<const float4*>(&sm.part[(lane + 32) * 4 + 2]);
+        ssmin = fminf((a01.x + a01.z) + (a23.x + a23.z), (b01.x + b01.z) + (b23.x + b23.z));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ssmin = fminf(ssmin, __shfl_xor_sync(0xffffffffu, ssmin, o));
+      }
+      const float bnd = 2.0f * fabsf(g64) / fmaxf(sqrtf(ssmin), 1e-12f);
       int e = ((__float_as_int(bnd) >> 23) & 0xff) - 127;
       e = bnd > 0.0f ? min(max(e, -100), 100) : 13;
       const float S2 = __int_as_float((127 + 13 - e) << 23);
       inv_s2 = __int_as_float((127 - 13 + e) << 23);
-      *reinterpret_cast<uint4*>(sm.dh2a + (pos >> 3) * 512 + cg2 * 128 + (pos & 7) * 16) =
-          make_uint4(pack_h2(v[0] * S2, v[1] * S2), pack_h2(v[2] * S2, v[3] * S2), pack_h2(v[4] * S2, v[5] * S2),
-                     pack_h2(v[6] * S2, v[7] * S2));
+      __half hv[8];
+#pragma unroll
+      for (int oo = 0; oo < 8; ++oo) hv[oo] = __float2half_rn(v[oo] * S2);
+      *reinterpret_cast<uint4*>(sm.dh2a + (pos >> 3) * 512 + cg2 * 128 + (pos & 7) * 16) = *reinterpret_cast<const uint4*>(hv);
+      unsigned char* bb = sm.dh2t + cg2 * kDh1bPitch + (pos >> 3) * 128 + (pos & 7) * 2;
+#pragma unroll
+      for (int oo = 0; oo < 8; ++oo) *reinterpret_cast<__half*>(bb + oo * 16) = hv[oo];
     }
     fence_proxy_async();
     tc_fence_before();  // conv2's accumulator has been read
     __syncthreads();
     AHV_PH(3);
 
-    // ---------------- dH1 = (dH2 W2) * [H1 > 0] on the tensor core; dW2 += dH2^T H1 meanwhile (fp32) ----------------
+    // ---------------- dH1 = (dH2 W2) * [H1 > 0] and dW2 += dH2^T H1 on the tensor core; half of the work list meanwhile ----------------
     if (warp == 0) {
       tc_fence_after();
 #pragma unroll
@@ -393,19 +455,16 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
         for (int j = 0; j < 2; ++j)
           umma_f16(tmem + kColDh1 + ((uint32_t)(16 * half) << 16), smem_desc(dh2a_s + j * 256, 128, 512),
                    smem_desc(w2tb_s + half * 1024 + j * 256, 128, 512), idC, j);
+#pragma unroll
+      for (int half = 0; half < 2; ++half)  // rows = channels o of dH2 (the upper 32 of the M=64 rows are padding), K = positions
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_f16(tmem + kColW2 + ((uint32_t)(16 * half) << 16), smem_desc(dh2t_s + j * 256, 128, kDh1bPitch),
+                   smem_desc(h1t_s + half * 2 * kDh1bPitch + j * 256, 128, kDh1bPitch), idC, j);
       umma_commit(bar_s + 16);
       __syncwarp();
     }
-    {
-      const int o = t >> 3, i0 = (t & 7) * 4;
-#pragma unroll 8
-      for (int p = 0; p < kP; ++p) {
-        const float d = sm.dh2[p * kH1Row + o];
-        const float4 h = *reinterpret_cast<const float4*>(sm.h1s + p * kH1Row + i0);
-        aW2[0] = fmaf(d, h.x, aW2[0]); aW2[1] = fmaf(d, h.y, aW2[1]);
-        aW2[2] = fmaf(d, h.z, aW2[2]); aW2[3] = fmaf(d, h.w, aW2[3]);
-      }
-    }
+    list_pass(0);
     float dh1[8];
     {
       mbar_wait(bar_s + 16, phase);
@@ -413,16 +472,24 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       uint32_t r8[8];
       tmem_ld8(tq + kColDh1 + hf * 8, r8);
       tmem_ld_wait();
-      const float* hp = sm.h1s + pos * kH1Row + cg2 * 8;  // ReLU mask (modules/modules.py:68)
+      const uint4 hm = *reinterpret_cast<const uint4*>(sm.h1a + (pos >> 3) * 512 + cg2 * 128 + (pos & 7) * 16);
+      const __half* hp = reinterpret_cast<const __half*>(&hm);  // ReLU mask (modules/modules.py:68)
       float mx = 0.0f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dh1[j] = hp[j] > 0.0f ? __uint_as_float(r8[j]) * inv_s2 : 0.0f;
+        dh1[j] = __half2float(hp[j]) > 0.0f ? __uint_as_float(r8[j]) * inv_s2 : 0.0f;
         mx = fmaxf(mx, fabsf(dh1[j]));
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       if (lane == 0) sm.red[warp] = mx;
+      if (qd < 2) {  // dW2 rows o = 16 qd + lane % 16 (quadrants 2, 3 hold the padding rows)
+        tmem_ld8(tq + kColW2 + hf * 8, r8);
+        tmem_ld_wait();
+        const float sc = inv_s2 * pinv;  // undo the dH2 scale and the pair scale of H1
+#pragma unroll
+        for (int j = 0; j < 8; ++j) aW2[j] = fmaf(__uint_as_float(r8[j]), sc, aW2[j]);
+      }
     }
     tc_fence_before();
     __syncthreads();
@@ -470,48 +537,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
       __syncwarp();
     }
 
-    // ---------------- meanwhile: the adjoint's work list ----------------
-    // Output voxel vo feeds the 8 input voxels of its tap with weight w.  Turned round: every INPUT voxel gets the list
-    // of its (vo, w) contributions, so that the adjoint below is one flat loop per input voxel.  A rigid rotation puts
-    // about 8 (at most ~12) contributions on a voxel: the list is a fixed row of kListCap entries per voxel, filled in
-    // ONE pass (the counter's atomic returns the place in the row).  A matrix that is not a rotation can exceed the
-    // row: then the item takes the exact path below (counting sort with prefix sums) - valid for any matrix R.
-    int* cnt = reinterpret_cast<int*>(sm.dh2 + kListTail);   // [512] contributions per input voxel
-    int* start = cnt + kVox;                                 // [512] exclusive prefix sum (exact path)
-    uint32_t* ent16 = reinterpret_cast<uint32_t*>(sm.rotA);  // [512][kListPitch]
-    uint2* ent = reinterpret_cast<uint2*>(sm.rotA);          // exact path: [<= 4096] (offset of dX[vo], weight)
-    {
-      cnt[t] = 0;
-      cnt[t + 256] = 0;
-      if (t == 0) sm.overflow = 0;
-      __syncthreads();
-      // The thread's two output voxels are chosen two apart in x and y and four in z across the lanes of a warp, so
-      // that the taps of one warp's voxels rarely meet in the same counter (adjacent voxels share half their taps and
-      // would serialise the atomics).
-      bool over = false;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int vo = out_voxel(t, j);
-        const uint32_t off4 = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW) >> 2;
-        const float4 tp = sm.taps[vo];
-        const int line = __float_as_int(tp.x);   // ((z0+1)*10 + (y0+1))*10 + (x0+1), corner in [-1, 7]^3
-        const int zl = line / (kHalo * kHalo), rl = line - zl * (kHalo * kHalo), yl = rl / kHalo, xl = rl - yl * kHalo;
-        const int x0 = xl - 1, y0 = yl - 1, z0 = zl - 1;
-        const int tgt0 = z0 * 64 + y0 * 8 + x0;
-#pragma unroll
-        for (int dlt = 0; dlt < 8; ++dlt) {
-          const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
-          if ((unsigned)(x0 + dx) < 8u && (unsigned)(y0 + dy) < 8u && (unsigned)(z0 + dz) < 8u) {
-            const int v = tgt0 + dz * 64 + dy * 8 + dx;
-            const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
-            const int r = atomicAdd(&cnt[v], 1);
-            if (r < kListCap) ent16[v * kListPitch + r] = off4 | (__float2uint_rn(w * 65535.0f) << 16);
-            else over = true;
-          }
-        }
-      }
-      if (over) sm.overflow = 1;
-    }
+    list_pass(1);   // second half of the adjoint's work list, in the shadow of the MMAs
 
     AHV_PH(6);
     // ---------------- accumulators: dW1^T -> registers, dA -> dX (fold of the three views) ----------------
@@ -701,8 +727,6 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     long long tot = 0;
     for (int i = 0; i < 10; ++i) tot += ph_[i];
-    printf("sort detail: issue+zero+count %lld | scan %lld | fill = rest\n", ph_[10] / (hi - lo), ph_[11] / (hi - lo));
-    ph_[6] += ph_[10] + ph_[11];
     printf("bwd_tc phases, cycles per item (CTA 0, %lld items): loop+R %lld | gather+H1 %lld | pack views %lld | conv2+dH2 %lld | dW2+dH1 %lld | "
            "operands %lld | MMA issue+sort %lld | MMA wait %lld | dW1 read+fold %lld | adjoint %lld | total %lld\n",
            (long long)(hi - lo), ph_[0] / (hi - lo), ph_[1] / (hi - lo), ph_[2] / (hi - lo), ph_[3] / (hi - lo), ph_[4] / (hi - lo),
@@ -716,12 +740,13 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
 #pragma unroll
     for (int oo = 0; oo < 16; ++oo) atomicAdd(g_W1 + (16 * hf + oo) * kK + view * 128 + 32 * qd + lane, aW1[view][oo]);
   {
-    const int o = t >> 3, i0 = (t & 7) * 4;
+    if (qd < 2) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(g_W2 + o * kO + i0 + i, aW2[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(g_W2 + (16 * qd + (lane & 15)) * kO + 16 * (lane >> 4) + 8 * hf + i, aW2[i]);
+    }
     // db2: sum over the 64 positions inside the CTA first (threads with equal cg2 = t & 3)
     __syncthreads();
-    float* red = sm.h1s;  // [4 cg2][8 oo][64 pos]
+    float* red = sm.dh2;  // [4 cg2][8 oo][64 pos]
 #pragma unroll
     for (int oo = 0; oo < 8; ++oo) red[(cg2 * 8 + oo) * kP + pos] = ab2[oo];
     __syncthreads();
