@@ -130,34 +130,45 @@ __device__ __forceinline__ void stage_volume_interleaved(float* __restrict__ vol
 __device__ __forceinline__ void gather_rotated(BwdTcSmem& sm, const float* R) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = lane & 3, q = lane >> 2;
+  // warp = h; iteration it = d; the 8 voxels of an iteration run along w (q), 4 lanes (j) per voxel.  The sample
+  // position of a voxel is computed ONCE, by lane (d % 4) * 8 + w for the four d of a half, and handed to the voxel's
+  // four lanes by shuffles (the four lanes used to recompute it: a third of the gather's instructions).
 #pragma unroll 1
-  for (int it = 0; it < 8; ++it) {
-    const int s = it * 8 + warp;
-    const int d = s >> 3, h = s & 7, w = q;
-    const Tap t = make_tap(R, sm.base[w], sm.base[h], sm.base[d]);
-    if (j == 0) sm.taps[d * 64 + h * 8 + w] = make_float4(__int_as_float(t.line), t.fx, t.fy, t.fz);
-    const int swap = (t.line ^ q) & 1;  // parity order: the two x-taps of a lane pair never share a bank half
-    const float wx_first = swap ? t.fx : 1.0f - t.fx;
-    const float wx_second = swap ? 1.0f - t.fx : t.fx;
-    const float* p0 = sm.vol + (t.line + swap) * kC + j * 4;
-    const float* p1 = sm.vol + (t.line + 1 - swap) * kC + j * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int half = 0; half < 2; ++half) {
+    const int dl = 4 * half + (lane >> 3), wl = lane & 7;
+    const Tap own = make_tap(R, sm.base[wl], sm.base[warp], sm.base[dl]);
+    sm.taps[dl * 64 + warp * 8 + wl] = make_float4(__int_as_float(own.line), own.fx, own.fy, own.fz);
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const int d = 4 * half + i, h = warp, w = q, src = i * 8 + q;
+      Tap t;
+      t.line = __shfl_sync(0xffffffffu, own.line, src);
+      t.fx = __shfl_sync(0xffffffffu, own.fx, src);
+      t.fy = __shfl_sync(0xffffffffu, own.fy, src);
+      t.fz = __shfl_sync(0xffffffffu, own.fz, src);
+      const int swap = (t.line ^ q) & 1;  // parity order: the two x-taps of a lane pair never share a bank half
+      const float wx_first = swap ? t.fx : 1.0f - t.fx;
+      const float wx_second = swap ? 1.0f - t.fx : t.fx;
+      const float* p0 = sm.vol + (t.line + swap) * kC + j * 4;
+      const float* p1 = sm.vol + (t.line + 1 - swap) * kC + j * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int dz = 0; dz < 2; ++dz)
+      for (int dz = 0; dz < 2; ++dz)
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
-        const float wyz = (dy ? t.fy : 1.0f - t.fy) * (dz ? t.fz : 1.0f - t.fz);
-        const int off = (dz * kHalo * kHalo + dy * kHalo) * kC;
-        const float4 a = *reinterpret_cast<const float4*>(p0 + off);
-        const float4 b = *reinterpret_cast<const float4*>(p1 + off);
-        const float wa = wyz * wx_first, wb = wyz * wx_second;
-        acc.x = fmaf(wa, a.x, acc.x); acc.y = fmaf(wa, a.y, acc.y);
-        acc.z = fmaf(wa, a.z, acc.z); acc.w = fmaf(wa, a.w, acc.w);
-        acc.x = fmaf(wb, b.x, acc.x); acc.y = fmaf(wb, b.y, acc.y);
-        acc.z = fmaf(wb, b.z, acc.z); acc.w = fmaf(wb, b.w, acc.w);
-      }
-    float* dst = sm.rotA + j * kRc + d * kRotD + h * 8 + w;   // the staged volume interleaves the channels: lane j holds j, j+4, j+8, j+12
-    dst[0] = acc.x; dst[4 * kRc] = acc.y; dst[8 * kRc] = acc.z; dst[12 * kRc] = acc.w;
+        for (int dy = 0; dy < 2; ++dy) {
+          const float wyz = (dy ? t.fy : 1.0f - t.fy) * (dz ? t.fz : 1.0f - t.fz);
+          const int off = (dz * kHalo * kHalo + dy * kHalo) * kC;
+          const float4 a = *reinterpret_cast<const float4*>(p0 + off);
+          const float4 b = *reinterpret_cast<const float4*>(p1 + off);
+          const float wa = wyz * wx_first, wb = wyz * wx_second;
+          acc.x = fmaf(wa, a.x, acc.x); acc.y = fmaf(wa, a.y, acc.y);
+          acc.z = fmaf(wa, a.z, acc.z); acc.w = fmaf(wa, a.w, acc.w);
+          acc.x = fmaf(wb, b.x, acc.x); acc.y = fmaf(wb, b.y, acc.y);
+          acc.z = fmaf(wb, b.z, acc.z); acc.w = fmaf(wb, b.w, acc.w);
+        }
+      float* dst = sm.rotA + j * kRc + d * kRotD + h * 8 + w;   // the staged volume interleaves the channels: lane j holds j, j+4, j+8, j+12
+      dst[0] = acc.x; dst[4 * kRc] = acc.y; dst[8 * kRc] = acc.z; dst[12 * kRc] = acc.w;
+    }
   }
 }
 
@@ -203,7 +214,11 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
   if (lo >= hi) return;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const uint32_t bar_s = smem_u32(&sm.bar[0]);
+  // shared-window address of the struct, made opaque once: ptxas otherwise re-derives it (S2UR SR_CgaCtaId + 5 uniform
+  // ops) in front of every MMA it issues
+  uint32_t sbase;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem_raw)));
+  const uint32_t bar_s = sbase + (uint32_t)offsetof(BwdTcSmem, bar);
 
   // ---- set-up: W2 (fp32), W1^T operand (fp16, permuted rows), base coordinates, barrier, TMEM ----
   for (int i = t; i < kO * kO; i += kThreads) {
@@ -234,9 +249,11 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
-  const uint32_t at_s = smem_u32(sm.at), w1t_s = smem_u32(sm.w1t), dh1a_s = smem_u32(sm.dh1a), dh1b_s = smem_u32(sm.dh1b);
-  const uint32_t h1t_s = smem_u32(sm.h1t), dh2t_s = smem_u32(sm.dh2t);
-  const uint32_t h1a_s = smem_u32(sm.h1a), dh2a_s = smem_u32(sm.dh2a), w2b_s = smem_u32(sm.w2b), w2tb_s = smem_u32(sm.w2tb);
+  const uint32_t at_s = sbase + (uint32_t)offsetof(BwdTcSmem, at), w1t_s = sbase + (uint32_t)offsetof(BwdTcSmem, w1t);
+  const uint32_t dh1a_s = sbase + (uint32_t)offsetof(BwdTcSmem, dh1a), dh1b_s = sbase + (uint32_t)offsetof(BwdTcSmem, dh1b);
+  const uint32_t h1t_s = sbase + (uint32_t)offsetof(BwdTcSmem, h1t), dh2t_s = sbase + (uint32_t)offsetof(BwdTcSmem, dh2t);
+  const uint32_t h1a_s = sbase + (uint32_t)offsetof(BwdTcSmem, h1a), dh2a_s = sbase + (uint32_t)offsetof(BwdTcSmem, dh2a);
+  const uint32_t w2b_s = sbase + (uint32_t)offsetof(BwdTcSmem, w2b), w2tb_s = sbase + (uint32_t)offsetof(BwdTcSmem, w2tb);
   constexpr uint32_t idA = instr_desc(64, kColW), idW = instr_desc(128, 32), idC = instr_desc(64, 16);
 
   // accumulator read-out mapping: TMEM quadrant of this warp, column half
@@ -372,13 +389,15 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     // ---------------- conv2 on the tensor core (the forward's own arithmetic), A^T operand meanwhile ----------------
     if (warp == 0) {
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half)  // output channels 16 half .. +15 -> lanes 16 half .. of every quadrant
+        for (int half = 0; half < 2; ++half)  // output channels 16 half .. +15 -> lanes 16 half .. of every quadrant
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          umma_f16(tmem + kColH2 + ((uint32_t)(16 * half) << 16), smem_desc(h1a_s + j * 256, 128, 512),
-                   smem_desc(w2b_s + half * 1024 + j * 256, 128, 512), idC, j);
-      umma_commit(bar_s + 8);
+          for (int j = 0; j < 2; ++j)
+            umma_f16_raw(tmem + kColH2 + ((uint32_t)(16 * half) << 16), smem_desc(h1a_s + j * 256, 128, 512),
+                         smem_desc(w2b_s + half * 1024 + j * 256, 128, 512), idC, j);
+        umma_commit_raw(bar_s + 8);
+      }
       __syncwarp();
     }
     pack_views(sm, 1.0f / pinv);
@@ -449,22 +468,26 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     // ---------------- dH1 = (dH2 W2) * [H1 > 0] and dW2 += dH2^T H1 on the tensor core; half of the work list meanwhile ----------------
     if (warp == 0) {
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          umma_f16(tmem + kColDh1 + ((uint32_t)(16 * half) << 16), smem_desc(dh2a_s + j * 256, 128, 512),
-                   smem_desc(w2tb_s + half * 1024 + j * 256, 128, 512), idC, j);
+          for (int j = 0; j < 2; ++j)
+            umma_f16_raw(tmem + kColDh1 + ((uint32_t)(16 * half) << 16), smem_desc(dh2a_s + j * 256, 128, 512),
+                         smem_desc(w2tb_s + half * 1024 + j * 256, 128, 512), idC, j);
 #pragma unroll
-      for (int half = 0; half < 2; ++half)  // rows = channels o of dH2 (the upper 32 of the M=64 rows are padding), K = positions
+        for (int half = 0; half < 2; ++half)  // rows = channels o of dH2 (the upper 32 of the M=64 rows are padding), K = positions
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_f16(tmem + kColW2 + ((uint32_t)(16 * half) << 16), smem_desc(dh2t_s + j * 256, 128, kDh1bPitch),
-                   smem_desc(h1t_s + half * 2 * kDh1bPitch + j * 256, 128, kDh1bPitch), idC, j);
-      umma_commit(bar_s + 16);
+          for (int j = 0; j < 4; ++j)
+            umma_f16_raw(tmem + kColW2 + ((uint32_t)(16 * half) << 16), smem_desc(dh2t_s + j * 256, 128, kDh1bPitch),
+                         smem_desc(h1t_s + half * 2 * kDh1bPitch + j * 256, 128, kDh1bPitch), idC, j);
+        umma_commit_raw(bar_s + 16);
+      }
       __syncwarp();
     }
+    AHV_PH(10);
     list_pass(0);
+    AHV_PH(11);
     float dh1[8];
     {
       mbar_wait(bar_s + 16, phase);
@@ -519,21 +542,23 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     // ---------------- the two contractions on the tensor core ----------------
     if (warp == 0) {
       tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half)  // dA: rows = positions, columns = 192 of the permuted W1^T rows
+        for (int half = 0; half < 2; ++half)  // dA: rows = positions, columns = 192 of the permuted W1^T rows
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          umma_f16(tmem + ((uint32_t)(16 * half) << 16), smem_desc(dh1a_s + j * 256, 128, 512),
-                   smem_desc(w1t_s + half * (kColW / 8) * 512 + j * 256, 128, 512), idA, j);
+          for (int j = 0; j < 2; ++j)
+            umma_f16_raw(tmem + ((uint32_t)(16 * half) << 16), smem_desc(dh1a_s + j * 256, 128, 512),
+                         smem_desc(w1t_s + half * (kColW / 8) * 512 + j * 256, 128, 512), idA, j);
 #pragma unroll
-      for (int view = 0; view < 3; ++view)  // dW1^T: rows = (c, kk) of the view, K = the 64 positions
+        for (int view = 0; view < 3; ++view)  // dW1^T: rows = (c, kk) of the view, K = the 64 positions
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          umma_f16(tmem + kColW + view * 32,
-                   view < 2 ? smem_desc(at_s + view * kAtView + j * 256, 128, 1024)
-                            : smem_desc(at_s + 2 * kAtView + j * 2 * kAtZLbo, kAtZLbo, kAtZSbo),
-                   smem_desc(dh1b_s + j * 256, 128, kDh1bPitch), idW, j);
-      umma_commit(bar_s);
+          for (int j = 0; j < 4; ++j)
+            umma_f16_raw(tmem + kColW + view * 32,
+                         view < 2 ? smem_desc(at_s + view * kAtView + j * 256, 128, 1024)
+                                  : smem_desc(at_s + 2 * kAtView + j * 2 * kAtZLbo, kAtZLbo, kAtZSbo),
+                         smem_desc(dh1b_s + j * 256, 128, kDh1bPitch), idW, j);
+        umma_commit_raw(bar_s);
+      }
       __syncwarp();
     }
 
@@ -727,6 +752,8 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     long long tot = 0;
     for (int i = 0; i < 10; ++i) tot += ph_[i];
+    printf("dW2+dH1 detail: MMA issue %lld | list pass 0 %lld | rest = wait + read-outs + barrier\n", ph_[10] / (hi - lo), ph_[11] / (hi - lo));
+    ph_[4] += ph_[10] + ph_[11];
     printf("bwd_tc phases, cycles per item (CTA 0, %lld items): loop+R %lld | gather+H1 %lld | pack views %lld | conv2+dH2 %lld | dW2+dH1 %lld | "
            "operands %lld | MMA issue+sort %lld | MMA wait %lld | dW1 read+fold %lld | adjoint %lld | total %lld\n",
            (long long)(hi - lo), ph_[0] / (hi - lo), ph_[1] / (hi - lo), ph_[2] / (hi - lo), ph_[3] / (hi - lo), ph_[4] / (hi - lo),
