@@ -72,9 +72,12 @@ constexpr int kColW = 192;
 constexpr int kRc = kS * kRotD + 8;
 constexpr int kColH2 = 288, kColDh1 = 304, kColW2 = 320;   // conv2, dH1, dW2 accumulators: 16 columns each, both lane halves
 // dX (gradient w.r.t. the rotated volume) lives over the A^T operand once its MMAs are done, voxel-major with the 16
-// channels innermost: element (d, h, w, c) at d*kDxD + h*kDxH + w*kDxW + c floats.  The pitches are 4*odd mod 32, so a
-// quarter-warp that runs over h (fold of view x) or over w (views y, z) hits eight distinct 16-byte bank groups.
-constexpr int kDxW = 20, kDxH = 164, kDxD = 1312;
+// channels innermost, in fp16: the adjoint's random reads of it are what bounds the kernel, and a record of 32 bytes
+// costs half the shared-memory wavefronts of an fp32 one.  Element (d, h, w, c) at word d*kDxD + h*kDxH + w*kDxW + c/2
+// (pitches in 4-byte words, multiples of 4 so that a record is two aligned LDS.128).  The values are the raw
+// accumulators (dH1's per-item scale S) times kappa, a power of two fixed per launch from W1 so that the sum of the
+// three views cannot overflow fp16: |dA| S < 2^14 * max_k sum_o |W1[o][k]|, kappa <= 2 / (3 * that maximum).
+constexpr int kDxW = 12, kDxH = 100, kDxD = 804;
 static_assert(8 * kDxD * 4 <= kAtBytes, "dX fits over the A^T operand");
 
 struct __align__(128) BwdTcSmem {
@@ -172,6 +175,25 @@ __device__ __forceinline__ void gather_rotated(BwdTcSmem& sm, const float* R) {
   }
 }
 
+// acc[0..15] += w * (the 16 fp16 channels of one dX record)
+__device__ __forceinline__ void axpy_record(float* acc, float w, const uint32_t* rec) {
+  const uint4 a = *reinterpret_cast<const uint4*>(rec), b = *reinterpret_cast<const uint4*>(rec + 4);
+  const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+    acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+  }
+}
+// four channels of a dX record += four accumulator values times kappa
+__device__ __forceinline__ void add4_record(uint32_t* p, float kappa, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  const uint2 x = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&x.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_h2(fmaf(__uint_as_float(r0), kappa, a.x), fmaf(__uint_as_float(r1), kappa, a.y)),
+                                            pack_h2(fmaf(__uint_as_float(r2), kappa, b.x), fmaf(__uint_as_float(r3), kappa, b.y)));
+}
+
 // output voxel (z*64 + y*8 + x) a thread lists for the adjoint: lane bits -> x2 x1 y2 y1 z2, warp bits and j -> the rest
 __device__ __forceinline__ int out_voxel(int t, int j) {
   const int x = ((t & 3) << 1) | ((t >> 5) & 1), y = (((t >> 2) & 3) << 1) | ((t >> 6) & 1);
@@ -234,6 +256,17 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
     *reinterpret_cast<__half*>(sm.w1t + grp * 512 + (o >> 3) * 128 + kk * 16 + (o & 7) * 2) = __float2half_rn(__ldg(W1 + i));
   }
   if (t < 8) sm.base[t] = base ? base[t] : 0.0f;
+  {  // largest L1 norm of a W1 column (fp16-rounded, as the MMA sees it): bounds |dA| / max|dH1| for the fp16 dX
+    float cmax = 0.0f;
+    for (int k = t; k < kK; k += kThreads) {
+      float c1 = 0.0f;
+      for (int o = 0; o < kO; ++o) c1 += fabsf(__half2float(__float2half_rn(__ldg(W1 + o * kK + k))));
+      cmax = fmaxf(cmax, c1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    if (lane == 0) sm.red[warp] = cmax;
+  }
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(bar_s, 1);
@@ -249,6 +282,18 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_slot;
+  float kappa = 1.0f, inv_kappa = 1.0f;
+  {
+    float c = sm.red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) c = fmaxf(c, sm.red[w]);
+    if (c > 0.0f) {
+      const float x = 2.0f / (3.0f * c);
+      const int e = min(max(((__float_as_int(x) >> 23) & 0xff) - 127, -60), 60);   // floor(log2 x)
+      kappa = __int_as_float((127 + e) << 23);
+      inv_kappa = __int_as_float((127 - e) << 23);
+    }
+  }
   const uint32_t at_s = sbase + (uint32_t)offsetof(BwdTcSmem, at), w1t_s = sbase + (uint32_t)offsetof(BwdTcSmem, w1t);
   const uint32_t dh1a_s = sbase + (uint32_t)offsetof(BwdTcSmem, dh1a), dh1b_s = sbase + (uint32_t)offsetof(BwdTcSmem, dh1b);
   const uint32_t h1t_s = sbase + (uint32_t)offsetof(BwdTcSmem, h1t), dh2t_s = sbase + (uint32_t)offsetof(BwdTcSmem, dh2t);
@@ -315,7 +360,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
   // warp, so that the taps of one warp's voxels rarely meet in the same counter.
   auto list_pass = [&](int j) {
     const int vo = out_voxel(t, j);
-    const uint32_t off4 = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW) >> 2;
+    const uint32_t off4 = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW) >> 2;   // record, in 16-byte units
     const float4 tp = sm.taps[vo];
     const int line = __float_as_int(tp.x);   // ((z0+1)*10 + (y0+1))*10 + (x0+1), corner in [-1, 7]^3
     const int zl = line / (kHalo * kHalo), rl = line - zl * (kHalo * kHalo), yl = rl / kHalo, xl = rl - yl * kHalo;
@@ -581,52 +626,44 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
         for (int oo = 0; oo < 16; ++oo) aW1[view][oo] = fmaf(__uint_as_float(r[oo]), sc, aW1[view][oo]);
       }
     }
-    float* dX = reinterpret_cast<float*>(sm.at);  // the A^T operand is dead: its MMAs have completed
+    uint32_t* dX = reinterpret_cast<uint32_t*>(sm.at);  // the A^T operand is dead: its MMAs have completed
     {
       uint32_t r[32];
       // view x: dX[d=p, h=q, w=kk, c] = ...   (every element of dX written exactly once: no zeroing needed)
       tmem_ld32(tq + hf * 96, r);
       tmem_ld_wait();
       {
-        float* dst = dX + fp * kDxD + fq * kDxH + 4 * fg;
+        uint32_t* dst = dX + fp * kDxD + fq * kDxH + 2 * fg;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          *reinterpret_cast<float4*>(dst + kk * kDxW) = make_float4(__uint_as_float(r[kk]) * invS, __uint_as_float(r[8 + kk]) * invS,
-                                                                   __uint_as_float(r[16 + kk]) * invS, __uint_as_float(r[24 + kk]) * invS);
+          *reinterpret_cast<uint2*>(dst + kk * kDxW) = make_uint2(pack_h2(__uint_as_float(r[kk]) * kappa, __uint_as_float(r[8 + kk]) * kappa),
+                                                                  pack_h2(__uint_as_float(r[16 + kk]) * kappa, __uint_as_float(r[24 + kk]) * kappa));
       }
       tmem_ld32(tq + hf * 96 + 32, r);  // view y, in flight across the barrier
       tmem_ld_wait();
       __syncthreads();
       {  // dX[d=p, h=kk, w=q, c] += ...
-        float* dst = dX + fp * kDxD + fq * kDxW + 4 * fg;
+        uint32_t* dst = dX + fp * kDxD + fq * kDxW + 2 * fg;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          float4 x = *reinterpret_cast<float4*>(dst + kk * kDxH);
-          x.x = fmaf(__uint_as_float(r[kk]), invS, x.x); x.y = fmaf(__uint_as_float(r[8 + kk]), invS, x.y);
-          x.z = fmaf(__uint_as_float(r[16 + kk]), invS, x.z); x.w = fmaf(__uint_as_float(r[24 + kk]), invS, x.w);
-          *reinterpret_cast<float4*>(dst + kk * kDxH) = x;
-        }
+        for (int kk = 0; kk < 8; ++kk) add4_record(dst + kk * kDxH, kappa, r[kk], r[8 + kk], r[16 + kk], r[24 + kk]);
       }
       tmem_ld32(tq + hf * 96 + 64, r);  // view z
       tmem_ld_wait();
       tc_fence_before();                // the next item's MMAs overwrite these accumulators
       __syncthreads();
       {  // dX[d=kk, h=p, w=q, c] += ...
-        float* dst = dX + fp * kDxH + fq * kDxW + 4 * fg;
+        uint32_t* dst = dX + fp * kDxH + fq * kDxW + 2 * fg;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          float4 x = *reinterpret_cast<float4*>(dst + kk * kDxD);
-          x.x = fmaf(__uint_as_float(r[kk]), invS, x.x); x.y = fmaf(__uint_as_float(r[8 + kk]), invS, x.y);
-          x.z = fmaf(__uint_as_float(r[16 + kk]), invS, x.z); x.w = fmaf(__uint_as_float(r[24 + kk]), invS, x.w);
-          *reinterpret_cast<float4*>(dst + kk * kDxD) = x;
-        }
+        for (int kk = 0; kk < 8; ++kk) add4_record(dst + kk * kDxD, kappa, r[kk], r[8 + kk], r[16 + kk], r[24 + kk]);
       }
     }
+    const float unscale = invS * inv_kappa;   // dX holds dA * S * kappa
     __syncthreads();
     AHV_PH(8);
 
     // ---------------- dV_b += rotate^T(dX): adjoint of utils.py:113-131, one flat list per input voxel ----------------
     if (sm.overflow == 0) {
+      const float wq = unscale * (1.0f / 65535.0f);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int vi = t + 256 * j;
@@ -647,14 +684,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
         for (int i = 0; i < kListCap; ++i) {
           if (i >= nmax) break;   // warp-uniform
           if (i < nn) {
-            const float w = (float)(en[i] >> 16) * (1.0f / 65535.0f);
-            const float* src = dX + ((en[i] & 0xffffu) << 2);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
-              aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
-              aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
-            }
+            axpy_record(aV[j], (float)(en[i] >> 16) * wq, dX + ((en[i] & 0xffffu) << 2));
           }
         }
       }
@@ -734,14 +764,7 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
 #pragma unroll 2
         for (int i = 0; i < nn; ++i) {
           const uint2 en = e[i];
-          const float w = __uint_as_float(en.y);
-          const float* src = dX + en.x;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
-            aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
-            aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
-          }
+          axpy_record(aV[j], __uint_as_float(en.y) * unscale, dX + en.x);
         }
       }
     }
