@@ -8,13 +8,13 @@
 //   X = rotate(V_b, R_n)                         fp32 gather in shared memory (taps recorded for the adjoint)
 //   H2 = H1 W2^T + b2   [64 pos x 32]            tcgen05.mma  M=64 N=16 (x2)  K=32   H1 = the fp16 rows the forward kept
 //   F = H2/|H2| ; dH2 ; dT += (g/64) F ; db2     fp32, thread = (position, 8 channels) as the accumulator presents them
-//   dH1 = (dH2 W2) * [H1 > 0]                    tcgen05.mma  M=64 N=16 (x2)  K=32   dH2 scaled per row (position)
-//   dW2 += dH2^T H1                              fp32 FFMA, in the shadow of the dH1 MMAs
+//   dH1 = (dH2 W2) * [H1 > 0]                    tcgen05.mma  M=64 N=16 (x2)  K=32   dH2 under one power of two per item
+//   dW2 += dH2^T H1                              tcgen05.mma  M=64 N=16 (x2)  K=64   rows = channels (32 + 32 padding)
 //   dA   [64 pos x 384]  = dH1 [64 x 32] . W1    tcgen05.mma  M=64 N=192 (x2) K=32
 //   dW1^T[384    x 32 ]  = A^T [384 x 64] . dH1  tcgen05.mma  M=128 (x3 views) N=32 K=64
 //   dX = fold(dA) (three tri-plane views onto the rotated volume) ; dV_b += rotate^T(dX)   (gather over a work list)
 //
-// 1.7 of the ~1.8 MFLOP per item are tensor-core work; the fp32 kernel spent 62 % of its time on them.
+// 1.75 of the ~1.8 MFLOP per item are tensor-core work; the fp32 kernel spent 69 % of its time on them.
 //
 // Operands (fp16, fp32 accumulation in TMEM), all K-major SWIZZLE_NONE core-matrix layouts
 // (element (row r, k) at (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2):
@@ -26,14 +26,15 @@
 //   A^T  as A of dW1  [m][pos]  : SBO 1024, LBO 128    (view z: 1152 / 144) m = view*128 + c*8 + kk; view y is the rotated
 //                                                      volume as it lies ([c][d][h][w]), view x its (h,w) transpose, view z
 //                                                      its (d,h) one
-//   dH1  as B of dW1  [o][pos]  : SBO 1040, LBO 128    (pitch 1040: the eight 2-byte stores of a warp hit distinct banks)
+//   dH1, dH2^T, H1^T  [ch][pos] : SBO 1040, LBO 128    B of dW1, A and B of dW2 (pitch 1040: the eight 2-byte stores of a
+//                                                      thread's channel block hit distinct banks across the warp)
 // Scales (powers of two, undone in fp32 when the accumulators are read): H1 and A^T carry the pair's scale of the
-// forward (pair_inv_scale); dH2 a per-position scale from the bound 2 |g/64| / |H2|; dH1 a per-item scale from
-// max |dH1| (2^13 <= max < 2^14).
+// forward (pair_inv_scale); dH2 a per-item scale from the bound 2 |g/64| / min_p |H2_p|; dH1 a per-item scale from
+// max |dH1| (2^13 <= max < 2^14); dX (fp16) a launch-wide one from W1's largest column L1 norm.
 // The M=64 accumulators come in pairs side by side in the lanes (lanes 0-15 / 16-31 of every 32-lane quadrant hold two
-// column blocks of the same 16 rows), so all 32 lanes of a warp read; dW1^T is read every item into per-thread fp32
-// accumulators (48 per thread), which keeps the accumulation across items in fp32 and lets the scale differ per item.
-// dX lies voxel-major, channels innermost, over the dead A^T operand; the adjoint walks, per input voxel, a row of up
+// column blocks of the same 16 rows), so all 32 lanes of a warp read; dW1^T and dW2 are read every item into per-thread
+// fp32 accumulators (48 + 8), which keeps the accumulation across items in fp32 and lets the scales differ per item.
+// dX lies voxel-major, channels innermost, in fp16, over the dead A^T operand; the adjoint walks, per input voxel, a row of up
 // to 16 (offset, weight) contributions built in one pass of shared-memory atomics (exact fallback for matrices that are
 // not rotations and crowd more contributions onto a voxel).
 //
