@@ -91,6 +91,12 @@ def test_argument_validation_of_round2_entries_without_gpu(ahv):
     assert lib.ahv_predict_host_ex(None, None, 0, None, None, 0, None, None, None, None, None, None, None, None, 1, 0, 1, 1, 0,
                                    0, 1, None, 0, 0, None) == E                      # no session
     assert lib.ahv_host_session_destroy(None) == 0
+    # saved-activation training entries: null buffers, unknown arithmetic mode, misaligned activation buffer
+    assert lib.ahv_score_train(None, None, None, 0, None, None, None, None, None, None, None, 2, 10, None, 0, None) == E
+    one = ctypes.c_void_p(16)
+    bwd = lambda h1, mode: lib.ahv_score_backward_saved(one, one, one, 0, one, one, one, one, one, h1, one, one, one, one, one, one,
+                                                        2, 10, mode, None)
+    assert bwd(one, 7) == E and bwd(ctypes.c_void_p(24), ahv.MATH_TC) == E and bwd(None, ahv.MATH_TC) == E
     assert lib.ahv_version() == 200
 
 
