@@ -24,3 +24,20 @@ rot = ahv.ops.rotate_volume(T(g["vol_src"])[0], R)
 mv, mi = ahv.ops.topk_merge(torch.stack([r.topk_val, r.topk_val]), torch.stack([r.topk_idx, r.topk_idx + 100]))
 torch.cuda.synchronize()
 print("done", rot.shape, mi[0].tolist())
+# training variant: exact backward, saved-activation forward, both saved-activation backward forms (tensor-core one
+# with a rotation set and with shrunk matrices - the adjoint's exact path), fused InfoNCE
+if os.environ.get("AHV_SAN_TRAIN", "1") != "0":
+    B, Nt = 2, int(os.environ.get("AHV_SAN_NT", "19"))
+    vs, vt = T(g["vol_src"][:B]), T(g["vol_tgt"][:B])
+    tgt = ahv.ops.forward_3d2d(vt, *W)
+    Rp = ahv.so3.sample_rotations(B * Nt, seed=3, device=dev).reshape(B, Nt, 3, 3).contiguous()
+    gs = torch.randn(B, Nt, device=dev)
+    g0 = ahv.ops.score_backward(vs, tgt, Rp, *W, gs)
+    sc, h1, pinv = ahv.ops.score_train(vs, tgt, Rp, *W)
+    g1 = ahv.ops.score_backward(vs, tgt, Rp, *W, gs, h1, pinv, ahv.MATH_FP32)
+    g2 = ahv.ops.score_backward(vs, tgt, Rp, *W, gs, h1, pinv, ahv.MATH_TC)
+    sc3, h13, pinv3 = ahv.ops.score_train(vs, tgt, (Rp * 0.35).contiguous(), *W)
+    g3 = ahv.ops.score_backward(vs, tgt, (Rp * 0.35).contiguous(), *W, gs, h13, pinv3, ahv.MATH_TC)
+    loss, dl = ahv.ops.infonce(sc, Rp, Rp[:, 0].contiguous(), 15.0)
+    torch.cuda.synchronize()
+    print("training", [f"{float((a - b).abs().max() / b.abs().max()):.1e}" for a, b in zip(g2, g1)], float(loss.sum()))
