@@ -448,7 +448,7 @@ def run_ours(args):
 
         # training variant: scores + InfoNCE forward/backward on the reference's training shape
         # (12 pairs x 9 000 per-pair hypotheses, ground truth first), p50 of 7 steps after 2 warm-ups, three backward forms
-        if not strong_headline and world == 1:
+        if not strong_headline and world == 1 and not args.no_train:
             try:
                 Bt, Nt = 12, 9000
                 tW1, tW2, tb2, tvs, tvt, _ = synthetic_inputs(torch, Bt, 16)
@@ -594,6 +594,7 @@ def main():
     ap.add_argument("--hyps", type=int, default=HYPS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and gpu_eager_baseline legs")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (config 3, B=1 latency)")
+    ap.add_argument("--no-train", action="store_true", help="skip the training_step sub-record (profiling runs: keeps the launch list to the path)")
     ap.add_argument("--config", type=int, choices=[2, 3], default=2,
                     help="2 (default): BASELINE configs[1], weak scaling; 3: configs[2], bf16 volumes, hypothesis set sharded (strong)")
     args = ap.parse_args()
