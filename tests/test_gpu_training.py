@@ -320,3 +320,30 @@ def test_saved_activation_backward_is_the_gradient_of_the_function_that_ran(ahv,
         for name, a, r in zip(("vol_src", "tgt_feat", "W1", "W2", "b2"), got, ref):
             err = float((a.double() - r.reshape(a.shape)).abs().max()) / float(r.abs().max())
             assert err <= tol, (per_pair, shrink, "tcgen05" if math == ahv.MATH_TC else "fp32", name, err)
+
+
+def test_tensor_core_backward_over_shapes_scales_and_weights(ahv, golden):
+    """The tcgen05 backward against the fp32 contractions on the same saved activations (same mask: operand rounding
+    only, 2e-3 of each gradient's maximum) over item counts around the CTA partition (1 item, fewer items than SMs,
+    ranges that cross pairs), volume scales, large head weights (the overflow-safe scale of the fp16 dX: kappa from
+    W1's column norms), zero and huge upstream gradients."""
+    dev = torch.device("cuda", 0)
+    g, w = golden["shared_n3000_b3"], golden["weights"]
+    T = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    gen = torch.Generator().manual_seed(21)
+    cases = [(1, 1, 1.0, 1.0, 1.0), (1, 3, 1.0, 1.0, 1.0), (3, 49, 1.0, 1.0, 1.0), (2, 149, 1e-3, 1.0, 1.0), (3, 211, 1.0, 40.0, 1.0),
+             (2, 97, 50.0, 0.05, 1e6), (3, 500, 1.0, 1.0, 1e-8), (1, 777, 1.0, 8.0, 1.0)]
+    for B, N, vscale, wscale, gscale in cases:
+        vs, vt = T(g["vol_src"][:B]) * vscale, T(g["vol_tgt"][:B])
+        W1, W2, b2 = T(w["W1"]) * wscale, T(w["W2"]), T(w["b2"])
+        R = T(g["R"][: B * N]).reshape(B, N, 3, 3).contiguous()
+        tgt = ahv.ops.forward_3d2d(vt, W1, W2, b2)
+        gs = (torch.randn(B, N, generator=gen) * gscale).to(dev)
+        gs[0, 0] = 0.0                                                    # an item without gradient: every scale must stay finite
+        _, h1, pinv = ahv.ops.score_train(vs, tgt, R, W1, W2, b2)
+        a = ahv.ops.score_backward(vs, tgt, R, W1, W2, b2, gs, h1, pinv, ahv.MATH_TC)
+        b = ahv.ops.score_backward(vs, tgt, R, W1, W2, b2, gs, h1, pinv, ahv.MATH_FP32)
+        for name, x, y in zip(("vol_src", "tgt_feat", "W1", "W2", "b2"), a, b):
+            assert torch.isfinite(x).all(), (B, N, vscale, wscale, gscale, name)
+            worst = float((x - y).abs().max()) / max(float(y.abs().max()), 1e-30)
+            assert worst <= 2e-3, (B, N, vscale, wscale, gscale, name, worst)
