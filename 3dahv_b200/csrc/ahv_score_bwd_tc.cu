@@ -65,8 +65,8 @@ namespace {
 constexpr int kAtView = 16384;     // bytes of one view of A^T: 128 rows x 64 positions fp16
 constexpr int kAtZLbo = 144, kAtZSbo = 8 * kAtZLbo;   // view z: K-chunk pitch 144 B (its stores run over h: distinct banks)
 constexpr int kAtBytes = 2 * kAtView + 16 * kAtZSbo;
-constexpr int kDh1bPitch = 1040;   // SBO of the dW1 B operand
-constexpr int kTmemCols = 512;     // dA: columns 0..191 (both lane halves); dW1^T: columns 192..287
+constexpr int kDh1bPitch = 1040;   // row-group pitch (SBO) of the [channel][position] operands
+constexpr int kTmemCols = 512;     // dA: columns 0..191 (both lane halves); dW1^T: 192..287; conv2, dH1, dW2: 288..335
 constexpr int kColW = 192;
 // rotated volume [c][d][h][w]: channel pitch 584 = 8 mod 32, so the gather's four lanes of a voxel (channels j, j+4, j+8, j+12)
 // and its eight voxels along w store to 32 distinct banks
@@ -83,14 +83,14 @@ static_assert(8 * kDxD * 4 <= kAtBytes, "dX fits over the A^T operand");
 
 struct __align__(128) BwdTcSmem {
   float vol[kLines * kC];          // halo'd source volume, channel innermost (as the fp32 scorer)
-  float rotA[kC * kRc];          // rotated volume X [c][d][h][w] (padded); dead after the operands -> work-list entries
+  float rotA[kC * kRc];            // rotated volume X [c][d][h][w] (padded); dead after the operands -> work-list entries
   float dh2[kP * kH1Row];          // scratch behind rotA: tail of the work list, its counters; db2 reduction at the end
   float4 taps[kVox];
   unsigned char at[kAtBytes];      // A^T operand
   unsigned char w1t[kK * kO * 2];  // W1^T operand (permuted rows)
   unsigned char dh1a[kP * kO * 2];
   unsigned char h1a[kP * kO * 2];  // H1 as the forward kept it: A of conv2
-  unsigned char dh2a[kP * kO * 2]; // dH2 (row-scaled): A of dH1
+  unsigned char dh2a[kP * kO * 2]; // dH2 [pos][o]: A of dH1
   unsigned char w2b[kO * kO * 2];  // W2 as B of conv2 [o][i]
   unsigned char w2tb[kO * kO * 2]; // W2^T as B of dH1 [i][o]
   float2 part[kP * 4];             // per (position, channel block): partial |H2|^2 and <H2, T>
@@ -100,7 +100,7 @@ struct __align__(128) BwdTcSmem {
   float base[8];
   float red[8];
   float Rcur[12];
-  unsigned long long bar[3];       // contractions | conv2 | dH1
+  unsigned long long bar[3];       // dA + dW1 | conv2 | dH1 + dW2
   uint32_t tmem_slot;
   int overflow;                    // some input voxel has more than kListCap contributions (degenerate R): exact path
 };
