@@ -505,6 +505,19 @@ def run_ours(args):
                     latency[f"N={n_lat}"] = {"p50_us": statistics.median(a.elapsed_time(b_) for a, b_ in lev) * 1e3, "calls": 100}
                 except Exception as e:  # noqa: BLE001
                     latency[f"N={n_lat}"] = {"error": repr(e)}
+            try:   # the same replay in the opt-in 16-bit-gather mode
+                vfast = ahv.HypothesisVerifier(verifier.W1, verifier.W2, verifier.b2, math=ahv.MATH_TC_F16GATHER)
+                gv = ahv.GraphedVerifier(vfast, 1, 3000, k=1, device=dev)
+                gv(vs[:1].float(), vt[:1], R[:3000] if N >= 3000 else ahv.so3.sample_rotations(3000, 1, 0, dev))
+                for _ in range(10):
+                    gv()
+                lev = _events(torch, 100)
+                for a, b_ in lev:
+                    a.record(); gv(); b_.record()
+                torch.cuda.synchronize()
+                latency["N=3000, AHV_MATH_TC_F16GATHER"] = {"p50_us": statistics.median(a.elapsed_time(b_) for a, b_ in lev) * 1e3, "calls": 100}
+            except Exception as e:  # noqa: BLE001
+                latency["extra_error"] = repr(e)
         if world == 1 and not args.no_cpu:
             try:
                 eager = gpu_eager_rate(torch, dev, 2, 10000)
