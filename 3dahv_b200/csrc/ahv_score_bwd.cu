@@ -19,10 +19,12 @@
 // pair); they leave the CTA through global atomics (caller zero-initialises the outputs).
 //
 // The adjoint of the resampling is a GATHER, not a scatter (floating-point shared-memory atomics would cost
-// ~130k cycles per hypothesis): the 512 output voxels are bucketed by the corner line of their taps (a counting
-// sort with 1 024 integer shared-memory atomics), every thread owns two input voxels and visits the 8 buckets
-// around each - exactly the output voxels that touch it, whatever the matrix R is - re-using the taps the forward
-// gather recorded, so the weights are the forward's bit for bit.
+// ~130k cycles per hypothesis): every INPUT voxel gets the list of the (output voxel, weight) contributions that reach
+// it (counting sort over the <= 4096 contributions with integer shared-memory atomics and prefix sums), and every
+// thread walks the lists of its two input voxels - exactly the output voxels that touch them, whatever the matrix R
+// is - reading dX, which lies voxel-major with the channels innermost, as four LDS.128 per contribution.
+#include <cstddef>
+
 #include "ahv_head_fp32.cuh"
 
 namespace ahv {
@@ -33,6 +35,23 @@ struct BwdSmem {
   float4 taps[kVox];       // (corner line, fx, fy, fz) of every output voxel of the current hypothesis
 };
 static_assert(sizeof(BwdSmem) <= 232448, "shared memory budget");
+
+// dX (gradient w.r.t. the rotated volume) overlays rotA / rotT once dW1 is done, voxel-major with the 16 channels
+// innermost: element (d, h, w, c) at d*kDxD + h*kDxH + w*kDxW + c floats - the adjoint reads a voxel's record as four
+// LDS.128.  The pitches are 4*odd mod 32: the fold's lanes (which run over h or over w) meet distinct bank groups.  The
+// adjoint's work list (<= 4096 entries of 8 bytes) follows it, into the dH1 buffer, which is dead by then as well.
+constexpr int kDxW = 20, kDxH = 164, kDxD = 1312, kDxFloats = 8 * kDxD;
+static_assert(offsetof(Fp32Smem, rotT) == offsetof(Fp32Smem, rotA) + sizeof(float) * kC * kRotC &&
+              offsetof(Fp32Smem, h1s) == offsetof(Fp32Smem, rotT) + sizeof(float) * kC * kRotC, "rotA, rotT, h1s are contiguous");
+static_assert((kDxFloats + 2 * kVox * 8) <= 2 * kC * kRotC + kP * kH1Row, "dX and the work list fit the dead buffers");
+static_assert(2 * kVox * sizeof(int) <= sizeof(float) * kP * kH1Row, "counters fit the dH2 buffer");
+
+// output voxel (z*64 + y*8 + x) a thread lists for the adjoint: lane bits -> x2 x1 y2 y1 z2, warp bits and j -> the rest
+__device__ __forceinline__ int adjoint_out_voxel(int t, int j) {
+  const int x = ((t & 3) << 1) | ((t >> 5) & 1), y = (((t >> 2) & 3) << 1) | ((t >> 6) & 1);
+  const int z = (((t >> 4) & 1) << 2) | (((t >> 7) & 1) << 1) | j;
+  return z * 64 + y * 8 + x;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tgt_feat,
@@ -218,12 +237,12 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
         }
       }
     }
-    __syncthreads();  // rotA / rotT are free: rotA becomes dX[c][d][h][w]
+    __syncthreads();  // rotA / rotT are free: they become dX, voxel-major with the channels innermost
 
     // ---------------- dA = dH1 W1, folded view by view into dX ----------------
     {
       const int pl = t & 15, c = t >> 4;  // positions pl + 16 j, channel c, all (view, kk)
-      float* dX = sm.rotA + c * kRotC;
+      float* dX = sm.rotA + c;            // element (d, h, w, c) at d*kDxD + h*kDxH + w*kDxW + c
 #pragma unroll 1
       for (int view = 0; view < 3; ++view) {
         float acc[4][8];
@@ -252,9 +271,9 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
           const int ps = pl + 16 * j, p = ps >> 3, q = ps & 7;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            if (view == 0) dX[p * kRotD + q * 8 + kk] = acc[j][kk];          // V'[c, d=p, h=q, w=kk]
-            else if (view == 1) dX[p * kRotD + kk * 8 + q] += acc[j][kk];    // V'[c, d=p, h=kk, w=q]
-            else dX[kk * kRotD + p * 8 + q] += acc[j][kk];                   // V'[c, d=kk, h=p, w=q]
+            if (view == 0) dX[p * kDxD + q * kDxH + kk * kDxW] = acc[j][kk];          // V'[c, d=p, h=q, w=kk]
+            else if (view == 1) dX[p * kDxD + kk * kDxH + q * kDxW] += acc[j][kk];    // V'[c, d=p, h=kk, w=q]
+            else dX[kk * kDxD + p * kDxH + q * kDxW] += acc[j][kk];                   // V'[c, d=kk, h=p, w=q]
           }
         }
         __syncthreads();
@@ -262,32 +281,49 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
     }
 
     // ---------------- dV_b += rotate^T(dX): adjoint of utils.py:113-131 as a gather ----------------
-    // Output voxel vo contributes to the 8 input voxels corner(vo) + {0,1}^3.  Turned round: input voxel v receives
-    // from the output voxels whose corner is v - delta, delta in {0,1}^3.  So the 512 output voxels are bucketed by
-    // their corner line (counting sort in shared memory, over the dH2 buffer, which is dead by now), and every
-    // thread visits the 8 buckets around each of its two input voxels - exactly the contributing voxels, no geometry
-    // test, valid for any matrix R - with the weights the forward gather recorded, bit for bit.
+    // Output voxel vo feeds the 8 input voxels of its tap, corner(vo) + {0,1}^3, with the forward's weights.  Turned round:
+    // every INPUT voxel gets the list of its (vo, weight) contributions - a counting sort over the <= 4096 contributions
+    // that land inside the volume (shared-memory integer atomics whose return value is the place in the list, prefix
+    // sums, 8-byte entries behind dX in the dead rotated-volume / dH1 buffers) - and the adjoint is one flat loop per
+    // input voxel: exactly the contributing voxels, no geometry test, valid for any matrix R, fp32 weights recomputed from
+    // the taps the forward gather recorded.
     {
-      int* cnt = reinterpret_cast<int*>(bs.dh2);            // [1000] voxels per corner line, then running fill offset
-      int* start = cnt + kLines;                            // [1000] exclusive prefix sum
-      unsigned short* list = reinterpret_cast<unsigned short*>(start + kLines);  // [512] output voxels sorted by corner line
-      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;
+      int* cnt = reinterpret_cast<int*>(bs.dh2);   // [512] contributions per input voxel
+      int* start = cnt + kVox;                     // [512] exclusive prefix sum
+      uint2* ent = reinterpret_cast<uint2*>(sm.rotA + kDxFloats);   // [<= 4096] (offset of dX[vo], weight)
+      cnt[t] = 0;
+      cnt[t + 256] = 0;
       __syncthreads();
-      int myline[2];
+      // the thread's two output voxels: two apart in x and y, four in z across the lanes of a warp, so that the taps of one
+      // warp's voxels rarely meet in the same counter
+      int tgt0[2];
+      uint32_t inside[2], rank[2][4];
+      float fx[2], fy[2], fz[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        myline[j] = __float_as_int(bs.taps[t + 256 * j].x);
-        atomicAdd(&cnt[myline[j]], 1);
+        const int vo = adjoint_out_voxel(t, j);
+        const float4 tp = bs.taps[vo];
+        const int line = __float_as_int(tp.x);   // ((z0+1)*10 + (y0+1))*10 + (x0+1), corner in [-1, 7]^3
+        const int zl = line / (kHalo * kHalo), rl = line - zl * (kHalo * kHalo), yl = rl / kHalo, xl = rl - yl * kHalo;
+        const int x0 = xl - 1, y0 = yl - 1, z0 = zl - 1;
+        fx[j] = tp.y; fy[j] = tp.z; fz[j] = tp.w;
+        tgt0[j] = z0 * 64 + y0 * 8 + x0;
+        uint32_t m = 0;
+        rank[j][0] = rank[j][1] = rank[j][2] = rank[j][3] = 0;
+#pragma unroll
+        for (int dlt = 0; dlt < 8; ++dlt) {
+          const int x = x0 + (dlt & 1), y = y0 + ((dlt >> 1) & 1), z = z0 + (dlt >> 2);
+          if ((unsigned)x < 8u && (unsigned)y < 8u && (unsigned)z < 8u) {
+            m |= 1u << dlt;   // the atomic's return value is this contribution's place in its list (<= 511: 16 bits)
+            rank[j][dlt >> 1] |= (uint32_t)atomicAdd(&cnt[tgt0[j] + (dlt >> 2) * 64 + ((dlt >> 1) & 1) * 8 + (dlt & 1)], 1) << (16 * (dlt & 1));
+          }
+        }
+        inside[j] = m;
       }
       __syncthreads();
-      {  // exclusive scan of 1000 counters: 4 per thread (250 threads), warp scan, then the 8 warp totals
-        const int i0 = 4 * t;
-        int c4[4] = {0, 0, 0, 0};
-        if (i0 < kLines) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) c4[e] = cnt[i0 + e];
-        }
-        const int local = c4[0] + c4[1] + c4[2] + c4[3];
+      {  // exclusive scan of the 512 counters: 2 per thread, warp scan, then the 8 warp totals
+        const int c0 = cnt[2 * t], c1 = cnt[2 * t + 1];
+        const int local = c0 + c1;
         int incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -299,41 +335,44 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
         __syncthreads();
         int basep = incl - local;
         for (int w = 0; w < (t >> 5); ++w) basep += wtot[w];
-        if (i0 < kLines) {
-          start[i0] = basep;
-          start[i0 + 1] = basep + c4[0];
-          start[i0 + 2] = basep + c4[0] + c4[1];
-          start[i0 + 3] = basep + c4[0] + c4[1] + c4[2];
-        }
+        start[2 * t] = basep;
+        start[2 * t + 1] = basep + c0;
       }
       __syncthreads();
-      for (int i = t; i < kLines; i += kThreads) cnt[i] = 0;   // re-used as the fill cursor
-      __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 2; ++j) list[start[myline[j]] + atomicAdd(&cnt[myline[j]], 1)] = (unsigned short)(t + 256 * j);
+      for (int j = 0; j < 2; ++j) {
+        const int vo = adjoint_out_voxel(t, j);
+        const uint32_t off = (uint32_t)((vo >> 6) * kDxD + ((vo >> 3) & 7) * kDxH + (vo & 7) * kDxW);
+#pragma unroll
+        for (int dlt = 0; dlt < 8; ++dlt)
+          if ((inside[j] >> dlt) & 1u) {
+            const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
+            const float w = (dx ? fx[j] : 1.0f - fx[j]) * (dy ? fy[j] : 1.0f - fy[j]) * (dz ? fz[j] : 1.0f - fz[j]);
+            const int v = tgt0[j] + dz * 64 + dy * 8 + dx;
+            ent[start[v] + ((rank[j][dlt >> 1] >> (16 * (dlt & 1))) & 0xffffu)] = make_uint2(off, __float_as_uint(w));
+          }
+      }
       __syncthreads();
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int vi = t + 256 * j;
-        const int z = vi >> 6, y = (vi >> 3) & 7, x = vi & 7;
-        const int lin = ((z + 1) * kHalo + (y + 1)) * kHalo + (x + 1);
-#pragma unroll 1
-        for (int dlt = 0; dlt < 8; ++dlt) {
-          const int dx = dlt & 1, dy = (dlt >> 1) & 1, dz = dlt >> 2;
-          const int cell = lin - (dz * kHalo * kHalo + dy * kHalo + dx);   // corner line of the voxels that tap v at (dx,dy,dz)
-          const int n = cnt[cell], s0 = start[cell];                      // cell >= 0: lin >= 111
-          for (int e = 0; e < n; ++e) {
-            const int vo = list[s0 + e];
-            const float4 tp = bs.taps[vo];
-            const float w = (dx ? tp.y : 1.0f - tp.y) * (dy ? tp.z : 1.0f - tp.z) * (dz ? tp.w : 1.0f - tp.w);
-            const float* src = sm.rotA + (vo >> 6) * kRotD + (vo & 63);
+        const int nn = cnt[vi];
+        const uint2* e = ent + start[vi];
+#pragma unroll 2
+        for (int i = 0; i < nn; ++i) {
+          const uint2 en = e[i];
+          const float w = __uint_as_float(en.y);
+          const float* src = sm.rotA + en.x;
 #pragma unroll
-            for (int c = 0; c < kC; ++c) aV[j][c] = fmaf(w, src[c * kRotC], aV[j][c]);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
+            aV[j][4 * c4] = fmaf(w, x.x, aV[j][4 * c4]); aV[j][4 * c4 + 1] = fmaf(w, x.y, aV[j][4 * c4 + 1]);
+            aV[j][4 * c4 + 2] = fmaf(w, x.z, aV[j][4 * c4 + 2]); aV[j][4 * c4 + 3] = fmaf(w, x.w, aV[j][4 * c4 + 3]);
           }
         }
       }
     }
-    __syncthreads();  // rotA (dX) and taps are re-used by the next hypothesis
+    __syncthreads();  // dX, the work list and the taps are re-used by the next hypothesis
   }
   flush_pair(cur_b);
   // weight gradients: one atomic per accumulator and CTA

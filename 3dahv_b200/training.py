@@ -132,7 +132,7 @@ def verification_scores(vol_src, vol_tgt, R, W1, W2, b2, math: int = MATH_TC, ch
     """Differentiable pred_sim [B,N] (modules/model.py:53-56 / :193).  R [N,3,3] or [B,N,3,3].
     `save_activations` (opt-in; tensor-core forward + fused backward only): the forward keeps conv1's ReLU'd output of
     every (pair, hypothesis) - 4 KB per item in fp16, against the ~420 KB per hypothesis the reference's autograd keeps -
-    and the backward kernel reads it instead of recomputing conv1 in fp32 (a third of its arithmetic; 27.5 -> 22.8 ms
+    and the backward kernel reads it instead of recomputing conv1 in fp32 (a third of its arithmetic; 24.8 -> 20.3 ms
     for the 12 x 9000 step).  The gradient is then that of the function the forward actually evaluated: the ReLU mask
     comes from the fp16-operand conv1, so the ~0.05 % of pre-activations within 3e-4 of zero can sit on the other side
     of ReLU's kink than in an fp32 evaluation.  Gradients that do not pass through the mask (vol_tgt, W2, b2) agree
