@@ -177,7 +177,8 @@ score_tc_ts_kernel(const __grid_constant__ CUtensorMap vol_map, const float* __r
     uint32_t vol_uses = 0;
     // Rotation prefetch, one tile ahead, 9 loads per lane (all lanes of a slot read the same 36 bytes).  A coalesced
     // variant - one load per warp + 9 shuffles - removes 70 LSU wavefronts per hypothesis but was 3-7 % SLOWER:
-    // the shuffles queue behind the gather's LDS.128 in the same pipe and sit on the coordinate critical path.
+    // the shuffles queue behind the gather's LDS.128 in the same pipe and sit on the coordinate critical path.  Three
+    // aligned 16-byte loads of the row's 48-byte window + selects: 13 % (fp32) / 30 % (16-bit) slower still.
     float Rn[9];
     auto fetch_R = [&](int fb, uint32_t fn) {
       const float* Rg = R + (r_per_pair ? ((size_t)fb * N + fn) : (size_t)fn) * 9;
