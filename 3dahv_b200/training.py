@@ -19,6 +19,12 @@ Arithmetic: with the default `math=MATH_TC` the FORWARD scores carry the tensor-
 against the reference's autograd in this mode, 2e-4 with `math=MATH_FP32`, which is 8x slower in the forward only).
 The backward accumulates dV, dT, dW1, dW2, db2 across CTAs with float atomics, so gradients are reproducible to
 rounding, not bit for bit, from run to run.
+
+Fast form (`save_activations=True`, opt-in): the tensor-core forward also keeps conv1's ReLU'd output (fp16, 4 KB per
+hypothesis - `ahv_score_train`), and the backward (`ahv_score_backward_saved`, csrc/ahv_score_bwd_tc.cu) reads it
+instead of recomputing conv1 and runs its five contractions (conv2, dH1, dW2, dA, dW1) on tcgen05: 8.7 ms against
+24.8 ms for the 12 x 9000 step.  Its gradient is that of the function the forward evaluated (the forward's ReLU
+mask), with fp16 operand rounding - see `verification_scores`.
 """
 from __future__ import annotations
 
@@ -66,7 +72,8 @@ def head_torch(vol: torch.Tensor, W1, W2, b2) -> torch.Tensor:
 
 
 class _VerifyScores(torch.autograd.Function):
-    """scores[b,n] of modules/model.py:53-56; forward fused, backward chunked recomputation."""
+    """scores[b,n] of modules/model.py:53-56; forward fused, backward fused (exact fp32 kernel, saved-activation
+    tensor-core kernel) or chunked recomputation."""
 
     @staticmethod
     def forward(ctx, vol_src, vol_tgt, R, W1, W2, b2, math, chunk, fused_backward, save_activations, tc_backward=True):
