@@ -290,7 +290,7 @@ score_bwd_kernel(const float* __restrict__ vol_src, const float* __restrict__ tg
     {
       int* cnt = reinterpret_cast<int*>(bs.dh2);   // [512] contributions per input voxel
       int* start = cnt + kVox;                     // [512] exclusive prefix sum
-      uint2* ent = reinterpret_cast<uint2*>(sm.rotA + kDxFloats);   // [<= 4096] (offset of dX[vo], weight)
+      uint2* ent = reinterpret_cast<uint2*>(smem_raw + offsetof(BwdSmem, f) + offsetof(Fp32Smem, rotA) + sizeof(float) * kDxFloats);   // [<= 4096] (offset of dX[vo], weight), behind dX
       cnt[t] = 0;
       cnt[t + 256] = 0;
       __syncthreads();

@@ -392,7 +392,6 @@ score_bwd_tc_kernel(const float* __restrict__ vol_src, const float* __restrict__
 #endif
   for (int64_t it = lo; it < hi; ++it) {
     const int b = (int)(it / N);
-    const int64_t n = it - (int64_t)b * N;
     if (b != cur_b) {
       if (cur_b >= 0) flush_pair(cur_b);
       __syncthreads();
